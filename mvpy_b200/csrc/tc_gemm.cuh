@@ -1,0 +1,444 @@
+// tc_gemm.cuh -- split-TF32 (3xTF32) tensor-core contraction core for sm_100a.
+//
+//   C[M,N] = sum_k A[m,k] * B[n,k]        (fp32 in, fp32 out, ~fp32 accuracy)
+//
+// Both operands are "separable gathers": element (r,k) = base[roff[r] + koff[k]].
+// That one form covers every contraction on the ridge hot path:
+//   * the implicit lag-expanded design  Xt[(trial,t),(c,w)] = Xpad[trial,c,t+w]
+//     (rows: roff = trial*C*Tp + t, cols: koff = c*Tp + w)  -- the lag expansion
+//     (reference: mvpy/estimators/timedelayed.py:394-431) is never materialised,
+//   * dense row-major matrices (eigenvector / coefficient operands),
+//   * feature masks and training-trial subsets (just shorter offset tables).
+//
+// Hardware mapping: tcgen05.mma kind::tf32, M=128 x N=BN tile per CTA, fp32
+// accumulator in TMEM.  Each fp32 operand value is split in registers into
+// hi = top 19 bits (exact TF32) and lo = x - hi; three MMAs per K-step
+// (hi*hi + hi*lo + lo*hi) recover ~2^-21 relative accuracy.  Operand tiles are
+// staged by the CTA's threads straight into the UMMA canonical K-major
+// no-swizzle layout (8x16B core matrices; LBO padded by 16 B so the stores are
+// bank-conflict free), double buffered, with tcgen05.commit -> mbarrier
+// releasing a buffer back to the loaders.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace mvb {
+
+struct GatherOperand {
+  const float* base;      // device pointer
+  const int64_t* roff;    // [rows] element offsets of the tile rows (M or N index)
+  const int64_t* koff;    // [K]    element offsets along the contraction index
+  int rows;               // number of valid rows
+  int lanes_along_k;      // 0: consecutive rows are contiguous in memory; 1: consecutive k are;
+                          // 2: as 1 and every 4-aligned group koff[4q..4q+3] is contiguous and 16-byte
+                          //    aligned for every row (dense row-major, ld % 4 == 0, K % 4 == 0): 128-bit loads
+};
+
+struct TcGemmParams {
+  GatherOperand A, B;
+  int M, N, K;
+  float* C;               // row-major [M][ldc] (+ z * c_split_stride for split-K partials)
+  int64_t ldc;
+  int64_t c_split_stride;
+  int symmetric;          // 1: A==B; tiles strictly above the diagonal are skipped and mirrored
+  int dbg;                // profiling only: 1 = skip operand staging, 2 = skip MMA issue (results invalid)
+};
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;          // fp32 elements per stage along K
+constexpr int KC = BK / 4;      // 16-byte chunks per stage row
+constexpr int NTHREADS = 256;
+// The tensor core adds into its fp32 accumulator with truncation, which biases long sums (measured:
+// error grows linearly with K).  Every DRAIN stages the TMEM tile is therefore folded into fp32
+// registers with round-to-nearest adds and the next MMA restarts the TMEM accumulator from zero.
+constexpr int DRAIN = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+
+// Bounded wait: a lost arrival traps (reported as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  printf("mvb tc_gemm: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+         blockIdx.z, threadIdx.x);
+  __trap();
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (layout_type 0), version 1.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]),
+        "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]),
+        "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]),
+        "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// fp32 -> (hi, lo) with hi, lo both exactly representable in TF32 (round-to-nearest on the
+// 13 dropped mantissa bits), so hi*hi + hi*lo + lo*hi carries ~2^-22 relative error per product
+// with no truncation bias.
+__device__ __forceinline__ float rn_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = rn_tf32(x);
+  lo = rn_tf32(x - hi);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_LBO = BM * 16 + 16;
+  static constexpr int B_LBO = BN * 16 + 16;
+  static constexpr int A_PLANE = KC * A_LBO;
+  static constexpr int B_PLANE = KC * B_LBO;
+  static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
+  static constexpr int BAR_OFF = 2 * STAGE;
+  static constexpr int ROFF_OFF = BAR_OFF + 64;
+  static constexpr int SMEM_BYTES = ROFF_OFF + (BM + BN) * 8;
+  // instruction descriptor: D=F32, A=B=TF32, K-major both, N=BN, M=128
+  static constexpr uint32_t IDESC =
+      (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+
+// Operand tile loader.  ROWS x BK fp32 values per stage, fetched into registers one stage ahead
+// (so the global/L2 latency overlaps the previous stage's MMAs) and then split + stored into the
+// hi / lo planes.  ALONG_K: a warp walks one tile row with its lanes on consecutive k (coalesced when
+// k is the contiguous direction); otherwise lanes sit on 32 consecutive rows and each thread owns one
+// 16-byte K chunk (coalesced when rows are contiguous, e.g. lags of one feature).
+template <int ROWS, int MODE>
+struct Loader {
+  static constexpr int NV = ROWS * BK / NTHREADS;
+  static constexpr int LBO = ROWS * 16 + 16;
+  float v[NV];
+
+  __device__ __forceinline__ void fetch(const GatherOperand& op, const int64_t* sroff, int row0, int k0, int K) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (MODE == 2) {
+      // lane -> (row-in-group-of-4, 16-byte chunk); 8 lanes read one row's 128 contiguous bytes
+      const int kc = lane & 7, rr = lane >> 3;
+      const int kg = k0 + kc * 4;
+      const bool kok = kg < K;
+      const float* src = op.base + (kok ? op.koff[kg] : 0);
+#pragma unroll
+      for (int i = 0; i < NV / 4; ++i) {
+        const int r = (warp + i * (NTHREADS / 32)) * 4 + rr;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kok && row0 + r < op.rows) t = __ldg(reinterpret_cast<const float4*>(src + sroff[r]));
+        v[i * 4 + 0] = t.x; v[i * 4 + 1] = t.y; v[i * 4 + 2] = t.z; v[i * 4 + 3] = t.w;
+      }
+    } else if (MODE == 1) {
+      const int kg = k0 + lane;
+      const bool kok = kg < K;
+      const float* src = op.base + (kok ? op.koff[kg] : 0);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int r = warp + i * (NTHREADS / 32);
+        v[i] = (kok && row0 + r < op.rows) ? __ldg(src + sroff[r]) : 0.f;
+      }
+    } else {
+      int64_t ko[4];
+      bool kok[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kg = k0 + warp * 4 + j;
+        kok[j] = kg < K;
+        ko[j] = kok[j] ? op.koff[kg] : 0;
+      }
+#pragma unroll
+      for (int rg = 0; rg < ROWS / 32; ++rg) {
+        const int r = rg * 32 + lane;
+        const bool rok = row0 + r < op.rows;
+        const float* src = op.base + sroff[r];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[rg * 4 + j] = (rok && kok[j]) ? __ldg(src + ko[j]) : 0.f;
+      }
+    }
+  }
+
+  __device__ __forceinline__ void store(uint8_t* hi_plane, uint8_t* lo_plane) const {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (MODE == 2) {
+      const int kc = lane & 7, rr = lane >> 3;
+#pragma unroll
+      for (int i = 0; i < NV / 4; ++i) {
+        const int r = (warp + i * (NTHREADS / 32)) * 4 + rr;
+        float4 h, l;
+        split_tf32(v[i * 4 + 0], h.x, l.x);
+        split_tf32(v[i * 4 + 1], h.y, l.y);
+        split_tf32(v[i * 4 + 2], h.z, l.z);
+        split_tf32(v[i * 4 + 3], h.w, l.w);
+        const uint32_t off = kc * LBO + r * 16;
+        *reinterpret_cast<float4*>(hi_plane + off) = h;
+        *reinterpret_cast<float4*>(lo_plane + off) = l;
+      }
+    } else if (MODE == 1) {
+      const uint32_t lane_off = (lane >> 2) * LBO + (lane & 3) * 4;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int r = warp + i * (NTHREADS / 32);
+        float hi, lo;
+        split_tf32(v[i], hi, lo);
+        const uint32_t off = lane_off + (r >> 3) * 128 + (r & 7) * 16;
+        *reinterpret_cast<float*>(hi_plane + off) = hi;
+        *reinterpret_cast<float*>(lo_plane + off) = lo;
+      }
+    } else {
+#pragma unroll
+      for (int rg = 0; rg < ROWS / 32; ++rg) {
+        const int r = rg * 32 + lane;
+        float4 h, l;
+        split_tf32(v[rg * 4 + 0], h.x, l.x);
+        split_tf32(v[rg * 4 + 1], h.y, l.y);
+        split_tf32(v[rg * 4 + 2], h.z, l.z);
+        split_tf32(v[rg * 4 + 3], h.w, l.w);
+        const uint32_t off = warp * LBO + r * 16;
+        *reinterpret_cast<float4*>(hi_plane + off) = h;
+        *reinterpret_cast<float4*>(lo_plane + off) = l;
+      }
+    }
+  }
+};
+
+template <int BN, int A_MODE, int B_MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams p) {
+  using C_ = Cfg<BN>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int m0 = blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  if (p.symmetric && n0 > m0 + BM - 1) return;  // strictly above the diagonal: mirrored by the lower tile
+
+  uint8_t* stage_base[2] = {smem, smem + C_::STAGE};
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::BAR_OFF);  // [0],[1]: buffer free; [2]: all MMAs done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C_::BAR_OFF + 32);
+  int64_t* sroffA = reinterpret_cast<int64_t*>(smem + C_::ROFF_OFF);
+  int64_t* sroffB = sroffA + BM;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init(smem_u32(&bars[2]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"((uint32_t)BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int r = threadIdx.x; r < BM + BN; r += NTHREADS) {
+    if (r < BM) sroffA[r] = (m0 + r < p.A.rows) ? p.A.roff[m0 + r] : 0;
+    else sroffB[r - BM] = (n0 + r - BM < p.B.rows) ? p.B.roff[n0 + r - BM] : 0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // K range of this split
+  const int nkb_total = (p.K + BK - 1) / BK;
+  const int splits = gridDim.z;
+  const int kb_per = (nkb_total + splits - 1) / splits;
+  const int kb_begin = blockIdx.z * kb_per;
+  const int kb_end = min(nkb_total, kb_begin + kb_per);
+  const int nkb = max(0, kb_end - kb_begin);
+
+  Loader<BM, A_MODE> la;
+  Loader<BN, B_MODE> lb;
+  if (nkb > 0) {
+    la.fetch(p.A, sroffA, m0, kb_begin * BK, p.K);
+    lb.fetch(p.B, sroffB, n0, kb_begin * BK, p.K);
+  }
+  constexpr int NACC = BN / 2;                 // columns per thread: warps 0-3 low half, 4-7 high half
+  const int q = warp & 3;                      // TMEM lane quarter this warp may access
+  const int col_half = warp >> 2;
+  float acc[NACC];
+#pragma unroll
+  for (int j = 0; j < NACC; ++j) acc[j] = 0.f;
+  int n_drained = 0;
+
+  for (int it = 0; it < nkb; ++it) {
+    const int s = it & 1;
+    if (it >= 2) mbar_wait(smem_u32(&bars[s]), (uint32_t)(((it >> 1) - 1) & 1));
+    uint8_t* sb = stage_base[s];
+    if (p.dbg != 1) {
+      la.store(sb, sb + C_::A_PLANE);
+      lb.store(sb + 2 * C_::A_PLANE, sb + 2 * C_::A_PLANE + C_::B_PLANE);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const bool chunk_first = (it % DRAIN) == 0;
+    const bool chunk_last = ((it + 1) % DRAIN) == 0 || it == nkb - 1;
+    if (threadIdx.x == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (p.dbg != 2) {
+        const uint32_t a_hi = smem_u32(sb), a_lo = a_hi + C_::A_PLANE;
+        const uint32_t b_hi = a_hi + 2 * C_::A_PLANE, b_lo = b_hi + C_::B_PLANE;
+#pragma unroll
+        for (int j = 0; j < BK / 8; ++j) {
+          const uint64_t da_hi = make_desc(a_hi + 2 * j * C_::A_LBO, C_::A_LBO, 128);
+          const uint64_t da_lo = make_desc(a_lo + 2 * j * C_::A_LBO, C_::A_LBO, 128);
+          const uint64_t db_hi = make_desc(b_hi + 2 * j * C_::B_LBO, C_::B_LBO, 128);
+          const uint64_t db_lo = make_desc(b_lo + 2 * j * C_::B_LBO, C_::B_LBO, 128);
+          mma_tf32(tmem_base, da_lo, db_hi, C_::IDESC, (!chunk_first || j > 0) ? 1u : 0u);
+          mma_tf32(tmem_base, da_hi, db_lo, C_::IDESC, 1u);
+          mma_tf32(tmem_base, da_hi, db_hi, C_::IDESC, 1u);
+        }
+      }
+      mma_commit(smem_u32(&bars[s]));
+      if (chunk_last) mma_commit(smem_u32(&bars[2]));
+    }
+    if (it + 1 < nkb && p.dbg != 1) {  // next stage's global loads fly while this stage's MMAs run
+      la.fetch(p.A, sroffA, m0, (kb_begin + it + 1) * BK, p.K);
+      lb.fetch(p.B, sroffB, n0, (kb_begin + it + 1) * BK, p.K);
+    }
+    if (chunk_last) {
+      mbar_wait(smem_u32(&bars[2]), (uint32_t)(n_drained & 1));
+      ++n_drained;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (p.dbg != 2) {
+#pragma unroll
+        for (int cc = 0; cc < NACC / 32; ++cc) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(col_half * NACC + cc * 32), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += v[j];
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+  }
+
+  // ---- epilogue: register accumulators -> global ------------------------------------------------
+  {
+    const int gm = m0 + q * 32 + lane;
+    float* Cz = p.C + (int64_t)blockIdx.z * p.c_split_stride;
+    if (gm < p.M) {
+#pragma unroll
+      for (int cc = 0; cc < NACC / 32; ++cc) {
+        const int c0 = col_half * NACC + cc * 32;
+        if (n0 + c0 < p.N) {
+          float* crow = Cz + (int64_t)gm * p.ldc + n0 + c0;
+          const int nvalid = min(32, p.N - (n0 + c0));
+          if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(crow + j) =
+                  make_float4(acc[cc * 32 + j], acc[cc * 32 + j + 1], acc[cc * 32 + j + 2], acc[cc * 32 + j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) crow[j] = acc[cc * 32 + j];
+          }
+          if (p.symmetric) {
+            // mirror into tiles that were skipped (row-tile of gn lies strictly above col-tile of gm)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int gn = n0 + c0 + j;
+              if (j < nvalid && gn < p.M && gm < p.N) {
+                const int mt0 = (gn / BM) * BM, nt0 = (gm / BN) * BN;
+                if (nt0 > mt0 + BM - 1) Cz[(int64_t)gn * p.ldc + gm] = acc[cc * 32 + j];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN)
+                 : "memory");
+  }
+}
+
+template <int BN, int AM, int BMODE>
+inline cudaError_t launch_variant(const TcGemmParams& p, int k_splits, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, AM, BMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg<BN>::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, k_splits);
+  tc_gemm_kernel<BN, AM, BMODE><<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int BN, int AM>
+inline cudaError_t launch_b(const TcGemmParams& p, int k_splits, cudaStream_t st) {
+  switch (p.B.lanes_along_k) {
+    case 0: return launch_variant<BN, AM, 0>(p, k_splits, st);
+    case 1: return launch_variant<BN, AM, 1>(p, k_splits, st);
+    default: return launch_variant<BN, AM, 2>(p, k_splits, st);
+  }
+}
+
+template <int BN>
+inline cudaError_t launch_a(const TcGemmParams& p, int k_splits, cudaStream_t st) {
+  switch (p.A.lanes_along_k) {
+    case 0: return launch_b<BN, 0>(p, k_splits, st);
+    case 1: return launch_b<BN, 1>(p, k_splits, st);
+    default: return launch_b<BN, 2>(p, k_splits, st);
+  }
+}
+
+}  // namespace tc
+
+// Launch helper.  bn = 256 for wide outputs, 128 otherwise; k_splits partial sums go to
+// C + z * c_split_stride (caller reduces them).
+inline cudaError_t tc_gemm_launch(const TcGemmParams& p, int k_splits, int bn, cudaStream_t st) {
+  if (p.M <= 0 || p.N <= 0) return cudaSuccess;
+  if (bn == 256) return tc::launch_a<256>(p, k_splits, st);
+  return tc::launch_a<128>(p, k_splits, st);
+}
+
+}  // namespace mvb

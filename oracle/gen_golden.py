@@ -1,0 +1,263 @@
+"""Generate the golden fixtures in tests/golden/ by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):   python oracle/gen_golden.py
+The GPU box has no /root/reference; tests there read the committed .npz files.  Everything is
+seeded; inputs are stored next to the outputs so neither side has to regenerate them.
+
+Fixtures (all produced through the reference's public classes/functions):
+  ridgecv.npz      _RidgeCV_torch on the reference's own test sizes (tests/estimators/test_ridgecv.py:
+                   10x20 "gram", 20x10 "svd"; 1/3 targets; +-intercept; per-target alphas), fp64,
+                   plus fp32 cases with more rows.
+  delay.npz        _delay_matrices known answer (arange(24).reshape(2,2,6), lags -3..2) + a random case.
+  scaler.npz       _Scaler_torch statistics/transforms for several dims.
+  kfold.npz        KFold index listings (plain + shuffled with seeds).
+  metrics.npz      math.r2 / math.pearsonr incl. zero-variance rows and the y_b baseline.
+  trf_small.npz    make_meeg_continuous(fs=50, n_trials=40, n_channels=8, n_features=4) seed 0:
+                   cross_val_score / hierarchical_score / shapley_score through Scaler+TimeDelayed.
+  decoder.npz      per-slice RidgeCV(alpha_per_target) + Haufe pattern (RidgeDecoder maths), Sliding.
+  encoder.npz      RidgeEncoder 2-D and 3-D (expanded design).
+  cfg1_summary.npz config 1 (README flow, fs=200): per-fold alphas, mean scores, strided score samples.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+warnings.filterwarnings('ignore')
+sys.path.insert(0, '/root/reference')
+import mvpy as ref  # noqa: E402
+from mvpy.estimators.ridgecv import _RidgeCV_torch  # noqa: E402
+from mvpy.estimators.timedelayed import _TimeDelayed_torch  # noqa: E402
+from sklearn.pipeline import make_pipeline  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden')
+os.makedirs(OUT, exist_ok=True)
+torch.set_num_threads(8)
+
+
+def npy(t):
+    if isinstance(t, torch.Tensor):
+        return t.detach().cpu().numpy()
+    return np.asarray(t)
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **{k: npy(v) for k, v in arrays.items()})
+    print(f'{name}: {os.path.getsize(path) / 1024:.1f} KiB, {len(arrays)} arrays')
+
+
+# ---------------------------------------------------------------------------------------- ridgecv
+def regression_problem(n_samples, n_features, n_targets, snr=10.0):
+    """the reference's own fixture (tests/conftest.py:56-85), default_rng(42)."""
+    rng = np.random.default_rng(42)
+    X = rng.normal(size=(n_samples, n_features))
+    B = rng.normal(size=(n_features, n_targets))
+    y = X @ B
+    y = y + rng.normal(size=y.shape) * (y.std() / snr)
+    return X, y
+
+
+def gen_ridgecv():
+    out = {}
+    alphas10 = np.logspace(-5, 5, 10)
+    cid = 0
+    for (n, p) in [(10, 20), (20, 10), (60, 7), (25, 25)]:
+        for f in (1, 3):
+            for icpt in (True, False):
+                for per_target in (False, True):
+                    X, y = regression_problem(n, p, f)
+                    m = _RidgeCV_torch(alphas=torch.from_numpy(alphas10), fit_intercept=icpt,
+                                       alpha_per_target=per_target).fit(torch.from_numpy(X), torch.from_numpy(y))
+                    pred = m.predict(torch.from_numpy(X))
+                    key = f'c{cid}'
+                    out[key + '_X'], out[key + '_y'] = X, y
+                    out[key + '_cfg'] = np.array([n, p, f, int(icpt), int(per_target)])
+                    out[key + '_coef'], out[key + '_alpha'] = m.coef_, m.alpha_
+                    out[key + '_intercept'] = m.intercept_ if icpt else np.zeros((1, f))
+                    out[key + '_pred'] = pred
+                    cid += 1
+    out['alphas'] = alphas10
+    out['n_cases'] = np.array(cid)
+    # fp32, tall problems (the regime of the TRF path)
+    g = torch.Generator().manual_seed(7)
+    X = torch.randn(400, 24, generator=g)
+    B = torch.randn(24, 5, generator=g)
+    y = X @ B + 3.0 * torch.randn(400, 5, generator=g) + 0.7
+    X = X + 0.3
+    al = torch.logspace(-3, 4, 12)
+    for per_target in (False, True):
+        m = _RidgeCV_torch(alphas=al, alpha_per_target=per_target).fit(X, y)
+        tag = 'f32pt' if per_target else 'f32'
+        out[tag + '_coef'], out[tag + '_alpha'], out[tag + '_intercept'] = m.coef_, m.alpha_, m.intercept_
+    out['f32_X'], out['f32_y'], out['f32_alphas'] = X, y, al
+    save('ridgecv.npz', **out)
+
+
+# ------------------------------------------------------------------------------------------ delay
+def gen_delay():
+    td = _TimeDelayed_torch(-0.03, 0.02, 100, alphas=torch.tensor([1.0]))
+    X = torch.arange(24).reshape(2, 2, 6).float()
+    Xt = td._delay_matrices(X)
+    g = torch.Generator().manual_seed(3)
+    Xr, yr = torch.randn(3, 2, 9, generator=g), torch.randn(3, 4, 9, generator=g)
+    td2 = _TimeDelayed_torch(0.01, 0.03, 100, alphas=torch.tensor([1.0]))
+    Xt2, yt2 = td2._delay_matrices(Xr, yr)
+    save('delay.npz', X=X, Xt=Xt, window=td.window, Xr=Xr, yr=yr, Xt2=Xt2, yt2=yt2, window2=td2.window,
+         window_cfg1=_TimeDelayed_torch(-1.0, 0.0, 200, alphas=torch.tensor([1.0])).window)
+
+
+# ----------------------------------------------------------------------------------------- scaler
+def gen_scaler():
+    g = torch.Generator().manual_seed(11)
+    X = torch.randn(12, 5, 7, generator=g) * 3 + 2
+    X[:, 2, 3] = 4.0  # zero-variance cell -> scale forced to 1
+    out = dict(X=X)
+    Xn = torch.randn(4, 5, 7, generator=g)
+    out['Xnew'] = Xn
+    for tag, dims in [('d0', None), ('d01', (0, 1)), ('d2', (2,)), ('d02', (0, 2))]:
+        sc = ref.preprocessing.Scaler(dims=dims).to_torch().fit(X)
+        out[tag + '_mean'], out[tag + '_var'], out[tag + '_scale'] = sc.mean_, sc.var_, sc.scale_
+        out[tag + '_tx'] = sc.transform(X)
+        if tag == 'd0':
+            out[tag + '_tnew'] = sc.transform(Xn)
+            out[tag + '_inv'] = sc.inverse_transform(sc.transform(Xn))
+    sc = ref.preprocessing.Scaler(with_std=False).to_torch().fit(X)
+    out['nostd_tx'] = sc.transform(X)
+    sc = ref.preprocessing.Scaler(with_mean=False).to_torch().fit(X)
+    out['nomean_tx'] = sc.transform(X)
+    save('scaler.npz', **out)
+
+
+# ------------------------------------------------------------------------------------------ kfold
+def gen_kfold():
+    out = {}
+    for n, k in [(10, 5), (11, 3), (120, 5), (7, 7)]:
+        X = torch.zeros(n, 2)
+        for i, (tr, te) in enumerate(ref.crossvalidation.KFold(n_splits=k).split(X)):
+            out[f'n{n}k{k}_tr{i}'], out[f'n{n}k{k}_te{i}'] = tr, te
+    for n, k, seed in [(20, 4, 0), (23, 5, 123)]:
+        X = torch.zeros(n, 2)
+        for i, (tr, te) in enumerate(ref.crossvalidation.KFold(n_splits=k, shuffle=True, random_state=seed).split(X)):
+            out[f'n{n}k{k}s{seed}_tr{i}'], out[f'n{n}k{k}s{seed}_te{i}'] = tr, te
+    save('kfold.npz', **out)
+
+
+# ---------------------------------------------------------------------------------------- metrics
+def gen_metrics():
+    g = torch.Generator().manual_seed(5)
+    y = torch.randn(6, 9, 24, generator=g)
+    yh = y + 0.5 * torch.randn(6, 9, 24, generator=g)
+    y[0, 0] = 1.5  # zero variance row: r2 -> 0 (guard), pearson -> nan
+    yb = torch.randn(6, 9, 1, generator=g) * 0.1
+    save('metrics.npz', y=y, yh=yh, yb=yb, r2=ref.math.r2(y, yh), r2_b=ref.math.r2(y, yh, yb),
+         pearsonr=ref.math.pearsonr(y, yh))
+
+
+# -------------------------------------------------------------------------------------- trf small
+def gen_trf_small():
+    torch.manual_seed(0)
+    X, y = ref.dataset.make_meeg_continuous(fs=50, n_trials=40, n_channels=8, n_features=4)
+    alphas = torch.logspace(-5, 5, 20)
+
+    def pipe():
+        return make_pipeline(ref.preprocessing.Scaler().to_torch(),
+                             ref.estimators.TimeDelayed(-0.4, 0.0, 50, alphas=alphas))
+
+    out = dict(X=X, y=y, alphas=alphas)
+    val, sc = ref.crossvalidation.cross_val_score(pipe(), X, y, cv=5)
+    out['cv_score'] = sc
+    out['cv_alpha'] = torch.stack([m[-1].estimator.alpha_ for m in val.model_])
+    out['cv_coef'] = torch.stack([m[-1].coef_ for m in val.model_])
+    out['cv_intercept'] = torch.stack([m[-1].intercept_ for m in val.model_])
+    out['cv_scaler_mean'] = torch.stack([m[0].mean_ for m in val.model_])
+    out['cv_scaler_scale'] = torch.stack([m[0].scale_ for m in val.model_])
+    # two metrics at once (dict output path)
+    _, sc2 = ref.crossvalidation.cross_val_score(pipe(), X, y, cv=5, metric=(ref.metrics.r2, ref.metrics.pearsonr))
+    out['cv2_r2'], out['cv2_pearsonr'] = sc2['r2'], sc2['pearsonr']
+    # bare estimator without the scaler, single fit: coefficients, patterns, predictions
+    td = ref.estimators.TimeDelayed(-0.4, 0.0, 50, alphas=alphas, patterns=True).fit(X[:32], y[:32])
+    out['fit_coef'], out['fit_pattern'], out['fit_intercept'] = td.coef_, td.pattern_, td.intercept_
+    out['fit_alpha'] = td.estimator.alpha_
+    out['fit_pred'] = td.predict(X[32:])
+    td2 = ref.estimators.TimeDelayed(-0.1, 0.06, 50, alphas=alphas, alpha_per_target=True, fit_intercept=False).fit(X[:32], y[:32])
+    out['fit2_coef'], out['fit2_alpha'], out['fit2_pred'] = td2.coef_, td2.estimator.alpha_, td2.predict(X[32:])
+    # hierarchical: identity groups (15 sets) and explicit groups (7 sets)
+    h, hs = ref.model_selection.hierarchical_score(pipe(), X, y, cv=5)
+    out['hier_score'], out['hier_mask'] = hs, torch.stack(list(h.mask_))
+    out['hier_sets'] = np.array([list(s) + [-1] * (4 - len(s)) for s in h.set_])
+    groups = [[1, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]]
+    h2, hs2 = ref.model_selection.hierarchical_score(pipe(), X, y, groups=groups, cv=5)
+    out['hier2_score'], out['hier2_mask'], out['groups'] = hs2, torch.stack(list(h2.mask_)), np.array(groups)
+    out['hier2_sets'] = np.array([list(s) + [-1] * (3 - len(s)) for s in h2.set_])
+    torch.manual_seed(1)
+    s, ss = ref.model_selection.shapley_score(pipe(), X, y, groups=groups, cv=5, n_permutations=3)
+    out['shap_score'], out['shap_order'] = ss, s.order_
+    save('trf_small.npz', **out)
+
+
+# ---------------------------------------------------------------------------------------- decoder
+def gen_decoder():
+    g = torch.Generator().manual_seed(21)
+    N, C, T, F = 80, 12, 6, 3
+    X = torch.randn(N, C, T, generator=g)
+    B = torch.randn(C, F, generator=g)
+    y = torch.einsum('nct,cf->nft', X, B) * torch.hann_window(T + 2)[1:-1] + 2.0 * torch.randn(N, F, T, generator=g)
+    alphas = torch.logspace(-5, 5, 20)
+    out = dict(X=X, y=y, alphas=alphas)
+    coefs, alps, icpts, pats, preds = [], [], [], [], []
+    for t in range(T):
+        Xt, yt = X[..., t], y[..., t]
+        m = _RidgeCV_torch(alphas=alphas, fit_intercept=True, alpha_per_target=True).fit(Xt, yt)
+        # the pattern formula of ridgedecoder.py:267-285 evaluated with reference torch ops
+        Xc, yc = Xt - Xt.mean(0, keepdim=True), yt - yt.mean(0, keepdim=True)
+        pat = torch.cov(Xc.T).mm(m.coef_.T).mm(torch.linalg.pinv(torch.cov(yc.T)))
+        coefs.append(m.coef_); alps.append(m.alpha_); icpts.append(m.intercept_); pats.append(pat)
+        preds.append(m.predict(Xt))
+    out.update(coef=torch.stack(coefs), alpha=torch.stack(alps), intercept=torch.stack(icpts),
+               pattern=torch.stack(pats), pred=torch.stack(preds, -1))
+    # Sliding over the last dim with the (working) RidgeCV estimator, through the reference class
+    sl = ref.estimators.Sliding(ref.estimators.RidgeCV(alphas=alphas, alpha_per_target=True), dims=-1).fit(X, y)
+    out['sliding_coef'] = sl.collect('coef_')
+    out['sliding_pred'] = sl.predict(X)
+    # single target column
+    m1 = _RidgeCV_torch(alphas=alphas, alpha_per_target=True).fit(X[..., 0], y[:, 0, 0])
+    out['single_coef'], out['single_alpha'] = m1.coef_, m1.alpha_
+    save('decoder.npz', **out)
+
+
+# ---------------------------------------------------------------------------------------- encoder
+def gen_encoder():
+    g = torch.Generator().manual_seed(31)
+    N, F, T, D = 30, 4, 5, 3
+    X = torch.randn(N, F, T, generator=g)
+    y = torch.randn(N, D, T, generator=g) + torch.einsum('nft,fd->ndt', X, torch.randn(F, D, generator=g))
+    alphas = torch.logspace(-3, 3, 9)
+    enc = ref.estimators.RidgeEncoder(alphas=alphas).fit(X, y)
+    out = dict(X=X, y=y, alphas=alphas, coef3=enc.coef_, intercept3=enc.intercept_, alpha3=enc.estimator.alpha_,
+               pred3=enc.predict(X))
+    enc2 = ref.estimators.RidgeEncoder(alphas=alphas).fit(X[..., 0], y[..., 0])
+    out.update(coef2=enc2.coef_, intercept2=enc2.intercept_, alpha2=enc2.estimator.alpha_, pred2=enc2.predict(X[..., 0]))
+    save('encoder.npz', **out)
+
+
+# ------------------------------------------------------------------------------------------- cfg1
+def gen_cfg1():
+    torch.manual_seed(0)
+    X, y = ref.dataset.make_meeg_continuous(fs=200)
+    alphas = torch.logspace(-5, 5, 20)
+    pipe = make_pipeline(ref.preprocessing.Scaler().to_torch(), ref.estimators.TimeDelayed(-1.0, 0.0, 200, alphas=alphas))
+    val, sc = ref.crossvalidation.cross_val_score(pipe, X, y, cv=5)
+    coef = torch.stack([m[-1].coef_ for m in val.model_])
+    save('cfg1_summary.npz', alpha=torch.stack([m[-1].estimator.alpha_ for m in val.model_]),
+         score_mean=sc.mean(), score_fold_mean=sc.mean((1, 2)), score_sub=sc[:, ::7, ::13],
+         coef_sub=coef[:, ::7, :, ::5], intercept=torch.stack([m[-1].intercept_ for m in val.model_]),
+         x_checksum=X.double().sum(), y_checksum=y.double().sum())
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['ridgecv', 'delay', 'scaler', 'kfold', 'metrics', 'trf_small', 'decoder', 'encoder', 'cfg1']
+    for w in which:
+        globals()['gen_' + w]()
