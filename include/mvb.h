@@ -1,0 +1,127 @@
+/* mvb.h -- C-ABI of libmvb.so: B200 (sm_100a) kernels for MVPy's cross-validated ridge hot path.
+ *
+ * The reference (FabulousFabs/MVPy) is pure Python and has no FFI; the boundary it offers is its
+ * estimator API.  This header is the boundary the reference-side classes bind instead of calling
+ * torch.linalg / ATen (see INTEGRATION.md for the ctypes stubs).  Each entry point names the
+ * reference code it replaces (file:line under mvpy/).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch tensors), row-major, contiguous
+ *     unless strides are given; nothing is allocated or freed inside the library;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work, they never synchronise;
+ *   - dtype: MVB_F32 or MVB_F64 (fp32 uses the tcgen05 split-TF32 contraction core, fp64 the
+ *     CUDA-core path that the reference's fp64 test-suite needs);
+ *   - return value: 0 = ok, <0 = error (MVB_E_*), message via mvb_last_error() (thread-local);
+ *   - scratch memory comes from the caller: ask the matching *_workspace_bytes() first.
+ */
+#ifndef MVB_H_
+#define MVB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVB_F32 0
+#define MVB_F64 1
+
+#define MVB_OK 0
+#define MVB_E_ARG (-1)       /* bad argument                          */
+#define MVB_E_WORKSPACE (-2) /* workspace too small                   */
+#define MVB_E_CUDA (-3)      /* CUDA runtime error                    */
+#define MVB_E_UNSUPPORTED (-4)
+
+int mvb_version(void);
+const char* mvb_last_error(void);
+/* number of kernels launched by this library in the calling process (all threads) */
+int64_t mvb_launch_count(void);
+
+/* ---- Scaler ------------------------------------------------------------------------------------
+ * replaces _Scaler_torch.fit / transform / inverse_transform  (preprocessing/scaler.py:301-428).
+ * X is viewed as [R][K]: R = product of the reduced dims (moved first), K = kept elements.
+ * mean/var/scale have K entries; var is unbiased; scale = sqrt(var), 0 or NaN -> 1.            */
+int mvb_scaler_fit(const void* X, int64_t R, int64_t K, int dtype, void* mean, void* var, void* scale, void* stream);
+int mvb_scaler_apply(const void* X, int64_t R, int64_t K, int dtype, const void* mean, const void* scale,
+                     int with_mean, int with_std, int inverse, void* out, void* stream);
+
+/* ---- layout helpers ----------------------------------------------------------------------------
+ * mvb_trf_pad: (N,C,T) -> (N,C,T+left+right) with replicated edge samples, i.e. the clamped lag
+ * indexing of _TimeDelayed_torch._delay_matrices (estimators/timedelayed.py:415-417) turned into
+ * a pure shift.  mvb_transpose: [R][C] -> [C][R] (dense 2-D designs become "series" rows).      */
+int mvb_trf_pad(const void* X, int N, int C, int T, int left, int right, int dtype, void* Xp, void* stream);
+int mvb_transpose(const void* X, int64_t R, int64_t C, int dtype, void* out, void* stream);
+
+/* ---- the implicit lag-expanded design -----------------------------------------------------------
+ * Column j = (f, w) of row i = (s, t) is  xp[trial(s)*trial_stride + feat(f)*feat_stride + t + w]:
+ * X_t of timedelayed.py:394-423 without ever materialising it.  n_lag = 1 describes a dense 2-D
+ * design stored column-major ("series" layout).  trial_idx / feat_idx select training trials and
+ * predictor subsets (NULL = all) -- what X[train] and index_select(X, dim, mask)
+ * (crossvalidation/validator.py:92, model_selection/hierarchical.py:177-182) do by copying.     */
+typedef struct {
+  const void* xp;
+  int64_t trial_stride, feat_stride;
+  int n_time, n_lag;
+  const int32_t* trial_idx; int n_trials;
+  const int32_t* feat_idx;  int n_feat;
+  int dtype;
+} mvb_design;
+
+/* targets: y[(trial*n_targets + f)*n_time + t]  (the (N,F,T) layout), same trial subset */
+
+/* ---- generic separable-gather contraction  C[M,N] = sum_k A(m,k) * B(n,k) ------------------------
+ * element (r,k) of an operand = base[roff[r] + koff[k]].  contig: 0 rows contiguous, 1 k contiguous,
+ * 2 k contiguous + 16-byte aligned groups of 4 (dense row-major).  fp32 -> tcgen05 split-TF32.      */
+typedef struct {
+  const void* base; const int64_t* roff; const int64_t* koff; int rows; int contig;
+} mvb_operand;
+size_t mvb_contract_workspace_bytes(int M, int N, int K, int dtype);
+int mvb_contract(const mvb_operand* A, const mvb_operand* B, int M, int N, int K, int dtype, void* C, int64_t ldc,
+                 int symmetric, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- sufficient statistics of one training set ---------------------------------------------------
+ * replaces the lag expansion + centring + X^T X / X^T y work of _RidgeCV_torch
+ * (estimators/ridgecv.py:81-88,123 and the products inside :218-224): centred Gram G (p x p),
+ * centred cross-moment XtY (p x F), column means mu (p), target means ybar (F).
+ * fit_intercept = 0 leaves everything uncentred and returns zeros in mu / ybar.                  */
+size_t mvb_trf_stats_workspace_bytes(const mvb_design* d, int n_targets);
+int mvb_trf_stats(const mvb_design* d, const void* y, int n_targets, int fit_intercept,
+                  void* G, void* XtY, void* mu, void* ybar, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- batched symmetric eigensolver ---------------------------------------------------------------
+ * replaces torch.linalg.svd / eigh in ridgecv.py:144,218.  A: batch x p x p symmetric (destroyed),
+ * Vt: batch x p x p, row k = k-th eigenvector; lam: batch x p (unsorted, >= 0 enforced).        */
+size_t mvb_eigh_workspace_bytes(int batch, int p, int dtype);
+int mvb_eigh(void* A, void* Vt, void* lam, int batch, int p, int dtype, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- exact leave-one-out ridge over an alpha grid --------------------------------------------------
+ * replaces _RidgeCV_torch.fit after the decomposition (ridgecv.py:223-301): per-row leverages,
+ * LOO residuals, loss (A x F), alpha selection (first minimum; shared or per target), coefficients
+ * coef (F x p), intercept (F).  G, XtY, mu, ybar come from mvb_trf_stats (G is destroyed).
+ * alpha_out has 1 (shared) or F entries, best likewise (int32 grid index).  loss may be NULL.   */
+size_t mvb_ridge_solve_workspace_bytes(const mvb_design* d, int n_targets, int n_alphas);
+int mvb_ridge_solve(const mvb_design* d, const void* y, int n_targets, void* G, const void* XtY, const void* mu,
+                    const void* ybar, const void* alphas, int n_alphas, int fit_intercept, int alpha_per_target,
+                    void* coef, void* intercept, void* alpha_out, int32_t* best, void* loss,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* ---- prediction -------------------------------------------------------------------------------------
+ * replaces _TimeDelayed_torch.predict / _RidgeCV_torch.predict (timedelayed.py:522-533,
+ * ridgecv.py:323): yhat[(s*F + f)*T + t] = sum_j X_t[(s,t), j] coef[f, j] + intercept[f].      */
+size_t mvb_trf_predict_workspace_bytes(const mvb_design* d, int n_targets);
+int mvb_trf_predict(const mvb_design* d, const void* coef, const void* intercept, int n_targets, void* yhat,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* ---- scoring ----------------------------------------------------------------------------------------
+ * replaces math.r2 / math.pearsonr after metrics.score's reduce_ (math/r2.py:80-100,
+ * math/pearsonr.py:55-56, metrics/score.py:17-46).  y, yhat viewed as [R][K] (R = reduced samples,
+ * e.g. test trials; K = F*T kept cells); y_b has K entries or is NULL (mean of y).  Either output
+ * may be NULL.  r2 is 0 where the denominator is <= 0; pearson is NaN on zero variance.          */
+int mvb_score(const void* y, const void* yhat, const void* y_b, int64_t R, int64_t K, int dtype,
+              void* r2_out, void* pearson_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVB_H_ */

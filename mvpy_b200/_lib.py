@@ -1,0 +1,274 @@
+"""ctypes binding of libmvb.so (include/mvb.h) and thin tensor-level wrappers.
+
+This is the only place that touches the C-ABI.  Everything here enqueues CUDA work on torch's
+current stream; torch is used for device memory (outputs, workspaces) and streams only.
+There is no CPU implementation: importing works without a GPU (so host-side logic can be tested),
+but any compute call raises if the library or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_int, c_int32, c_int64, c_size_t, c_void_p
+from typing import Optional, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmvb.so')
+
+F32, F64 = 0, 1
+
+
+class MvbError(RuntimeError):
+    pass
+
+
+class mvb_design(ctypes.Structure):
+    _fields_ = [('xp', c_void_p), ('trial_stride', c_int64), ('feat_stride', c_int64), ('n_time', c_int),
+                ('n_lag', c_int), ('trial_idx', c_void_p), ('n_trials', c_int), ('feat_idx', c_void_p),
+                ('n_feat', c_int), ('dtype', c_int)]
+
+
+class mvb_operand(ctypes.Structure):
+    _fields_ = [('base', c_void_p), ('roff', c_void_p), ('koff', c_void_p), ('rows', c_int), ('contig', c_int)]
+
+
+# every symbol declared in include/mvb.h (tests/test_abi.py checks the list against the header)
+_SIGNATURES = {
+    'mvb_version': (c_int, []),
+    'mvb_last_error': (c_char_p, []),
+    'mvb_launch_count': (c_int64, []),
+    'mvb_scaler_fit': (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'mvb_scaler_apply': (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'mvb_trf_pad': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'mvb_transpose': (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    'mvb_contract_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'mvb_contract': (c_int, [POINTER(mvb_operand), POINTER(mvb_operand), c_int, c_int, c_int, c_int, c_void_p, c_int64,
+                             c_int, c_void_p, c_size_t, c_void_p]),
+    'mvb_trf_stats_workspace_bytes': (c_size_t, [POINTER(mvb_design), c_int]),
+    'mvb_trf_stats': (c_int, [POINTER(mvb_design), c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_size_t, c_void_p]),
+    'mvb_eigh_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'mvb_eigh': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    'mvb_ridge_solve_workspace_bytes': (c_size_t, [POINTER(mvb_design), c_int, c_int]),
+    'mvb_ridge_solve': (c_int, [POINTER(mvb_design), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_size_t, c_void_p]),
+    'mvb_trf_predict_workspace_bytes': (c_size_t, [POINTER(mvb_design), c_int]),
+    'mvb_trf_predict': (c_int, [POINTER(mvb_design), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'mvb_score': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load libmvb.so; loud failure if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MvbError(f'{LIB_PATH} not found: build it with `python -m mvpy_b200.build` '
+                       '(nvcc, sm_100a).  mvpy_b200 has no CPU or PyTorch fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise MvbError(f'{what} failed (rc={rc}): {load().mvb_last_error().decode()}')
+
+
+def launch_count() -> int:
+    return int(load().mvb_launch_count())
+
+
+# ------------------------------------------------------------------------------------------- helpers
+def compute_device() -> torch.device:
+    """CUDA device used for host (CPU) inputs."""
+    if not torch.cuda.is_available():
+        raise MvbError('mvpy_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def to_device(x: torch.Tensor) -> torch.Tensor:
+    """Move a host tensor to the compute device (non-blocking from pinned memory); CUDA tensors pass."""
+    if x.is_cuda:
+        return x
+    return x.to(compute_device(), non_blocking=True)
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float64:
+        return F64
+    raise TypeError(f'mvpy_b200 kernels support float32 / float64 tensors, got {t.dtype}')
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _stream(t: torch.Tensor):
+    return c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+class Design:
+    """Python mirror of ``mvb_design``: the implicit lag-expanded design over a padded stimulus array.
+
+    xp: (n_all_trials, C, Tp) contiguous CUDA tensor (edge-replicated by ``trf_pad``) or, for dense 2-D
+    designs, a (1, p, n) "series" array with n_lag = 1.
+    """
+
+    def __init__(self, xp: torch.Tensor, n_time: int, n_lag: int, trial_idx: Optional[torch.Tensor] = None,
+                 feat_idx: Optional[torch.Tensor] = None):
+        assert xp.is_cuda and xp.is_contiguous() and xp.ndim == 3
+        self.xp = xp
+        self.n_time, self.n_lag = int(n_time), int(n_lag)
+        self.trial_idx = None if trial_idx is None else trial_idx.to(device=xp.device, dtype=torch.int32).contiguous()
+        self.feat_idx = None if feat_idx is None else feat_idx.to(device=xp.device, dtype=torch.int32).contiguous()
+        self.n_trials = xp.shape[0] if self.trial_idx is None else int(self.trial_idx.numel())
+        self.n_feat = xp.shape[1] if self.feat_idx is None else int(self.feat_idx.numel())
+
+    @property
+    def n_rows(self) -> int:
+        return self.n_trials * self.n_time
+
+    @property
+    def n_cols(self) -> int:
+        return self.n_feat * self.n_lag
+
+    def subset(self, trial_idx=None, feat_idx=None) -> 'Design':
+        return Design(self.xp, self.n_time, self.n_lag, trial_idx if trial_idx is not None else self.trial_idx,
+                      feat_idx if feat_idx is not None else self.feat_idx)
+
+    def c_struct(self) -> mvb_design:
+        xp = self.xp
+        return mvb_design(xp.data_ptr(), xp.stride(0), xp.stride(1), self.n_time, self.n_lag,
+                          None if self.trial_idx is None else self.trial_idx.data_ptr(), self.n_trials,
+                          None if self.feat_idx is None else self.feat_idx.data_ptr(), self.n_feat, dtype_code(xp))
+
+
+# --------------------------------------------------------------------------------------------- ops
+def scaler_fit(X2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """X2: (R, K) contiguous -> mean, var, scale (K,)."""
+    R, K = X2.shape
+    mean, var, scale = (torch.empty(K, dtype=X2.dtype, device=X2.device) for _ in range(3))
+    check(load().mvb_scaler_fit(_ptr(X2), R, K, dtype_code(X2), _ptr(mean), _ptr(var), _ptr(scale), _stream(X2)), 'mvb_scaler_fit')
+    return mean, var, scale
+
+
+def scaler_apply(X2: torch.Tensor, mean, scale, with_mean: bool, with_std: bool, inverse: bool = False) -> torch.Tensor:
+    R, K = X2.shape
+    out = torch.empty_like(X2)
+    check(load().mvb_scaler_apply(_ptr(X2), R, K, dtype_code(X2), _ptr(mean), _ptr(scale), int(with_mean), int(with_std),
+                                  int(inverse), _ptr(out), _stream(X2)), 'mvb_scaler_apply')
+    return out
+
+
+def trf_pad(X: torch.Tensor, left: int, right: int) -> torch.Tensor:
+    N, C, T = X.shape
+    out = torch.empty((N, C, T + left + right), dtype=X.dtype, device=X.device)
+    check(load().mvb_trf_pad(_ptr(X), N, C, T, left, right, dtype_code(X), _ptr(out), _stream(X)), 'mvb_trf_pad')
+    return out
+
+
+def transpose(X2: torch.Tensor) -> torch.Tensor:
+    R, C = X2.shape
+    out = torch.empty((C, R), dtype=X2.dtype, device=X2.device)
+    check(load().mvb_transpose(_ptr(X2), R, C, dtype_code(X2), _ptr(out), _stream(X2)), 'mvb_transpose')
+    return out
+
+
+def trf_stats(design: Design, y: torch.Tensor, fit_intercept: bool = True):
+    """Centred Gram / cross-moment / means of the training rows of ``design`` against y (N, F, T)."""
+    F = y.shape[1]
+    p = design.n_cols
+    dev, dt = design.xp.device, design.xp.dtype
+    G = torch.empty((p, p), dtype=dt, device=dev)
+    XtY = torch.empty((p, F), dtype=dt, device=dev)
+    mu = torch.empty(p, dtype=dt, device=dev)
+    ybar = torch.empty(F, dtype=dt, device=dev)
+    cs = design.c_struct()
+    lib = load()
+    ws = _workspace(lib.mvb_trf_stats_workspace_bytes(ctypes.byref(cs), F), dev)
+    check(lib.mvb_trf_stats(ctypes.byref(cs), _ptr(y), F, int(fit_intercept), _ptr(G), _ptr(XtY), _ptr(mu), _ptr(ybar),
+                            _ptr(ws), ws.numel(), _stream(y)), 'mvb_trf_stats')
+    return G, XtY, mu, ybar
+
+
+def ridge_solve(design: Design, y: torch.Tensor, G, XtY, mu, ybar, alphas: torch.Tensor, fit_intercept: bool,
+                alpha_per_target: bool, want_loss: bool = False):
+    """LOO sweep from sufficient statistics (G is overwritten).  Returns coef (F,p), intercept (F,),
+    alpha (1 or F), best (int32), loss (A,F) or None."""
+    F = y.shape[1]
+    p, A = design.n_cols, int(alphas.numel())
+    dev, dt = design.xp.device, design.xp.dtype
+    coef = torch.empty((F, p), dtype=dt, device=dev)
+    icpt = torch.empty(F, dtype=dt, device=dev)
+    nb = F if alpha_per_target else 1
+    alpha_out = torch.empty(nb, dtype=dt, device=dev)
+    best = torch.empty(nb, dtype=torch.int32, device=dev)
+    loss = torch.empty((A, F), dtype=dt, device=dev) if want_loss else None
+    cs = design.c_struct()
+    lib = load()
+    ws = _workspace(lib.mvb_ridge_solve_workspace_bytes(ctypes.byref(cs), F, A), dev)
+    check(lib.mvb_ridge_solve(ctypes.byref(cs), _ptr(y), F, _ptr(G), _ptr(XtY), _ptr(mu), _ptr(ybar), _ptr(alphas), A,
+                              int(fit_intercept), int(alpha_per_target), _ptr(coef), _ptr(icpt), _ptr(alpha_out), _ptr(best),
+                              _ptr(loss), _ptr(ws), ws.numel(), _stream(y)), 'mvb_ridge_solve')
+    return coef, icpt, alpha_out, best, loss
+
+
+def trf_predict(design: Design, coef: torch.Tensor, intercept: Optional[torch.Tensor]) -> torch.Tensor:
+    """(n_trials, F, T) predictions for the (selected) trials of ``design``."""
+    F = coef.shape[0]
+    dev, dt = design.xp.device, design.xp.dtype
+    out = torch.empty((design.n_trials, F, design.n_time), dtype=dt, device=dev)
+    cs = design.c_struct()
+    lib = load()
+    ws = _workspace(lib.mvb_trf_predict_workspace_bytes(ctypes.byref(cs), F), dev)
+    check(lib.mvb_trf_predict(ctypes.byref(cs), _ptr(coef), _ptr(intercept), F, _ptr(out), _ptr(ws), ws.numel(), _stream(coef)),
+          'mvb_trf_predict')
+    return out
+
+
+def score(y2: torch.Tensor, yh2: torch.Tensor, yb: Optional[torch.Tensor], want_r2: bool, want_pearson: bool):
+    """y2, yh2: (R, K) contiguous; yb: (K,) or None -> (r2 (K,) | None, pearson (K,) | None)."""
+    R, K = y2.shape
+    r2 = torch.empty(K, dtype=y2.dtype, device=y2.device) if want_r2 else None
+    pr = torch.empty(K, dtype=y2.dtype, device=y2.device) if want_pearson else None
+    check(load().mvb_score(_ptr(y2), _ptr(yh2), _ptr(yb), R, K, dtype_code(y2), _ptr(r2), _ptr(pr), _stream(y2)), 'mvb_score')
+    return r2, pr
+
+
+def eigh(A: torch.Tensor):
+    """Batched symmetric eigensolve.  A: (b, p, p) (destroyed) -> Vt (b, p, p) rows = eigenvectors, lam (b, p)."""
+    b, p, _ = A.shape
+    Vt = torch.empty_like(A)
+    lam = torch.empty((b, p), dtype=A.dtype, device=A.device)
+    lib = load()
+    ws = _workspace(lib.mvb_eigh_workspace_bytes(b, p, dtype_code(A)), A.device)
+    check(lib.mvb_eigh(_ptr(A), _ptr(Vt), _ptr(lam), b, p, dtype_code(A), _ptr(ws), ws.numel(), _stream(A)), 'mvb_eigh')
+    return Vt, lam
+
+
+def contract(a_base, a_roff, a_koff, a_contig, b_base, b_roff, b_koff, b_contig, M, N, K, symmetric=False) -> torch.Tensor:
+    """Generic separable-gather contraction C[M,N] = sum_k A(m,k) B(n,k) (tests, patterns)."""
+    C = torch.empty((M, N), dtype=a_base.dtype, device=a_base.device)
+    A = mvb_operand(a_base.data_ptr(), a_roff.data_ptr(), a_koff.data_ptr(), M, a_contig)
+    B = mvb_operand(b_base.data_ptr(), b_roff.data_ptr(), b_koff.data_ptr(), N, b_contig)
+    lib = load()
+    ws = _workspace(lib.mvb_contract_workspace_bytes(M, N, K, dtype_code(a_base)), a_base.device)
+    check(lib.mvb_contract(ctypes.byref(A), ctypes.byref(B), M, N, K, dtype_code(a_base), _ptr(C), N, int(symmetric), _ptr(ws),
+                           ws.numel(), _stream(a_base)), 'mvb_contract')
+    return C

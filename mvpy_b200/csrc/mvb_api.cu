@@ -1,0 +1,545 @@
+// mvb_api.cu -- the C-ABI of libmvb.so (include/mvb.h): argument checking, workspace carving and
+// the kernel sequences of the ridge hot path.  No allocation, no synchronisation, no host fallback.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/mvb.h"
+#include "mvb_kernels.cuh"
+#include "tc_gemm.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define MVB_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess)                                                             \
+      return fail(MVB_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define MVB_LAUNCHED()                                                                   \
+  do {                                                                                   \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                  \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess)                                                              \
+      return fail(MVB_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+inline int grid_for(int64_t total, int threads = 256, int cap = 148 * 16) {
+  int64_t g = (total + threads - 1) / threads;
+  if (g < 1) g = 1;
+  return (int)(g > cap ? cap : g);
+}
+
+bool force_simt() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MVB_FORCE_SIMT");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// bump allocator over the caller's workspace
+struct Arena {
+  char* base; size_t size; size_t off = 0; bool dry;
+  Arena(void* b, size_t s) : base((char*)b), size(s), dry(b == nullptr) {}
+  template <typename U> U* take(size_t count) {
+    off = align_up(off);
+    U* p = dry ? nullptr : (U*)(base + off);
+    off += count * sizeof(U);
+    return p;
+  }
+  bool ok() const { return dry || off <= size; }
+};
+
+// ---- contraction dispatch ---------------------------------------------------------------------------
+struct SplitPlan { int splits; size_t ws_elems; };
+
+SplitPlan plan_contract(int M, int N, int K, int dtype, int symmetric) {
+  SplitPlan pl{1, 0};
+  const bool tc = (dtype == MVB_F32) && !force_simt();
+  const int bm = tc ? 128 : 64;
+  const int bn = tc ? (N > 128 ? 256 : 128) : 64;
+  const int bk = tc ? 32 * mvb::tc::DRAIN : 64;
+  int64_t tiles = (int64_t)cdiv(M, bm) * cdiv(N, bn);
+  if (symmetric) tiles = tiles / 2 + cdiv(M, bm);
+  const int kblocks = cdiv(K, bk);
+  const int target = tc ? 148 : 296;
+  int s = 1;
+  if (tiles < target) s = (int)((target + tiles - 1) / tiles);
+  if (s > kblocks) s = kblocks;
+  if (s > 64) s = 64;
+  if (s < 1) s = 1;
+  pl.splits = s;
+  pl.ws_elems = s > 1 ? (size_t)s * M * N : 0;
+  return pl;
+}
+
+template <typename T>
+int run_contract(const mvb_operand& A, const mvb_operand& B, int M, int N, int K, T* C, int64_t ldc, int symmetric,
+                 void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return MVB_OK;
+  constexpr int dtype = sizeof(T) == 4 ? MVB_F32 : MVB_F64;
+  const SplitPlan pl = plan_contract(M, N, K, dtype, symmetric);
+  T* out = C;
+  int64_t ld = ldc, stride = 0;
+  if (pl.splits > 1) {
+    if (ws_bytes < pl.ws_elems * sizeof(T)) return fail(MVB_E_WORKSPACE, "contract: workspace %zu < %zu", ws_bytes, pl.ws_elems * sizeof(T));
+    out = (T*)ws; ld = N; stride = (int64_t)M * N;
+  }
+  const bool tc = (dtype == MVB_F32) && !force_simt();
+  if (tc) {
+    mvb::TcGemmParams p;
+    p.A = {(const float*)A.base, A.roff, A.koff, A.rows, A.contig};
+    p.B = {(const float*)B.base, B.roff, B.koff, B.rows, B.contig};
+    p.M = M; p.N = N; p.K = K; p.C = (float*)out; p.ldc = ld; p.c_split_stride = stride; p.symmetric = symmetric; p.dbg = 0;
+    MVB_CUDA(mvb::tc_gemm_launch(p, pl.splits, N > 128 ? 256 : 128, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  } else {
+    mvb::GOp<T> a{(const T*)A.base, A.roff, A.koff, A.rows}, b{(const T*)B.base, B.roff, B.koff, B.rows};
+    dim3 grid(cdiv(N, 64), cdiv(M, 64), pl.splits);
+    mvb::simt_contract_kernel<T><<<grid, 256, 0, st>>>(a, b, M, N, K, out, ld, stride, symmetric);
+    MVB_LAUNCHED();
+  }
+  if (pl.splits > 1) {
+    mvb::reduce_splits_kernel<T><<<grid_for((int64_t)M * N), 256, 0, st>>>(out, pl.splits, stride, M, N, ld, C, ldc);
+    MVB_LAUNCHED();
+  }
+  return MVB_OK;
+}
+
+int dense_mode(int64_t ld, int K, const void* base, size_t elem) {
+  return (elem == 4 && ld % 4 == 0 && K % 4 == 0 && ((uintptr_t)base & 15) == 0) ? 2 : 1;
+}
+
+bool design_ok(const mvb_design* d) {
+  return d && d->xp && d->n_time > 0 && d->n_lag > 0 && d->n_trials > 0 && d->n_feat > 0 &&
+         (d->dtype == MVB_F32 || d->dtype == MVB_F64);
+}
+
+// ---- stats ------------------------------------------------------------------------------------------
+struct StatsWs {
+  int64_t *row_off, *col_off, *yrow_off, *ycol_off;
+  double *partial, *mu64, *ybar64;
+  void* contract_ws; size_t contract_bytes;
+  int parts;
+};
+
+template <typename T>
+size_t carve_stats(Arena& ar, const mvb_design* d, int F, StatsWs& w) {
+  const int64_t n = (int64_t)d->n_trials * d->n_time, p = (int64_t)d->n_feat * d->n_lag;
+  w.parts = (int)std::min<int64_t>(64, std::max<int64_t>(1, n / 256));
+  w.row_off = ar.take<int64_t>(n);
+  w.col_off = ar.take<int64_t>(p);
+  w.yrow_off = ar.take<int64_t>(n);
+  w.ycol_off = ar.take<int64_t>(F);
+  w.partial = ar.take<double>((size_t)w.parts * (p + F));
+  w.mu64 = ar.take<double>(p);
+  w.ybar64 = ar.take<double>(F);
+  constexpr int dt = sizeof(T) == 4 ? MVB_F32 : MVB_F64;
+  size_t cb = std::max(plan_contract((int)p, (int)p, (int)n, dt, 1).ws_elems, plan_contract((int)p, F, (int)n, dt, 0).ws_elems) * sizeof(T);
+  w.contract_bytes = cb;
+  w.contract_ws = ar.take<char>(cb);
+  return ar.off;
+}
+
+template <typename T>
+int trf_stats_impl(const mvb_design* d, const T* y, int F, int fit_intercept, T* G, T* XtY, T* mu, T* ybar, void* ws,
+                   size_t ws_bytes, cudaStream_t st) {
+  const int64_t n = (int64_t)d->n_trials * d->n_time, p = (int64_t)d->n_feat * d->n_lag;
+  Arena ar(ws, ws_bytes);
+  StatsWs w;
+  carve_stats<T>(ar, d, F, w);
+  if (!ar.ok()) return fail(MVB_E_WORKSPACE, "trf_stats: workspace %zu < %zu", ws_bytes, ar.off);
+  const int Tn = d->n_time;
+  mvb::design_offsets_kernel<<<grid_for(n + p), 256, 0, st>>>(d->trial_idx, d->n_trials, Tn, d->trial_stride, d->feat_idx,
+                                                            d->n_feat, d->n_lag, d->feat_stride, (int64_t)F * Tn,
+                                                            w.row_off, w.col_off, w.yrow_off);
+  MVB_LAUNCHED();
+  mvb::iota_offsets_kernel<<<grid_for(F), 256, 0, st>>>(w.ycol_off, F, Tn);
+  MVB_LAUNCHED();
+  // column / target sums -> means
+  {
+    dim3 gx(cdiv(p, 128), w.parts), gy(cdiv(F, 128), w.parts);
+    mvb::col_sums_kernel<T><<<gx, 128, 0, st>>>((const T*)d->xp, w.row_off, w.col_off, n, p, w.partial);
+    MVB_LAUNCHED();
+    mvb::col_sums_kernel<T><<<gy, 128, 0, st>>>(y, w.yrow_off, w.ycol_off, n, F, w.partial + (size_t)w.parts * p);
+    MVB_LAUNCHED();
+    mvb::sums_finish_kernel<T><<<cdiv(p, 256), 256, 0, st>>>(w.partial, w.parts, p, 1.0 / (double)n, fit_intercept, mu, w.mu64);
+    MVB_LAUNCHED();
+    mvb::sums_finish_kernel<T><<<cdiv(F, 256), 256, 0, st>>>(w.partial + (size_t)w.parts * p, w.parts, F, 1.0 / (double)n,
+                                                             fit_intercept, ybar, w.ybar64);
+    MVB_LAUNCHED();
+  }
+  mvb_operand xc{d->xp, w.col_off, w.row_off, (int)p, 1};
+  mvb_operand yc{y, w.ycol_off, w.yrow_off, F, 1};
+  int rc = run_contract<T>(xc, xc, (int)p, (int)p, (int)n, G, p, 1, w.contract_ws, w.contract_bytes, st);
+  if (rc) return rc;
+  rc = run_contract<T>(xc, yc, (int)p, F, (int)n, XtY, F, 0, w.contract_ws, w.contract_bytes, st);
+  if (rc) return rc;
+  if (fit_intercept) {
+    mvb::centre_moments_kernel<T><<<grid_for(p * p + p * F), 256, 0, st>>>(G, p, XtY, F, w.mu64, w.ybar64, (double)n);
+    MVB_LAUNCHED();
+  }
+  return MVB_OK;
+}
+
+// ---- eigensolver -------------------------------------------------------------------------------------
+constexpr int kMaxSweeps = 40;
+
+template <typename T>
+int eigh_impl(T* A, T* Vt, T* lam, int batch, int p, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const size_t need = (size_t)batch * kMaxSweeps * sizeof(unsigned int);
+  if (ws_bytes < need) return fail(MVB_E_WORKSPACE, "eigh: workspace %zu < %zu", ws_bytes, need);
+  MVB_CUDA(cudaMemsetAsync(ws, 0, need, st));
+  int cluster = 1;
+  if (p > 96) cluster = 8;
+  int threads = p <= 64 ? 256 : 1024;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(batch * cluster);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const double eps = sizeof(T) == 4 ? 5.96e-8 : 1.11e-16;
+  const double tol = eps * sqrt((double)(p < 4 ? 4 : p));
+  MVB_CUDA(cudaLaunchKernelEx(&cfg, mvb::jacobi_rows_kernel<T>, A, Vt, lam, p, kMaxSweeps, tol, (unsigned int*)ws, cluster));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return MVB_OK;
+}
+
+// ---- ridge solve ---------------------------------------------------------------------------------------
+struct SolveWs {
+  int64_t *row_off, *col_off, *yrow_off, *iota_p, *iota_1, *iota_F;
+  void *Vt, *lam, *w, *Vtb, *theta, *beta, *ZR, *d;
+  double *mu64, *ybar64, *cz, *mb, *loss_partial, *loss64;
+  void* eig_ws; size_t eig_bytes;
+  void* contract_ws; size_t contract_bytes;
+  int slabs;
+};
+
+template <typename T>
+void carve_solve(Arena& ar, const mvb_design* d, int F, int A, SolveWs& w) {
+  const int64_t n = (int64_t)d->n_trials * d->n_time, p = (int64_t)d->n_feat * d->n_lag;
+  const int64_t AF = (int64_t)A * F;
+  constexpr int dt = sizeof(T) == 4 ? MVB_F32 : MVB_F64;
+  w.slabs = (int)std::min<int64_t>(128, std::max<int64_t>(1, n / 128));
+  w.row_off = ar.take<int64_t>(n);
+  w.col_off = ar.take<int64_t>(p);
+  w.yrow_off = ar.take<int64_t>(n);
+  w.iota_p = ar.take<int64_t>(std::max<int64_t>(p, AF));
+  w.iota_1 = ar.take<int64_t>(std::max<int64_t>(p, AF));
+  w.iota_F = ar.take<int64_t>(p);
+  w.Vt = ar.take<T>(p * p);
+  w.lam = ar.take<T>(p);
+  w.w = ar.take<T>((size_t)A * p);
+  w.Vtb = ar.take<T>(p * F);
+  w.theta = ar.take<T>(AF * p);
+  w.beta = ar.take<T>(AF * p);
+  w.ZR = ar.take<T>(n * std::max<int64_t>(p, AF));
+  w.d = ar.take<T>(n * A);
+  w.mu64 = ar.take<double>(p);
+  w.ybar64 = ar.take<double>(F);
+  w.cz = ar.take<double>(p);
+  w.mb = ar.take<double>(AF);
+  w.loss_partial = ar.take<double>((size_t)w.slabs * AF);
+  w.loss64 = ar.take<double>(AF);
+  w.eig_bytes = (size_t)kMaxSweeps * sizeof(unsigned int);
+  w.eig_ws = ar.take<char>(w.eig_bytes);
+  size_t cb = 0;
+  cb = std::max(cb, plan_contract((int)p, F, (int)p, dt, 0).ws_elems);
+  cb = std::max(cb, plan_contract((int)AF, (int)p, (int)p, dt, 0).ws_elems);
+  cb = std::max(cb, plan_contract((int)n, (int)p, (int)p, dt, 0).ws_elems);
+  cb = std::max(cb, plan_contract((int)n, (int)AF, (int)p, dt, 0).ws_elems);
+  w.contract_bytes = cb * sizeof(T);
+  w.contract_ws = ar.take<char>(w.contract_bytes);
+}
+
+template <typename T>
+__global__ void to_double_kernel(const T* __restrict__ in, int64_t n, double* out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (double)in[i];
+}
+
+template <typename T>
+int ridge_solve_impl(const mvb_design* d, const T* y, int F, T* G, const T* XtY, const T* mu, const T* ybar,
+                     const T* alphas, int A, int fit_intercept, int per_target, T* coef, T* intercept, T* alpha_out,
+                     int32_t* best, T* loss, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int64_t n = (int64_t)d->n_trials * d->n_time, p = (int64_t)d->n_feat * d->n_lag;
+  const int64_t AF = (int64_t)A * F;
+  const int Tn = d->n_time;
+  Arena ar(ws, ws_bytes);
+  SolveWs w;
+  carve_solve<T>(ar, d, F, A, w);
+  if (!ar.ok()) return fail(MVB_E_WORKSPACE, "ridge_solve: workspace %zu < %zu", ws_bytes, ar.off);
+  T *Vt = (T*)w.Vt, *lam = (T*)w.lam, *wt = (T*)w.w, *Vtb = (T*)w.Vtb, *theta = (T*)w.theta, *beta = (T*)w.beta,
+    *ZR = (T*)w.ZR, *dd = (T*)w.d;
+
+  mvb::design_offsets_kernel<<<grid_for(n + p), 256, 0, st>>>(d->trial_idx, d->n_trials, Tn, d->trial_stride, d->feat_idx,
+                                                            d->n_feat, d->n_lag, d->feat_stride, (int64_t)F * Tn,
+                                                            w.row_off, w.col_off, w.yrow_off);
+  MVB_LAUNCHED();
+  const int64_t niota = std::max<int64_t>(p, AF);
+  mvb::iota_offsets_kernel<<<grid_for(niota), 256, 0, st>>>(w.iota_p, niota, p);   // i * p
+  MVB_LAUNCHED();
+  mvb::iota_offsets_kernel<<<grid_for(niota), 256, 0, st>>>(w.iota_1, niota, 1);   // i
+  MVB_LAUNCHED();
+  to_double_kernel<T><<<grid_for(p), 256, 0, st>>>(mu, p, w.mu64);
+  MVB_LAUNCHED();
+  to_double_kernel<T><<<grid_for(F), 256, 0, st>>>(ybar, F, w.ybar64);
+  MVB_LAUNCHED();
+
+  // 1. G = V diag(lam) V^T
+  int rc = eigh_impl<T>(G, Vt, lam, 1, (int)p, w.eig_ws, w.eig_bytes, st);
+  if (rc) return rc;
+  // 2. ridge weights for the whole alpha grid
+  mvb::ridge_weights_kernel<T><<<grid_for((int64_t)A * p), 256, 0, st>>>(lam, alphas, A, (int)p, wt);
+  MVB_LAUNCHED();
+  // 3. Vtb[k][f] = sum_j Vt[k][j] XtY[j][f]
+  const int vmode = dense_mode(p, (int)p, Vt, sizeof(T));
+  mvb_operand opVt{Vt, w.iota_p, w.iota_1, (int)p, vmode};                 // rows k, contraction j (contiguous)
+  mvb::iota_offsets_kernel<<<grid_for(p), 256, 0, st>>>(w.iota_F, p, F);     // j * F
+  MVB_LAUNCHED();
+  mvb_operand opXtYt{XtY, w.iota_1, w.iota_F, F, 0};                       // rows f (contiguous), contraction j (stride F)
+  rc = run_contract<T>(opVt, opXtYt, (int)p, F, (int)p, Vtb, F, 0, w.contract_ws, w.contract_bytes, st);
+  if (rc) return rc;
+  // 4. theta_t[(a,f)][k] = w[a][k] Vtb[k][f];  beta_all[(a,f)][j] = sum_k theta_t[(a,f)][k] Vt[k][j]
+  mvb::theta_kernel<T><<<grid_for(AF * p), 256, 0, st>>>(wt, Vtb, A, F, (int)p, theta);
+  MVB_LAUNCHED();
+  mvb_operand opTheta{theta, w.iota_p, w.iota_1, (int)AF, dense_mode(p, (int)p, theta, sizeof(T))};
+  mvb_operand opVcols{Vt, w.iota_1, w.iota_p, (int)p, 0};                  // rows j (contiguous), contraction k (stride p)
+  rc = run_contract<T>(opTheta, opVcols, (int)AF, (int)p, (int)p, beta, p, 0, w.contract_ws, w.contract_bytes, st);
+  if (rc) return rc;
+  // 5. centring terms: cz[k] = <Vt[k], mu>,  mb[(a,f)] = <beta_all[(a,f)], mu>
+  mvb::matvec_rows_kernel<T><<<cdiv(p * 32, 256), 256, 0, st>>>(Vt, p, p, w.mu64, w.cz);
+  MVB_LAUNCHED();
+  mvb::matvec_rows_kernel<T><<<cdiv(AF * 32, 256), 256, 0, st>>>(beta, AF, p, w.mu64, w.mb);
+  MVB_LAUNCHED();
+  // 6. Z = X_t V  (implicit design rows x eigenvectors), leverages -> d = 1 - h - c0
+  mvb_operand opRows{d->xp, w.row_off, w.col_off, (int)n, 0};              // rows i (t contiguous), contraction j
+  rc = run_contract<T>(opRows, opVt, (int)n, (int)p, (int)p, ZR, p, 0, w.contract_ws, w.contract_bytes, st);
+  if (rc) return rc;
+  mvb::leverage_kernel<T><<<cdiv(n, 64), 256, 0, st>>>(ZR, n, (int)p, p, w.cz, wt, A, fit_intercept ? 1.0 / (double)n : 0.0, dd);
+  MVB_LAUNCHED();
+  // 7. fitted values for every (alpha, target): R = X_t beta_all^T
+  mvb_operand opBeta{beta, w.iota_p, w.iota_1, (int)AF, dense_mode(p, (int)p, beta, sizeof(T))};
+  rc = run_contract<T>(opRows, opBeta, (int)n, (int)AF, (int)p, ZR, AF, 0, w.contract_ws, w.contract_bytes, st);
+  if (rc) return rc;
+  // 8. LOO losses, alpha selection, coefficients
+  {
+    dim3 grid(cdiv(AF, 128), w.slabs);
+    mvb::loo_loss_kernel<T><<<grid, 128, 0, st>>>(ZR, n, A, F, AF, y, w.yrow_off, (int64_t)Tn, w.ybar64, w.mb, dd, w.loss_partial);
+    MVB_LAUNCHED();
+    mvb::select_alpha_kernel<T><<<1, 256, 0, st>>>(w.loss_partial, w.slabs, A, F, 1.0 / (double)n, alphas, per_target, loss, best,
+                                                   alpha_out, w.loss64);
+    MVB_LAUNCHED();
+    mvb::gather_coef_kernel<T><<<grid_for((int64_t)F * p), 256, 0, st>>>(beta, F, p, best, per_target, w.ybar64, w.mb, fit_intercept,
+                                                                          coef, intercept);
+    MVB_LAUNCHED();
+  }
+  return MVB_OK;
+}
+
+template <typename T>
+int predict_impl(const mvb_design* d, const T* coef, const T* intercept, int F, T* yhat, void* ws, size_t ws_bytes,
+                 cudaStream_t st) {
+  const int64_t n = (int64_t)d->n_trials * d->n_time, p = (int64_t)d->n_feat * d->n_lag;
+  constexpr int dt = sizeof(T) == 4 ? MVB_F32 : MVB_F64;
+  Arena ar(ws, ws_bytes);
+  int64_t* row_off = ar.take<int64_t>(n);
+  int64_t* col_off = ar.take<int64_t>(p);
+  int64_t* iota_p = ar.take<int64_t>(F);
+  int64_t* iota_1 = ar.take<int64_t>(p);
+  T* P = ar.take<T>(n * F);
+  const size_t cb = plan_contract((int)n, F, (int)p, dt, 0).ws_elems * sizeof(T);
+  void* cws = ar.take<char>(cb);
+  if (!ar.ok()) return fail(MVB_E_WORKSPACE, "trf_predict: workspace %zu < %zu", ws_bytes, ar.off);
+  if (!ws) return MVB_OK;
+  mvb::design_offsets_kernel<<<grid_for(n + p), 256, 0, st>>>(d->trial_idx, d->n_trials, d->n_time, d->trial_stride, d->feat_idx,
+                                                            d->n_feat, d->n_lag, d->feat_stride, 0, row_off, col_off, nullptr);
+  MVB_LAUNCHED();
+  mvb::iota_offsets_kernel<<<grid_for(F), 256, 0, st>>>(iota_p, F, p);
+  MVB_LAUNCHED();
+  mvb::iota_offsets_kernel<<<grid_for(p), 256, 0, st>>>(iota_1, p, 1);
+  MVB_LAUNCHED();
+  mvb_operand opRows{d->xp, row_off, col_off, (int)n, 0};
+  mvb_operand opCoef{coef, iota_p, iota_1, F, dense_mode(p, (int)p, coef, sizeof(T))};
+  int rc = run_contract<T>(opRows, opCoef, (int)n, F, (int)p, P, F, 0, cws, cb, st);
+  if (rc) return rc;
+  dim3 grid(cdiv(d->n_time, 32), cdiv(F, 32), d->n_trials), block(32, 8);
+  mvb::predict_layout_kernel<T><<<grid, block, 0, st>>>(P, d->n_trials, F, d->n_time, F, intercept, yhat);
+  MVB_LAUNCHED();
+  return MVB_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int mvb_version(void) { return 100; }
+const char* mvb_last_error(void) { return g_err; }
+int64_t mvb_launch_count(void) { return g_launches.load(); }
+
+int mvb_scaler_fit(const void* X, int64_t R, int64_t K, int dtype, void* mean, void* var, void* scale, void* stream) {
+  if (!X || !mean || !var || !scale || R < 1 || K < 1) return fail(MVB_E_ARG, "scaler_fit: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MVB_F32) mvb::scaler_fit_kernel<float><<<cdiv(K, 128), 128, 0, st>>>((const float*)X, R, K, (float*)mean, (float*)var, (float*)scale);
+  else if (dtype == MVB_F64) mvb::scaler_fit_kernel<double><<<cdiv(K, 128), 128, 0, st>>>((const double*)X, R, K, (double*)mean, (double*)var, (double*)scale);
+  else return fail(MVB_E_UNSUPPORTED, "scaler_fit: dtype %d", dtype);
+  MVB_LAUNCHED();
+  return MVB_OK;
+}
+
+int mvb_scaler_apply(const void* X, int64_t R, int64_t K, int dtype, const void* mean, const void* scale, int with_mean,
+                     int with_std, int inverse, void* out, void* stream) {
+  if (!X || !out || R < 1 || K < 1 || (with_mean && !mean) || (with_std && !scale)) return fail(MVB_E_ARG, "scaler_apply: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = R * K;
+  if (dtype == MVB_F32) mvb::scaler_apply_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)X, total, K, (const float*)mean, (const float*)scale, with_mean, with_std, inverse, (float*)out);
+  else if (dtype == MVB_F64) mvb::scaler_apply_kernel<double><<<grid_for(total), 256, 0, st>>>((const double*)X, total, K, (const double*)mean, (const double*)scale, with_mean, with_std, inverse, (double*)out);
+  else return fail(MVB_E_UNSUPPORTED, "scaler_apply: dtype %d", dtype);
+  MVB_LAUNCHED();
+  return MVB_OK;
+}
+
+int mvb_trf_pad(const void* X, int N, int C, int T, int left, int right, int dtype, void* Xp, void* stream) {
+  if (!X || !Xp || N < 1 || C < 1 || T < 1 || left < 0 || right < 0) return fail(MVB_E_ARG, "trf_pad: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = (int64_t)N * C;
+  const int Tp = T + left + right;
+  if (dtype == MVB_F32) mvb::pad_kernel<float><<<grid_for(rows * Tp), 256, 0, st>>>((const float*)X, rows, T, left, Tp, (float*)Xp);
+  else if (dtype == MVB_F64) mvb::pad_kernel<double><<<grid_for(rows * Tp), 256, 0, st>>>((const double*)X, rows, T, left, Tp, (double*)Xp);
+  else return fail(MVB_E_UNSUPPORTED, "trf_pad: dtype %d", dtype);
+  MVB_LAUNCHED();
+  return MVB_OK;
+}
+
+int mvb_transpose(const void* X, int64_t R, int64_t C, int dtype, void* out, void* stream) {
+  if (!X || !out || R < 1 || C < 1) return fail(MVB_E_ARG, "transpose: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(cdiv(C, 32), cdiv(R, 32)), block(32, 8);
+  if (dtype == MVB_F32) mvb::transpose_kernel<float><<<grid, block, 0, st>>>((const float*)X, R, C, (float*)out);
+  else if (dtype == MVB_F64) mvb::transpose_kernel<double><<<grid, block, 0, st>>>((const double*)X, R, C, (double*)out);
+  else return fail(MVB_E_UNSUPPORTED, "transpose: dtype %d", dtype);
+  MVB_LAUNCHED();
+  return MVB_OK;
+}
+
+size_t mvb_contract_workspace_bytes(int M, int N, int K, int dtype) {
+  const size_t a = plan_contract(M, N, K, dtype, 0).ws_elems, b = plan_contract(M, N, K, dtype, 1).ws_elems;
+  return std::max(a, b) * (dtype == MVB_F32 ? 4 : 8) + 256;
+}
+
+int mvb_contract(const mvb_operand* A, const mvb_operand* B, int M, int N, int K, int dtype, void* C, int64_t ldc,
+                 int symmetric, void* ws, size_t ws_bytes, void* stream) {
+  if (!A || !B || !C || !A->base || !B->base || !A->roff || !A->koff || !B->roff || !B->koff || M < 0 || N < 0 || K < 0 || ldc < N)
+    return fail(MVB_E_ARG, "contract: bad argument");
+  if (A->rows < M || B->rows < N) return fail(MVB_E_ARG, "contract: operand rows smaller than M/N");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MVB_F32) return run_contract<float>(*A, *B, M, N, K, (float*)C, ldc, symmetric, ws, ws_bytes, st);
+  if (dtype == MVB_F64) return run_contract<double>(*A, *B, M, N, K, (double*)C, ldc, symmetric, ws, ws_bytes, st);
+  return fail(MVB_E_UNSUPPORTED, "contract: dtype %d", dtype);
+}
+
+size_t mvb_trf_stats_workspace_bytes(const mvb_design* d, int n_targets) {
+  if (!design_ok(d) || n_targets < 1) return 0;
+  Arena ar(nullptr, 0);
+  StatsWs w;
+  if (d->dtype == MVB_F32) carve_stats<float>(ar, d, n_targets, w); else carve_stats<double>(ar, d, n_targets, w);
+  return ar.off + 256;
+}
+
+int mvb_trf_stats(const mvb_design* d, const void* y, int n_targets, int fit_intercept, void* G, void* XtY, void* mu,
+                  void* ybar, void* ws, size_t ws_bytes, void* stream) {
+  if (!design_ok(d) || !y || n_targets < 1 || !G || !XtY || !mu || !ybar || !ws) return fail(MVB_E_ARG, "trf_stats: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype == MVB_F32) return trf_stats_impl<float>(d, (const float*)y, n_targets, fit_intercept, (float*)G, (float*)XtY, (float*)mu, (float*)ybar, ws, ws_bytes, st);
+  return trf_stats_impl<double>(d, (const double*)y, n_targets, fit_intercept, (double*)G, (double*)XtY, (double*)mu, (double*)ybar, ws, ws_bytes, st);
+}
+
+size_t mvb_eigh_workspace_bytes(int batch, int p, int dtype) {
+  (void)p; (void)dtype;
+  return (size_t)batch * kMaxSweeps * sizeof(unsigned int) + 256;
+}
+
+int mvb_eigh(void* A, void* Vt, void* lam, int batch, int p, int dtype, void* ws, size_t ws_bytes, void* stream) {
+  if (!A || !Vt || !lam || batch < 1 || p < 1 || !ws) return fail(MVB_E_ARG, "eigh: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MVB_F32) return eigh_impl<float>((float*)A, (float*)Vt, (float*)lam, batch, p, ws, ws_bytes, st);
+  if (dtype == MVB_F64) return eigh_impl<double>((double*)A, (double*)Vt, (double*)lam, batch, p, ws, ws_bytes, st);
+  return fail(MVB_E_UNSUPPORTED, "eigh: dtype %d", dtype);
+}
+
+size_t mvb_ridge_solve_workspace_bytes(const mvb_design* d, int n_targets, int n_alphas) {
+  if (!design_ok(d) || n_targets < 1 || n_alphas < 1) return 0;
+  Arena ar(nullptr, 0);
+  SolveWs w;
+  if (d->dtype == MVB_F32) carve_solve<float>(ar, d, n_targets, n_alphas, w); else carve_solve<double>(ar, d, n_targets, n_alphas, w);
+  return ar.off + 256;
+}
+
+int mvb_ridge_solve(const mvb_design* d, const void* y, int n_targets, void* G, const void* XtY, const void* mu,
+                    const void* ybar, const void* alphas, int n_alphas, int fit_intercept, int alpha_per_target,
+                    void* coef, void* intercept, void* alpha_out, int32_t* best, void* loss, void* ws, size_t ws_bytes,
+                    void* stream) {
+  if (!design_ok(d) || !y || n_targets < 1 || !G || !XtY || !mu || !ybar || !alphas || n_alphas < 1 || !coef || !intercept ||
+      !alpha_out || !best || !ws)
+    return fail(MVB_E_ARG, "ridge_solve: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype == MVB_F32)
+    return ridge_solve_impl<float>(d, (const float*)y, n_targets, (float*)G, (const float*)XtY, (const float*)mu, (const float*)ybar,
+                                   (const float*)alphas, n_alphas, fit_intercept, alpha_per_target, (float*)coef, (float*)intercept,
+                                   (float*)alpha_out, best, (float*)loss, ws, ws_bytes, st);
+  return ridge_solve_impl<double>(d, (const double*)y, n_targets, (double*)G, (const double*)XtY, (const double*)mu,
+                                  (const double*)ybar, (const double*)alphas, n_alphas, fit_intercept, alpha_per_target,
+                                  (double*)coef, (double*)intercept, (double*)alpha_out, best, (double*)loss, ws, ws_bytes, st);
+}
+
+size_t mvb_trf_predict_workspace_bytes(const mvb_design* d, int n_targets) {
+  if (!design_ok(d) || n_targets < 1) return 0;
+  const int64_t n = (int64_t)d->n_trials * d->n_time, p = (int64_t)d->n_feat * d->n_lag;
+  const size_t es = d->dtype == MVB_F32 ? 4 : 8;
+  size_t b = align_up(n * 8) + align_up(p * 8) + align_up((size_t)n_targets * 8) + align_up(p * 8) + align_up(n * n_targets * es) +
+             align_up(plan_contract((int)n, n_targets, (int)p, d->dtype, 0).ws_elems * es);
+  return b + 1024;
+}
+
+int mvb_trf_predict(const mvb_design* d, const void* coef, const void* intercept, int n_targets, void* yhat, void* ws,
+                    size_t ws_bytes, void* stream) {
+  if (!design_ok(d) || !coef || n_targets < 1 || !yhat || !ws) return fail(MVB_E_ARG, "trf_predict: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype == MVB_F32) return predict_impl<float>(d, (const float*)coef, (const float*)intercept, n_targets, (float*)yhat, ws, ws_bytes, st);
+  return predict_impl<double>(d, (const double*)coef, (const double*)intercept, n_targets, (double*)yhat, ws, ws_bytes, st);
+}
+
+int mvb_score(const void* y, const void* yhat, const void* y_b, int64_t R, int64_t K, int dtype, void* r2_out,
+              void* pearson_out, void* stream) {
+  if (!y || !yhat || R < 1 || K < 1 || (!r2_out && !pearson_out)) return fail(MVB_E_ARG, "score: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MVB_F32) mvb::score_kernel<float><<<cdiv(K, 128), 128, 0, st>>>((const float*)y, (const float*)yhat, (const float*)y_b, R, K, (float*)r2_out, (float*)pearson_out);
+  else if (dtype == MVB_F64) mvb::score_kernel<double><<<cdiv(K, 128), 128, 0, st>>>((const double*)y, (const double*)yhat, (const double*)y_b, R, K, (double*)r2_out, (double*)pearson_out);
+  else return fail(MVB_E_UNSUPPORTED, "score: dtype %d", dtype);
+  MVB_LAUNCHED();
+  return MVB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,548 @@
+// mvb_kernels.cuh -- CUDA-core kernels of the ridge hot path (everything that is not the
+// tcgen05 contraction core): scaler statistics, edge padding, offset tables, the fp64/validation
+// contraction, centring, the Jacobi eigensolver, leverage / LOO-loss reductions, alpha selection,
+// prediction layout and the fused R2 / Pearson scoring kernel.  Templated on float / double.
+#pragma once
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace mvb {
+namespace cg = cooperative_groups;
+
+template <typename T> struct Acc { using type = double; };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scaler (preprocessing/scaler.py:355-360, 385-393).  X viewed as [R][K]; one thread per kept cell,
+// consecutive threads on consecutive cells (coalesced); two passes with fp64 accumulators, which is
+// how torch's CPU var kernel accumulates fp32 input (results are rounded to T at the end, so tiny
+// variances underflow to 0 exactly like the reference -- SURVEY.md H5).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void scaler_fit_kernel(const T* __restrict__ X, int64_t R, int64_t K, T* mean, T* var, T* scale) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  double s = 0;
+  for (int64_t r = 0; r < R; ++r) s += (double)X[r * K + k];
+  const double m = s / (double)R;
+  const T mT = (T)m;
+  double q = 0;
+  for (int64_t r = 0; r < R; ++r) {
+    const double d = (double)X[r * K + k] - m;
+    q += d * d;
+  }
+  const T v = (T)(q / (double)(R - 1));  // R == 1 -> NaN like torch.var
+  T sc = (T)sqrt((double)v);
+  if (sc == (T)0 || sc != sc) sc = (T)1;
+  mean[k] = mT;
+  var[k] = v;
+  scale[k] = sc;
+}
+
+template <typename T>
+__global__ void scaler_apply_kernel(const T* __restrict__ X, int64_t total, int64_t K, const T* __restrict__ mean,
+                                    const T* __restrict__ scale, int with_mean, int with_std, int inverse, T* out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = i % K;
+    T x = X[i];
+    if (!inverse) {
+      if (with_mean) x = x - mean[k];
+      if (with_std) x = x / scale[k];
+    } else {
+      if (with_std) x = x * scale[k];
+      if (with_mean) x = x + mean[k];
+    }
+    out[i] = x;
+  }
+}
+
+// (N,C,T) -> (N,C,T+left+right), replicated edges  (timedelayed.py:415-417: clamp(t + lag, 0, T-1))
+template <typename T>
+__global__ void pad_kernel(const T* __restrict__ X, int64_t rows, int Tn, int left, int Tp, T* out) {
+  const int64_t total = rows * Tp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / Tp;
+    int j = (int)(i - r * Tp) - left;
+    j = j < 0 ? 0 : (j > Tn - 1 ? Tn - 1 : j);
+    out[i] = X[r * Tn + j];
+  }
+}
+
+template <typename T>
+__global__ void transpose_kernel(const T* __restrict__ X, int64_t R, int64_t C, T* out) {
+  __shared__ T tile[32][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int64_t r = r0 + j, c = c0 + threadIdx.x;
+    if (r < R && c < C) tile[j][threadIdx.x] = X[r * C + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int64_t c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < C) out[c * R + r] = tile[threadIdx.x][j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// offset tables of the implicit design (rows i=(s,t), columns j=(f,w)) and of the targets
+// ------------------------------------------------------------------------------------------------
+__global__ void design_offsets_kernel(const int32_t* trial_idx, int n_trials, int n_time, int64_t trial_stride,
+                                      const int32_t* feat_idx, int n_feat, int n_lag, int64_t feat_stride,
+                                      int64_t y_trial_stride, int64_t* row_off, int64_t* col_off, int64_t* yrow_off) {
+  const int64_t n = (int64_t)n_trials * n_time, p = (int64_t)n_feat * n_lag;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n + p; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < n) {
+      const int s = (int)(i / n_time), t = (int)(i % n_time);
+      const int64_t tr = trial_idx ? trial_idx[s] : s;
+      row_off[i] = tr * trial_stride + t;
+      if (yrow_off) yrow_off[i] = tr * y_trial_stride + t;
+    } else {
+      const int64_t j = i - n;
+      const int f = (int)(j / n_lag), w = (int)(j % n_lag);
+      const int64_t ft = feat_idx ? feat_idx[f] : f;
+      col_off[j] = ft * feat_stride + w;
+    }
+  }
+}
+
+__global__ void iota_offsets_kernel(int64_t* out, int64_t n, int64_t stride) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = i * stride;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core contraction with the same separable-gather operands as the tensor-core core.
+// fp64 path (reference tests run in fp64) and cross-check for the tcgen05 kernel.
+// 64x64 tile, 16-deep K slabs, 256 threads, 4x4 outputs per thread; split-K partials over blockIdx.z.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct GOp {
+  const T* base; const int64_t* roff; const int64_t* koff; int rows;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) simt_contract_kernel(GOp<T> A, GOp<T> B, int M, int N, int K, T* C, int64_t ldc,
+                                                            int64_t split_stride, int symmetric) {
+  constexpr int TM = 64, TN = 64, TK = 16;
+  __shared__ T As[TK][TM + 1];
+  __shared__ T Bs[TK][TN + 1];
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  if (symmetric && n0 > m0 + TM - 1) return;
+  const int nk = (K + TK - 1) / TK;
+  const int per = (nk + gridDim.z - 1) / gridDim.z;
+  const int kb0 = blockIdx.z * per, kb1 = min(nk, kb0 + per);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  typename Acc<T>::type acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+  for (int kb = kb0; kb < kb1; ++kb) {
+    const int k0 = kb * TK;
+    for (int e = threadIdx.x; e < TM * TK; e += 256) {
+      const int r = e % TM, kk = e / TM;
+      const int gr = m0 + r, gk = k0 + kk;
+      As[kk][r] = (gr < A.rows && gk < K) ? A.base[A.roff[gr] + A.koff[gk]] : (T)0;
+    }
+    for (int e = threadIdx.x; e < TN * TK; e += 256) {
+      const int r = e % TN, kk = e / TN;
+      const int gr = n0 + r, gk = k0 + kk;
+      Bs[kk][r] = (gr < B.rows && gk < K) ? B.base[B.roff[gr] + B.koff[gk]] : (T)0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += (typename Acc<T>::type)a[i] * (typename Acc<T>::type)b[j];
+    }
+    __syncthreads();
+  }
+  T* Cz = C + (int64_t)blockIdx.z * split_stride;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      Cz[(int64_t)gm * ldc + gn] = (T)acc[i][j];
+      if (symmetric && gn < M && gm < N) {
+        const int mt0 = (gn / TM) * TM, nt0 = (gm / TN) * TN;
+        if (nt0 > mt0 + TM - 1) Cz[(int64_t)gn * ldc + gm] = (T)acc[i][j];
+      }
+    }
+  }
+}
+
+// out[m][n] = sum_z part[z][m][n]   (round-to-nearest adds of split-K partials, fixed order)
+template <typename T>
+__global__ void reduce_splits_kernel(const T* __restrict__ part, int splits, int64_t split_stride, int M, int N,
+                                     int64_t ld_part, T* out, int64_t ld_out) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / N, n = i - m * N;
+    typename Acc<T>::type s = 0;
+    for (int z = 0; z < splits; ++z) s += part[z * split_stride + m * ld_part + n];
+    out[m * ld_out + n] = (T)s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column / target sums of the implicit design (for centring: ridgecv.py:81-88)
+// one thread per column j, consecutive j -> consecutive lags -> coalesced; fp64 accumulation.
+// grid.y splits the rows; partial sums are combined by sums_finish_kernel.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void col_sums_kernel(const T* __restrict__ base, const int64_t* __restrict__ row_off,
+                                const int64_t* __restrict__ col_off, int64_t n, int64_t p, double* partial) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p) return;
+  const int64_t per = (n + gridDim.y - 1) / gridDim.y;
+  const int64_t i0 = blockIdx.y * per, i1 = min(n, i0 + per);
+  const T* src = base + col_off[j];
+  double s = 0;
+  for (int64_t i = i0; i < i1; ++i) s += (double)src[row_off[i]];
+  partial[(int64_t)blockIdx.y * p + j] = s;
+}
+
+template <typename T>
+__global__ void sums_finish_kernel(const double* __restrict__ partial, int parts, int64_t p, double inv_n, int enabled,
+                                   T* mean_out, double* mean64) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p) return;
+  double s = 0;
+  for (int z = 0; z < parts; ++z) s += partial[(int64_t)z * p + j];
+  const double m = enabled ? s * inv_n : 0.0;
+  mean_out[j] = (T)m;
+  mean64[j] = m;
+}
+
+// G[i][j] -= n * mu_i * mu_j ;  XtY[j][f] -= n * mu_j * ybar_f    (centred moments from raw ones)
+template <typename T>
+__global__ void centre_moments_kernel(T* G, int64_t p, T* XtY, int F, const double* __restrict__ mu,
+                                      const double* __restrict__ ybar, double n) {
+  const int64_t totalG = p * p, total = totalG + p * F;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    if (e < totalG) {
+      const int64_t i = e / p, j = e - i * p;
+      G[e] = (T)((double)G[e] - n * mu[i] * mu[j]);
+    } else {
+      const int64_t q = e - totalG;
+      const int64_t j = q / F, f = q - j * F;
+      XtY[q] = (T)((double)XtY[q] - n * mu[j] * ybar[f]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One-sided (Hestenes) Jacobi eigensolver on the rows of a symmetric matrix, batched.
+//   B <- J^T B, Vt <- J^T Vt (Vt starts as I).  At convergence the rows of B are mutually orthogonal,
+//   B = Lambda Vt, so row k of Vt is an eigenvector and lambda_k = <B_k, Vt_k>.
+// One thread-block cluster per matrix; each round-robin step's p/2 disjoint row pairs are spread over
+// the warps of the cluster; cluster barriers separate steps.  Rows live in global memory (L2).
+// Replaces torch.linalg.svd / eigh of ridgecv.py:144,218 on the centred Gram.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024) jacobi_rows_kernel(T* Aall, T* Vall, T* lam_all, int p, int max_sweeps,
+                                                           double tol, unsigned int* counters, int cluster_size) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int mat = blockIdx.x / cluster_size;
+  T* B = Aall + (int64_t)mat * p * p;
+  T* V = Vall + (int64_t)mat * p * p;
+  T* lam = lam_all + (int64_t)mat * p;
+  unsigned int* cnt = counters + (int64_t)mat * max_sweeps;
+  const int warps_per_block = blockDim.x >> 5;
+  const int gw = crank * warps_per_block + (threadIdx.x >> 5);
+  const int nw = cluster_size * warps_per_block;
+  const int lane = threadIdx.x & 31;
+  const int m = p + (p & 1);
+
+  for (int64_t e = (int64_t)crank * blockDim.x + threadIdx.x; e < (int64_t)p * p; e += (int64_t)cluster_size * blockDim.x) {
+    const int64_t i = e / p, j = e - i * p;
+    V[e] = (i == j) ? (T)1 : (T)0;
+  }
+  __threadfence();
+  cluster.sync();
+
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    unsigned int my_rot = 0;
+    for (int step = 0; step < m - 1; ++step) {
+      for (int q = gw; q < m / 2; q += nw) {
+        int i, j;
+        if (q == 0) { i = m - 1; j = step; }
+        else { i = (step + q) % (m - 1); j = (step - q + (m - 1)) % (m - 1); }
+        if (i >= p || j >= p) continue;
+        T* bi = B + (int64_t)i * p; T* bj = B + (int64_t)j * p;
+        double aa = 0, bb = 0, gg = 0;
+        for (int k = lane; k < p; k += 32) {
+          const double x = (double)__ldcg(bi + k), y = (double)__ldcg(bj + k);
+          aa += x * x; bb += y * y; gg += x * y;
+        }
+        aa = warp_sum(aa); bb = warp_sum(bb); gg = warp_sum(gg);
+        if (aa * bb > 0.0 && fabs(gg) > tol * sqrt(aa * bb)) {
+          const double zeta = (bb - aa) / (2.0 * gg);
+          const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+          T* vi = V + (int64_t)i * p; T* vj = V + (int64_t)j * p;
+          for (int k = lane; k < p; k += 32) {
+            const double x = (double)__ldcg(bi + k), y = (double)__ldcg(bj + k);
+            __stcg(bi + k, (T)(c * x - s * y));
+            __stcg(bj + k, (T)(s * x + c * y));
+            const double u = (double)__ldcg(vi + k), w = (double)__ldcg(vj + k);
+            __stcg(vi + k, (T)(c * u - s * w));
+            __stcg(vj + k, (T)(s * u + c * w));
+          }
+          if (lane == 0) ++my_rot;
+        }
+      }
+      __threadfence();
+      cluster.sync();
+    }
+    if (lane == 0 && my_rot) atomicAdd(&cnt[sweep], my_rot);
+    __threadfence();
+    cluster.sync();
+    const unsigned int total = __ldcg(&cnt[sweep]);
+    if (total == 0) break;
+  }
+  for (int k = gw; k < p; k += nw) {
+    const T* bk = B + (int64_t)k * p; const T* vk = V + (int64_t)k * p;
+    double s = 0;
+    for (int c = lane; c < p; c += 32) s += (double)__ldcg(bk + c) * (double)__ldcg(vk + c);
+    s = warp_sum(s);
+    if (lane == 0) lam[k] = (T)(s > 0 ? s : 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LOO sweep pieces (ridgecv.py:230-251 restated in the primal basis; SURVEY.md section 8 a-note)
+// ------------------------------------------------------------------------------------------------
+// w[a][k] = 1 / (lam_k + alpha_a)
+template <typename T>
+__global__ void ridge_weights_kernel(const T* __restrict__ lam, const T* __restrict__ alphas, int A, int p, T* w) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)A * p; e += (int64_t)gridDim.x * blockDim.x) {
+    const int a = (int)(e / p), k = (int)(e - (int64_t)a * p);
+    w[e] = (T)(1.0 / ((double)lam[k] + (double)alphas[a]));
+  }
+}
+
+// theta_t[(a,f)][k] = w[a][k] * Vtb[k][f]
+template <typename T>
+__global__ void theta_kernel(const T* __restrict__ w, const T* __restrict__ Vtb, int A, int F, int p, T* theta_t) {
+  const int64_t total = (int64_t)A * F * p;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t af = e / p;
+    const int k = (int)(e - af * p);
+    const int a = (int)(af / F), f = (int)(af - (int64_t)a * F);
+    theta_t[e] = w[(int64_t)a * p + k] * Vtb[(int64_t)k * F + f];
+  }
+}
+
+// out[r] = sum_j M[r][j] * v[j]   (row-major M, one warp per row; fp64 v)
+template <typename T>
+__global__ void matvec_rows_kernel(const T* __restrict__ M, int64_t rows, int64_t cols, const double* __restrict__ v,
+                                   double* out) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  double s = 0;
+  for (int64_t j = lane; j < cols; j += 32) s += (double)M[r * cols + j] * v[j];
+  s = warp_sum(s);
+  if (lane == 0) out[r] = s;
+}
+
+// d[i][a] = 1 - c0 - sum_k (Z[i][k] - cz[k])^2 * w[a][k]
+// block: 64 rows x all alphas; K swept in slabs of 64 staged through shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256) leverage_kernel(const T* __restrict__ Z, int64_t n, int p, int64_t ldz,
+                                                       const double* __restrict__ cz, const T* __restrict__ w, int A,
+                                                       double c0, T* d) {
+  constexpr int RT = 64, KT = (sizeof(T) == 8) ? 32 : 64, AMAX = 32;
+  __shared__ T zs[RT][KT + 1];
+  __shared__ T ws[AMAX][KT];
+  const int64_t r0 = (int64_t)blockIdx.x * RT;
+  const int r = threadIdx.x & 63, ag = threadIdx.x >> 6;  // 4 alpha groups
+  for (int a0 = 0; a0 < A; a0 += AMAX) {
+    const int na = min(AMAX, A - a0);
+    double acc[AMAX / 4];
+#pragma unroll
+    for (int u = 0; u < AMAX / 4; ++u) acc[u] = 0;
+    for (int k0 = 0; k0 < p; k0 += KT) {
+      for (int e = threadIdx.x; e < RT * KT; e += 256) {
+        const int rr = e / KT, kk = e % KT;
+        const int64_t gi = r0 + rr; const int gk = k0 + kk;
+        T z = 0;
+        if (gi < n && gk < p) z = (T)((double)Z[gi * ldz + gk] - cz[gk]);
+        zs[rr][kk] = z * z;
+      }
+      for (int e = threadIdx.x; e < na * KT; e += 256) {
+        const int aa = e / KT, kk = e % KT;
+        const int gk = k0 + kk;
+        ws[aa][kk] = (gk < p) ? w[(int64_t)(a0 + aa) * p + gk] : (T)0;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < AMAX / 4; ++u) {
+        const int aa = ag + 4 * u;
+        if (aa < na) {
+          double s = 0;
+#pragma unroll 8
+          for (int kk = 0; kk < KT; ++kk) s += (double)(zs[r][kk] * ws[aa][kk]);
+          acc[u] += s;
+        }
+      }
+      __syncthreads();
+    }
+    if (r0 + r < n) {
+#pragma unroll
+      for (int u = 0; u < AMAX / 4; ++u) {
+        const int aa = ag + 4 * u;
+        if (aa < na) d[(r0 + r) * A + a0 + aa] = (T)(1.0 - c0 - acc[u]);
+      }
+    }
+  }
+}
+
+// loss partials: for column c=(a,f) and a slab of rows:
+//   e = (y[i][f] - ybar_f - R[i][c] + mb[c]) / d[i][a];   partial[slab][c] = sum_i e^2
+template <typename T>
+__global__ void __launch_bounds__(256) loo_loss_kernel(const T* __restrict__ R, int64_t n, int A, int F, int64_t ldr,
+                                                       const T* __restrict__ ybase, const int64_t* __restrict__ yrow_off,
+                                                       int64_t y_feat_stride, const double* __restrict__ ybar,
+                                                       const double* __restrict__ mb, const T* __restrict__ d,
+                                                       double* partial) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int AF = A * F;
+  const int64_t per = (n + gridDim.y - 1) / gridDim.y;
+  const int64_t i0 = blockIdx.y * per, i1 = min(n, i0 + per);
+  if (c >= AF) return;
+  const int a = c / F, f = c - a * F;
+  const double yb = ybar[f], m = mb[c];
+  const T* ycol = ybase + (int64_t)f * y_feat_stride;
+  double s = 0;
+  for (int64_t i = i0; i < i1; ++i) {
+    const double e = ((double)ycol[yrow_off[i]] - yb - (double)R[i * ldr + c] + m) / (double)d[i * A + a];
+    s += e * e;
+  }
+  partial[(int64_t)blockIdx.y * AF + c] = s;
+}
+
+// loss[a][f] = sum_slabs / n ; then first-minimum selection (ridgecv.py:253-256, 271-274);
+// single block.  per_target: best[f] = argmin_a loss[a][f]; else best[0] = argmin_a mean_f loss[a][f]
+template <typename T>
+__global__ void select_alpha_kernel(const double* __restrict__ partial, int slabs, int A, int F, double inv_n,
+                                    const T* __restrict__ alphas, int per_target, T* loss_out, int32_t* best,
+                                    T* alpha_out, double* loss64) {
+  const int AF = A * F;
+  for (int c = threadIdx.x; c < AF; c += blockDim.x) {
+    double s = 0;
+    for (int z = 0; z < slabs; ++z) s += partial[(int64_t)z * AF + c];
+    s *= inv_n;
+    loss64[c] = s;
+    if (loss_out) loss_out[c] = (T)s;
+  }
+  __syncthreads();
+  if (per_target) {
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+      int b = 0; T bv = (T)loss64[f];
+      for (int a = 1; a < A; ++a) {
+        const T v = (T)loss64[a * F + f];
+        if (v < bv) { bv = v; b = a; }
+      }
+      best[f] = b;
+      alpha_out[f] = alphas[b];
+    }
+  } else if (threadIdx.x == 0) {
+    int b = 0; T bv = 0;
+    for (int a = 0; a < A; ++a) {
+      // mean over targets in working precision T, like losses.mean(1) on a T tensor
+      double s = 0;
+      for (int f = 0; f < F; ++f) s += (double)(T)loss64[a * F + f];
+      const T v = (T)(s / F);
+      if (a == 0 || v < bv) { bv = v; b = a; }
+    }
+    best[0] = b;
+    alpha_out[0] = alphas[b];
+  }
+}
+
+// coef[f][j] = beta_all[(best_f, f)][j];  intercept[f] = ybar_f - mb[(best_f, f)]
+template <typename T>
+__global__ void gather_coef_kernel(const T* __restrict__ beta_all, int F, int64_t p, const int32_t* __restrict__ best,
+                                   int per_target, const double* __restrict__ ybar, const double* __restrict__ mb,
+                                   int fit_intercept, T* coef, T* intercept) {
+  const int64_t total = (int64_t)F * p;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(e / p);
+    const int64_t j = e - (int64_t)f * p;
+    const int a = per_target ? best[f] : best[0];
+    coef[e] = beta_all[((int64_t)a * F + f) * p + j];
+    if (j == 0) intercept[f] = fit_intercept ? (T)(ybar[f] - mb[(int64_t)a * F + f]) : (T)0;
+  }
+}
+
+// yhat[(s*F + f)*T + t] = P[(s*T + t)][f] + intercept[f]    (timedelayed.py:531-533 reshape/swapaxes)
+template <typename T>
+__global__ void predict_layout_kernel(const T* __restrict__ P, int64_t n_trials, int F, int Tn, int64_t ldp,
+                                      const T* __restrict__ intercept, T* yhat) {
+  __shared__ T tile[32][33];
+  const int s = blockIdx.z;
+  const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int t = t0 + j, f = f0 + threadIdx.x;
+    if (t < Tn && f < F) tile[j][threadIdx.x] = P[((int64_t)s * Tn + t) * ldp + f];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int f = f0 + j, t = t0 + threadIdx.x;
+    if (t < Tn && f < F) yhat[((int64_t)s * F + f) * Tn + t] = tile[threadIdx.x][j] + (intercept ? intercept[f] : (T)0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused scoring: y, yhat viewed as [R][K]; each thread owns one kept cell k and walks the R reduced
+// samples (coalesced across k).  One read of y / yhat per pass serves both metrics.
+//   r2      = 1 - sum (y - yhat)^2 / sum (y - y_b)^2, 0 where the denominator <= 0   (math/r2.py:92-100)
+//   pearson = sum dx dy / sqrt(sum dx^2 sum dy^2) with dx, dy centred                  (math/pearsonr.py:55-56)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void score_kernel(const T* __restrict__ y, const T* __restrict__ yh, const T* __restrict__ yb, int64_t R,
+                             int64_t K, T* r2, T* pr) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  double sy = 0, sh = 0;
+  for (int64_t r = 0; r < R; ++r) { sy += (double)y[r * K + k]; sh += (double)yh[r * K + k]; }
+  const T my = (T)(sy / R), mh = (T)(sh / R);
+  const T base = yb ? yb[k] : my;
+  double num = 0, den = 0, sxy = 0, sxx = 0, syy = 0;
+  for (int64_t r = 0; r < R; ++r) {
+    const T a = y[r * K + k], b = yh[r * K + k];
+    const T e = a - b, g = a - base, dx = a - my, dy = b - mh;
+    num += (double)(e * e); den += (double)(g * g);
+    sxy += (double)(dx * dy); sxx += (double)(dx * dx); syy += (double)(dy * dy);
+  }
+  if (r2) r2[k] = ((T)den > (T)0) ? (T)1 - (T)num / (T)den : (T)0;
+  if (pr) pr[k] = (T)sxy / (T)sqrt((double)((T)sxx * (T)syy));
+}
+
+}  // namespace mvb

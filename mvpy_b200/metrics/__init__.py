@@ -1,0 +1,6 @@
+from .metric import Metric
+from .r2 import R2, r2
+from .pearsonr import Pearsonr, pearsonr
+from .score import score, reduce_
+
+__all__ = ['Metric', 'R2', 'r2', 'Pearsonr', 'pearsonr', 'score', 'reduce_']
