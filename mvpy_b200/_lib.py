@@ -103,6 +103,15 @@ def to_device(x: torch.Tensor) -> torch.Tensor:
     return x.to(compute_device(), non_blocking=True)
 
 
+def stage(x: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Driver-level staging (Validator / Hierarchical / Shapley): host tensors go to the GPU once when one
+    is present.  Without a GPU the tensor is returned as is -- the drivers are pure host logic and stay
+    usable with user-supplied models; the CUDA estimators themselves still raise in ``to_device``."""
+    if x is None or x.is_cuda or not torch.cuda.is_available():
+        return x
+    return x.to(compute_device(), non_blocking=True)
+
+
 def dtype_code(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return F32

@@ -6,7 +6,7 @@ generator is restated here.  It draws from the global torch RNG in the same orde
 (``mvpy/dataset/make_meeg_continuous.py:16-197``: randint for stimulus frequencies, rand for
 background phases, one randperm per source for the sensor dipoles, randn for the innovations), so a
 given ``torch.manual_seed`` reproduces the reference's arrays on CPU (checked bit-for-bit by
-``oracle/gen_golden.py`` and ``tests/test_dataset.py``).
+``tests/test_host_logic.py`` against the reference's checksums).
 
 Model: ``n_background`` 1/f oscillatory sources plus ``n_features`` AR(1) stimulus series (active
 only in [t_baseline, t_baseline + t_duration)) are convolved with Hann-tapered sinusoidal response

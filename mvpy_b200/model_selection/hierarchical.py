@@ -1,0 +1,127 @@
+"""Hierarchical (all-subsets) predictor-set scoring -- drop-in for ``mvpy.model_selection.Hierarchical``
+(mvpy/model_selection/hierarchical.py:17-518).
+
+Host side: enumerate all non-empty unions of group rows in ``itertools.combinations`` order, drop
+duplicate masks keeping the first occurrence, run one full cross-validation per mask.  The (set)
+units are independent: under ``torch.distributed`` they are sharded over the GPUs and the scores
+all-gathered once (``_dist``)."""
+from __future__ import annotations
+
+import warnings
+from itertools import chain, combinations
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+
+from .. import _dist, _lib
+from ..crossvalidation import Validator
+from ..crossvalidation.validator import _move_tensors
+
+
+def prepare_groups_(X: torch.Tensor, groups, dim: Optional[int], on_underspecified: str = 'raise'):
+    """Shared argument handling (hierarchical.py:52-86, shapley.py:378-418): default feature dim (-2 for
+    3-D X, else -1), identity groups by default, list -> tensor, coverage check, bool mask."""
+    if dim is None:
+        dim = -2 if X.ndim > 2 else -1
+    if groups is None:
+        groups = torch.eye(X.shape[dim], dtype=torch.bool, device=X.device)
+    else:
+        if isinstance(groups, list):
+            groups = torch.tensor(groups, dtype=torch.long, device=X.device)
+        if groups.shape[1] != X.shape[dim]:
+            raise ValueError(f'Expected `groups` to be of shape (n_groups, n_features) matching n_features in `X`, '
+                             f'but got groups={groups.shape} and X={X.shape} with dim={dim}.')
+        if not (groups.sum(0) > 0).all():
+            if on_underspecified == 'warn':
+                warnings.warn(f'Supplied `groups` do not include all available predictors. Counted {groups.sum(0)} instances.')
+            elif on_underspecified != 'ignore':
+                raise ValueError('When supplying `groups`, each predictor must appear in at least one grouping.')
+        groups = groups.to(torch.bool)
+    return dim, groups
+
+
+def check_dims_and_groups_(X: torch.Tensor, y: torch.Tensor, groups=None, dim: Optional[int] = None,
+                           on_underspecified: str = 'raise'):
+    """-> (dim, group_ids, sets, masks); sets in combinations order by subset size, duplicate masks removed
+    keeping the first occurrence (hierarchical.py:88-131)."""
+    dim, groups = prepare_groups_(X, groups, dim, on_underspecified)
+    n_groups = groups.shape[0]
+    group_ids = list(range(n_groups))
+    sets, masks, seen = [], [], set()
+    g_host = groups.cpu()
+    for comb in chain.from_iterable(combinations(group_ids, r) for r in range(1, n_groups + 1)):
+        m = g_host[list(comb)].any(0)
+        key = tuple(m.tolist())
+        if key in seen:
+            continue
+        seen.add(key)
+        sets.append(comb)
+        masks.append(m)
+    masks = torch.stack(masks, dim=0).to(X.device)
+    return dim, group_ids, sets, masks, groups
+
+
+def fit_validator_(validator: Validator, X: torch.Tensor, y: torch.Tensor, mask: torch.Tensor, dim: int) -> Validator:
+    """One cross-validation on the predictors selected by ``mask`` (hierarchical.py:150-207)."""
+    X_i = torch.index_select(X, dim=dim, index=torch.nonzero(mask.to(X.device), as_tuple=False).squeeze(-1))
+    v = validator.clone()
+    v.fit(X_i, y)
+    return v
+
+
+def _stack_scores(scores: List, multi_names):
+    if multi_names is not None:
+        return {name: torch.stack([s[name] for s in scores], dim=0) for name in multi_names}
+    return torch.stack(scores, dim=0)
+
+
+class Hierarchical:
+    """Attributes: ``validator_`` (fitted per set; ``None`` if fitted on another rank), ``score_``
+    ((n_sets, n_folds, ...)), ``mask_, group_, group_id_, set_``."""
+
+    def __init__(self, validator: Validator, n_jobs: Optional[int] = None, verbose: Union[int, bool] = False,
+                 on_underspecified: str = 'raise'):
+        self.validator = validator
+        self.n_jobs = n_jobs
+        self.verbose = verbose
+        self.on_underspecified = on_underspecified
+        self.validator_ = []
+        self.score_ = []
+        self.mask_ = []
+        self.group_ = []
+        self.group_id_ = []
+        self.set_ = []
+
+    def fit(self, X: torch.Tensor, y: torch.Tensor, groups=None, dim: Optional[int] = None) -> 'Hierarchical':
+        if not (isinstance(X, torch.Tensor) and isinstance(y, torch.Tensor)):
+            raise ValueError(f'Both `X` and `y` must be of type torch.Tensor, but got {type(X)} and {type(y)}.')
+        dim, group_ids, sets, masks, groups = check_dims_and_groups_(X, y, groups=groups, dim=dim,
+                                                                     on_underspecified=self.on_underspecified)
+        out_dev = X.device
+        multi = [m.name for m in self.validator.metric] if (self.validator.metric is not None and len(self.validator.metric) > 1) else None
+        shard = _dist.sharding_active()
+        mine = set(_dist.my_units(len(masks))) if shard else set(range(len(masks)))
+        Xd, yd = _lib.stage(X), _lib.stage(y)          # one host->device copy for all sets
+        self.validator_, local = [], {}
+        with _dist.sharded_region():
+            for i, mask in enumerate(masks):
+                if i not in mine:
+                    self.validator_.append(None)
+                    continue
+                v = fit_validator_(self.validator, Xd, yd, mask, dim)
+                local[i] = v.score_
+                self.validator_.append(_move_tensors(v, out_dev) if Xd.device != out_dev else v)
+        if multi is not None:
+            self.score_ = {}
+            for name in multi:
+                per = {i: s[name] for i, s in local.items()}
+                per = _dist.gather_units(per, len(masks)) if shard else [per[i] for i in range(len(masks))]
+                self.score_[name] = torch.stack(per, dim=0).to(out_dev)
+        else:
+            per = _dist.gather_units(local, len(masks)) if shard else [local[i] for i in range(len(masks))]
+            self.score_ = torch.stack(per, dim=0).to(out_dev)
+        self.mask_ = [masks[i] for i in range(len(masks))]
+        self.set_ = list(sets)
+        self.group_ = groups
+        self.group_id_ = group_ids
+        return self

@@ -1,0 +1,20 @@
+"""``hierarchical_score`` -- same signature as mvpy/model_selection/hierarchical_score.py:12-153."""
+from typing import Any, List, Optional, Tuple, Union
+
+import torch
+
+from .. import metrics
+from ..crossvalidation import Validator
+from .hierarchical import Hierarchical
+
+
+def hierarchical_score(model, X: torch.Tensor, y: torch.Tensor, groups: Optional[Union[List, torch.Tensor]] = None,
+                       dim: Optional[int] = None, cv: Union[int, Any] = 5,
+                       metric: Optional[Union[metrics.Metric, Tuple[metrics.Metric]]] = None, return_hierarchical: bool = True,
+                       n_jobs: Optional[int] = None, n_jobs_validator: Optional[int] = None, verbose: Union[int, bool] = False,
+                       verbose_validator: Union[int, bool] = False):
+    validator = Validator(model, cv=cv, metric=metric, n_jobs=n_jobs_validator, verbose=verbose_validator)
+    hierarchical = Hierarchical(validator, n_jobs=n_jobs, verbose=verbose).fit(X, y, groups=groups, dim=dim)
+    if return_hierarchical:
+        return hierarchical, hierarchical.score_
+    return hierarchical.score_

@@ -1,0 +1,169 @@
+"""Host-side logic that needs no GPU: fold indices, lag windows, group enumeration, the metric protocol,
+driver argument handling.  Index-type outputs are compared bit-exactly with the reference's goldens."""
+import numpy as np
+import pytest
+import torch
+
+import mvpy_b200 as mv
+from mvpy_b200.estimators.timedelayed import lag_window
+from mvpy_b200.model_selection.hierarchical import check_dims_and_groups_
+
+T = torch.from_numpy
+
+
+def test_kfold_bit_exact(golden):
+    g = golden('kfold.npz')
+    for n, k in [(10, 5), (11, 3), (120, 5), (7, 7)]:
+        for i, (tr, te) in enumerate(mv.crossvalidation.KFold(n_splits=k).split(torch.zeros(n, 2))):
+            assert tr.dtype == torch.long and np.array_equal(tr.numpy(), g[f'n{n}k{k}_tr{i}'])
+            assert np.array_equal(te.numpy(), g[f'n{n}k{k}_te{i}'])
+    for n, k, seed in [(20, 4, 0), (23, 5, 123)]:
+        for i, (tr, te) in enumerate(mv.crossvalidation.KFold(n_splits=k, shuffle=True, random_state=seed).split(torch.zeros(n, 2))):
+            assert np.array_equal(tr.numpy(), g[f'n{n}k{k}s{seed}_tr{i}']) and np.array_equal(te.numpy(), g[f'n{n}k{k}s{seed}_te{i}'])
+    with pytest.raises(ValueError):
+        list(mv.crossvalidation.KFold(n_splits=5).split(torch.zeros(3, 2)))
+
+
+def test_lag_windows(golden):
+    g = golden('delay.npz')
+    assert np.array_equal(lag_window(-0.03, 0.02, 100), g['window'])
+    assert np.array_equal(lag_window(0.01, 0.03, 100), g['window2'])
+    assert np.array_equal(lag_window(-1.0, 0.0, 200), g['window_cfg1'])
+    td = mv.estimators.TimeDelayed(-1.0, 0.0, 200, alphas=torch.logspace(-5, 5, 20))
+    assert td.window.dtype == torch.int32 and td.window.shape == (201,) and int(td.window[0]) == -200
+
+
+def test_group_enumeration(golden):
+    g = golden('trf_small.npz')
+    X, y = torch.zeros(5, 4, 10), torch.zeros(5, 2, 10)
+    dim, ids, sets, masks, groups = check_dims_and_groups_(X, y)
+    assert dim == -2 and ids == [0, 1, 2, 3]
+    assert np.array_equal(masks.numpy(), g['hier_mask'])
+    assert [list(s) + [-1] * (4 - len(s)) for s in sets] == g['hier_sets'].tolist()
+    _, _, sets2, masks2, _ = check_dims_and_groups_(X, y, groups=g['groups'].tolist())
+    assert np.array_equal(masks2.numpy(), g['hier2_mask'])
+    assert [list(s) + [-1] * (3 - len(s)) for s in sets2] == g['hier2_sets'].tolist()
+    # cfg3 groups: baseline block in every row -> exactly 8 unique masks
+    gr = torch.zeros(4, 64, dtype=torch.long)
+    gr[:, :16] = 1
+    for r in range(1, 4):
+        gr[r, 16 * r:16 * (r + 1)] = 1
+    _, _, sets3, masks3, _ = check_dims_and_groups_(torch.zeros(2, 64, 3), torch.zeros(2, 1, 3), groups=gr)
+    assert len(sets3) == 8 and sets3 == [(0,), (1,), (2,), (3,), (1, 2), (1, 3), (2, 3), (1, 2, 3)]
+    assert masks3.sum(1).tolist() == [16, 32, 32, 32, 48, 48, 48, 64]
+    with pytest.raises(ValueError):
+        check_dims_and_groups_(X, y, groups=[[1, 0, 0, 0]])
+    with pytest.raises(ValueError):
+        check_dims_and_groups_(X, y, groups=[[1, 0, 0]])
+
+
+def test_metric_protocol():
+    m = mv.metrics.r2
+    assert m.name == 'r2' and m.request == ('y', 'predict', 'y_b') and m.reduce == (0,)
+    assert mv.metrics.pearsonr.request == ('y', 'predict')
+    m2 = m.mutate(reduce=(2,))
+    assert m2.reduce == (2,) and m.reduce == (0,) and m2.f is m.f
+    m3 = mv.metrics.Metric()
+    m3.grant({'a': 1})
+    m3.grant({'b': 2})
+    assert m3.metadata == {'a': 1, 'b': 2}
+    with pytest.raises(ValueError):
+        m3.grant([1])
+
+
+def test_reduce_is_a_view_for_leading_dims():
+    x = torch.arange(2 * 3 * 4.0).reshape(2, 3, 4)
+    r = mv.metrics.reduce_(x, (0,))
+    assert r.shape == (3, 4, 2) and r.data_ptr() == x.data_ptr()
+    assert torch.equal(r[1, 2], x[:, 1, 2])
+    assert mv.metrics.reduce_(x, (0, 2)).shape == (3, 8)
+    assert torch.equal(mv.metrics.reduce_(x, -1), x)
+    with pytest.raises(ValueError):
+        mv.metrics.reduce_(x, (0, 0))
+    with pytest.raises(ValueError):
+        mv.metrics.reduce_(x, (5,))
+
+
+class _MeanModel:
+    """tiny user model (CPU torch) to exercise the drivers without a GPU"""
+    metric_ = mv.metrics.Metric(name='mse', request=('y', 'predict'), reduce=(0,),
+                                f=lambda y, p: ((y - p) ** 2).mean(-1))
+
+    def fit(self, X, y):
+        self.m_ = y.mean(0, keepdim=True) + 0 * X.sum()
+        return self
+
+    def predict(self, X):
+        return self.m_.expand(X.shape[0], *self.m_.shape[1:])
+
+    def score(self, X, y):
+        return mv.metrics.score(self, self.metric_, X, y)
+
+    def clone(self):
+        return _MeanModel()
+
+
+def test_validator_driver_on_host_model():
+    X, y = torch.randn(20, 3), torch.randn(20, 2)
+    val, sc = mv.crossvalidation.cross_val_score(_MeanModel(), X, y, cv=4)
+    assert sc.shape == (4, 2) and len(val.model_) == 4 and len(val.test_) == 4
+    for k, (tr, te) in enumerate(mv.crossvalidation.KFold(4).split(X)):
+        assert torch.equal(val.test_[k], te)
+        np.testing.assert_allclose(sc[k].numpy(), ((y[te] - y[tr].mean(0)) ** 2).mean(0).numpy(), rtol=1e-6)
+    assert val.collect('m_').shape == (4, 1, 2)
+    with pytest.raises(ValueError):
+        mv.crossvalidation.Validator(object(), cv=3)
+    with pytest.raises(ValueError):
+        mv.crossvalidation.Validator(_MeanModel(), cv='nope')
+    with pytest.raises(ValueError):
+        mv.crossvalidation.Validator(_MeanModel()).collect('m_')
+    # a splitter with n_repeats multiplies cv_n_ (validator.py:310-313)
+    class Rep:
+        n_splits, n_repeats = 3, 2
+        def split(self, X, y=None):
+            return iter(())
+    assert mv.crossvalidation.Validator(_MeanModel(), cv=Rep()).cv_n_ == 6
+
+
+def test_hierarchical_and_shapley_drivers_on_host_model():
+    torch.manual_seed(3)
+    X, y = torch.randn(12, 4, 5), torch.randn(12, 2, 5)
+    h, hs = mv.model_selection.hierarchical_score(_MeanModel(), X, y, cv=3)
+    assert hs.shape == (15, 3, 2, 5) and len(h.set_) == 15 and h.group_.shape == (4, 4)
+    torch.manual_seed(5)
+    s, ss = mv.model_selection.shapley_score(_MeanModel(), X, y, groups=[[1, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], cv=3,
+                                             n_permutations=4)
+    assert ss.shape == (4, 3, 3, 2, 5) and s.order_.shape == (4, 2)
+    torch.manual_seed(5)                                     # RNG call order of the reference: perm then data, per permutation
+    for i in range(4):
+        perm = 1 + torch.randperm(2)
+        torch.randperm(12)
+        assert torch.equal(s.order_[i], perm)
+
+
+def test_sliding_and_dispatch_arguments():
+    est = mv.estimators.RidgeDecoder(alphas=torch.logspace(-1, 1, 3))
+    assert mv.estimators.Sliding(est, dims=-1).dims == (-1,)
+    assert mv.estimators.Sliding(est, dims=[1, 2]).dims == (1, 2)
+    assert mv.estimators.Sliding(est, dims=np.array([2])).dims == (2,)
+    with pytest.raises(ValueError):
+        mv.estimators.Sliding(est, dims='x')
+    with pytest.raises(ValueError):
+        mv.estimators.Sliding(3)
+    with pytest.raises(ValueError):
+        mv.estimators.RidgeCV(alphas=np.array([1.0]))
+    d = mv.estimators.RidgeDecoder(alphas=1.0, normalise=False)          # the keyword the reference trips over
+    assert d.alpha_per_target is True and d.fit_intercept is True
+    r = mv.estimators.RidgeCV(alphas=[0.1, 1.0])
+    assert isinstance(r.alphas, torch.Tensor) and r.clone().alpha_per_target is False
+    td = mv.estimators.TimeDelayed(-0.1, 0.0, 100, alphas=2.0, alpha_per_target=True)
+    assert td.estimator.alpha_per_target is True and td.clone().kwargs == {'alpha_per_target': True}
+
+
+def test_dataset_matches_reference_checksum(golden):
+    g = golden('cfg1_summary.npz')
+    torch.manual_seed(0)
+    X, y = mv.dataset.make_meeg_continuous(fs=200)
+    assert X.shape == (120, 3, 400) and y.shape == (120, 64, 400)
+    assert abs(float(X.double().sum()) - float(g['x_checksum'])) < 1e-9
+    assert abs(float(y.double().sum()) - float(g['y_checksum'])) < 1e-9
