@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- TRF ridge fits/s (folds x alphas x sets) of the cross-validated ridge hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg1] [--impl ours|reference]
+
+One step = one ``cross_val_score(make_pipeline(Scaler, TimeDelayed), X, y, cv=5)`` with 20 alphas
+(= 100 fits) on make_meeg_continuous-style synthetic data.  Default workload: BASELINE.json configs[1]
+(64 stimulus features x 306 channels, 1 s of lags at 200 Hz: n = 38 400 rows, p = 12 864 columns per fold).
+With N GPUs (torchrun, one rank per GPU) every rank runs its own trial-permuted cross-validation unit
+(the unit of shapley_score / hierarchical_score sharding; no data-path collective) and the score shards
+are all-gathered over NCCL at the end of each step: weak scaling, value = N * 100 fits / max-over-ranks time.
+
+JSON line (rank 0): metric/value/unit/... per the driver contract plus
+  roofline      dominant kernel (tcgen05 split-TF32 contraction): algorithmic FLOP/s achieved inside the timed
+                region (CUDA events on the launching stream, via the library's profiling hook) vs the measured
+                TF32 peak / 3 (three MMAs per fp32 product)
+  cpu_baseline  the oracle port of the reference's algorithm (materialised lag expansion + SVD) on the host cores,
+                bounded sample
+  e2e           same metric through the public API with pinned HOST tensors (h2d + d2h inside the timed region)
+``--impl reference`` times the CPU restatement of the reference (oracle/) on the host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_ALPHAS, N_FOLDS = 20, 5
+WORKLOADS = {
+    'cfg2': dict(n_features=64, n_channels=306, label='TimeDelayed TRF 64 features x 306 channels, 201 lags @200Hz, '
+                                                      'cross_val_score 5-fold x 20 alphas (BASELINE configs[1])'),
+    'cfg1': dict(n_features=3, n_channels=64, label='make_meeg_continuous(fs=200) + Scaler + TimeDelayed(-1,0), '
+                                                    '5-fold x 20 alphas (BASELINE configs[0])'),
+}
+
+
+def make_data(workload: str):
+    from mvpy_b200.dataset import make_meeg_continuous
+    cfg = WORKLOADS[workload]
+    torch.manual_seed(0)
+    X, y = make_meeg_continuous(fs=200, n_features=cfg['n_features'], n_channels=cfg['n_channels'])
+    return X.contiguous(), y.contiguous()
+
+
+def make_pipe(mv, alphas):
+    from sklearn.pipeline import make_pipeline
+    return make_pipeline(mv.preprocessing.Scaler().to_torch(), mv.estimators.TimeDelayed(-1.0, 0.0, 200, alphas=alphas))
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.index), '-lms', '200'], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith('active')})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------- CPU baseline
+def cpu_reference_sample(X, y, alphas, n_feat_sample: int, threads: int):
+    """One fold of the oracle's restatement of the reference algorithm (Scaler -> lag expansion -> SVD LOO ridge ->
+    predict -> r2) on a predictor subset; returns seconds."""
+    from oracle import mvpy_oracle as orc
+    torch.set_num_threads(threads)
+    Xs = X[:, :n_feat_sample].contiguous()
+    win = orc.lag_window(-1.0, 0.0, 200)
+    t0 = time.perf_counter()
+    orc.cross_val_trf(Xs, y, win, alphas, cv=N_FOLDS, folds=[0])
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(X, y, alphas, workload: str):
+    threads = os.cpu_count() or 1
+    C = X.shape[1]
+    n_s = C if workload == 'cfg1' else 8
+    sec = cpu_reference_sample(X, y, alphas, n_s, threads)
+    W = 201
+    n_rows = (X.shape[0] - X.shape[0] // N_FOLDS) * X.shape[2]
+    # the reference's cost is dominated by the thin SVD of the (n x p) design and the (A x n x p x f) dual products: ~ n p^2
+    scale = (C / n_s) ** 2
+    per_fold_full = sec * scale
+    value = N_ALPHAS / per_fold_full
+    sample = (f'1 of {N_FOLDS} folds, {n_s} of {C} stimulus features (p={n_s * W} of {C * W} columns, n={n_rows} rows, '
+              f'{y.shape[1]} channels, {N_ALPHAS} alphas) took {sec:.2f} s on {threads} threads = {N_ALPHAS / sec:.3f} fits/s; '
+              f'value extrapolates to the full column count with the n*p^2 cost law (x{scale:.0f})')
+    return dict(value=value, unit='fits/s', cores=threads, kind='port', sample=sample), sec
+
+
+# ------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=2)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--workload', default='cfg2', choices=list(WORKLOADS))
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    alphas = torch.logspace(-5, 5, N_ALPHAS)
+    cfg = WORKLOADS[args.workload]
+    config = dict(workload=cfg['label'], trials=120, features=cfg['n_features'], channels=cfg['n_channels'], timepoints=400,
+                  lags=201, alphas=N_ALPHAS, folds=N_FOLDS, units_per_step_per_gpu=1, parallelism=f'units-sharded x{args.gpus}',
+                  l2='inputs + per-fold operands (>=1.3 GB at cfg2) exceed the 126 MB L2; no explicit flush')
+    fits_per_unit = N_ALPHAS * N_FOLDS
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        X, y = make_data(args.workload)
+        steps = max(1, args.steps)
+        secs = []
+        for _ in range(min(args.warmup, 1)):
+            cpu_baseline(X, y, alphas, args.workload)
+        cb = None
+        for _ in range(steps):
+            cb, sec = cpu_baseline(X, y, alphas, args.workload)
+            secs.append(sec)
+        value = cb['value']
+        print(json.dumps(dict(metric='TRF ridge fits/s (folds x alphas x sets)', value=value, unit='fits/s', impl='reference',
+                              n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 1), ms_per_step=1e3 * float(np.mean(secs)),
+                              higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                              config=config, cpu_baseline=cb,
+                              e2e=dict(value=value, unit='fits/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return
+
+    import mvpy_b200 as mv
+    from mvpy_b200 import _lib
+    assert torch.cuda.is_available(), 'bench.py (impl=ours) needs a CUDA device: there is no CPU fallback'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    X, y = make_data(args.workload)
+    # every rank owns one unit per step: a trial-permuted cross-validation (the Shapley / hierarchical sharding unit)
+    g = torch.Generator().manual_seed(1000 + rank)
+    order = torch.randperm(X.shape[0], generator=g) if world > 1 else torch.arange(X.shape[0])
+    Xh, yh = X[order].contiguous().pin_memory(), y[order].contiguous().pin_memory()
+    Xd, yd = Xh.to(dev), yh.to(dev)
+    pipe = make_pipe(mv, alphas)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        _, sc = mv.crossvalidation.cross_val_score(pipe, Xd, yd, cv=N_FOLDS)
+        if world > 1:
+            out = torch.empty((world,) + tuple(sc.shape), dtype=sc.dtype, device=dev)
+            dist.all_gather_into_tensor(out, sc.contiguous())
+            return out
+        return sc
+
+    def step_host():
+        val, sc = mv.crossvalidation.cross_val_score(pipe, Xh, yh, cv=N_FOLDS)      # h2d inside, results back on host
+        return val, sc
+
+    # ---- TF32 peak on this box (cuBLAS, allow_tf32), measured like MEASURED_PEAKS.json's bf16 figure ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    torch.backends.cuda.matmul.allow_tf32 = True
+    a = torch.randn(8192, 8192, device=dev)
+    b = torch.randn(8192, 8192, device=dev)
+    best = 1e9
+    for i in range(12):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+        if i >= 2:
+            best = min(best, e0.elapsed_time(e1))
+    tf32_peak = 2 * 8192 ** 3 / best * 1e-9
+    torch.backends.cuda.matmul.allow_tf32 = False
+    del a, b
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    _lib.profile_reset()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step_device()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - n0
+    prof = _lib.profile_read()
+    clk = clocks.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * fits_per_unit / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the public API with host tensors ----
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        val, sc_h = step_host()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_s = (time.perf_counter() - t0) / max(1, args.steps)
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    d2h = sc_h.numel() * sc_h.element_size()
+    for m in val.model_:
+        td = m[-1]
+        d2h += td.estimator.coef_.numel() * 4 + td.estimator.intercept_.numel() * 4 + m[0].mean_.numel() * 8
+    e2e = dict(value=world * fits_per_unit / e2e_s, unit='fits/s', h2d_bytes_per_step=int(Xh.numel() * 4 + yh.numel() * 4),
+               d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * e2e_s)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the tcgen05 contraction), from the library's CUDA-event hook ----
+    peak_eff = tf32_peak / 3.0
+    roof = None
+    if prof:
+        top = max(prof.items(), key=lambda kv: kv[1]['ms'])
+        name, r = top
+        achieved = r['flops'] / (r['ms'] * 1e-3) * 1e-12 if r['ms'] > 0 else 0.0
+        roof = dict(bound='tensor', kernel=f'tc_gemm_kernel [{name}]', achieved=achieved, peak=peak_eff, unit='TFLOP/s',
+                    frac=achieved / peak_eff, traffic=None, launches=r['n'], ms_total=r['ms'],
+                    share_of_step=r['ms'] / ms,
+                    note=f'algorithmic 2*M*N*K flops / CUDA-event time; peak = TF32 dense peak measured here with cuBLAS '
+                         f'({tf32_peak:.0f} TFLOP/s) / 3 MMAs per fp32 product (split-TF32); MEASURED_PEAKS bf16 = '
+                         f'{peaks.get("bf16_tflops")} burst / {peaks.get("bf16_tflops_sustained")} sustained',
+                    by_kernel={k: dict(ms=v['ms'], n=v['n'], tflops=(v['flops'] / (v['ms'] * 1e-3) * 1e-12 if v['ms'] > 0 else 0.0),
+                                       frac=(v['flops'] / (v['ms'] * 1e-3) * 1e-12 / peak_eff if v['ms'] > 0 else 0.0))
+                               for k, v in prof.items()})
+    cb = None
+    if not args.no_cpu_baseline:
+        cb, _ = cpu_baseline(X, y, alphas, args.workload)
+    line = dict(metric='TRF ridge fits/s (folds x alphas x sets)', value=value, unit='fits/s', n_gpus=world, steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f32', data='synthetic', config=config, clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roof,
+                cpu_baseline=cb)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

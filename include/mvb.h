@@ -38,6 +38,18 @@ const char* mvb_last_error(void);
 /* number of kernels launched by this library in the calling process (all threads) */
 int64_t mvb_launch_count(void);
 
+/* ---- measurement hook ----------------------------------------------------------------------------
+ * Off by default.  After mvb_profile_reset() every tensor-core contraction launch is bracketed by CUDA
+ * events on its own stream (at most 512 timed launches per kernel class; the rest are only counted).
+ * mvb_profile_read synchronises those events and reports, per class c < n_classes: timed milliseconds,
+ * algorithmic flops (2*M*N*K) of the timed launches, flops of all launches, #timed and #all launches.
+ * Used by bench.py for the roofline line; mvb_profile_disable() turns the hook off again.            */
+void mvb_profile_reset(void);
+void mvb_profile_disable(void);
+int mvb_profile_read(double* ms_timed, double* flops_timed, double* flops_all, int64_t* n_timed, int64_t* n_all,
+                     int max_classes);
+const char* mvb_profile_name(int cls);
+
 /* ---- Scaler ------------------------------------------------------------------------------------
  * replaces _Scaler_torch.fit / transform / inverse_transform  (preprocessing/scaler.py:301-428).
  * X is viewed as [R][K]: R = product of the reduced dims (moved first), K = kept elements.

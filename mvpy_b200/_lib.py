@@ -39,6 +39,11 @@ _SIGNATURES = {
     'mvb_version': (c_int, []),
     'mvb_last_error': (c_char_p, []),
     'mvb_launch_count': (c_int64, []),
+    'mvb_profile_reset': (None, []),
+    'mvb_profile_disable': (None, []),
+    'mvb_profile_read': (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double),
+                                 POINTER(c_int64), POINTER(c_int64), c_int]),
+    'mvb_profile_name': (c_char_p, [c_int]),
     'mvb_scaler_fit': (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'mvb_scaler_apply': (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'mvb_trf_pad': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -86,6 +91,30 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(load().mvb_launch_count())
+
+
+def profile_reset() -> None:
+    load().mvb_profile_reset()
+
+
+def profile_read(disable: bool = True) -> dict:
+    """Per kernel class: ms / flops / n are ESTIMATES for all launches of the class (timed subset scaled by flops),
+    plus the raw timed figures.  Synchronises the recorded events."""
+    lib = load()
+    nc = 16
+    ms, ft, fa = (ctypes.c_double * nc)(), (ctypes.c_double * nc)(), (ctypes.c_double * nc)()
+    nt, na = (c_int64 * nc)(), (c_int64 * nc)()
+    n = lib.mvb_profile_read(ms, ft, fa, nt, na, nc)
+    out = {}
+    for c in range(n):
+        if na[c] == 0:
+            continue
+        scale = fa[c] / ft[c] if ft[c] > 0 else 0.0
+        out[lib.mvb_profile_name(c).decode()] = dict(ms=ms[c] * scale, flops=fa[c], n=int(na[c]), ms_timed=ms[c],
+                                                     flops_timed=ft[c], n_timed=int(nt[c]))
+    if disable:
+        lib.mvb_profile_disable()
+    return out
 
 
 # ------------------------------------------------------------------------------------------- helpers

@@ -1,6 +1,7 @@
 // mvb_api.cu -- the C-ABI of libmvb.so (include/mvb.h): argument checking, workspace carving and
 // the kernel sequences of the ridge hot path.  No allocation, no synchronisation, no host fallback.
 #include <atomic>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -9,6 +10,7 @@
 #include "../../include/mvb.h"
 #include "mvb_kernels.cuh"
 #include "tc_gemm.cuh"
+#include "jacobi_block.cuh"
 
 namespace {
 
@@ -37,6 +39,52 @@ int fail(int code, const char* fmt, ...) {
     if (e__ != cudaSuccess)                                                              \
       return fail(MVB_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
+
+// ---- measurement hook (include/mvb.h) ------------------------------------------------------------------
+enum ProfClass { PC_GRAM = 0, PC_XTY, PC_SMALL, PC_LEVERAGE_Z, PC_RESIDUAL, PC_PREDICT, PC_EIG_GRAM, PC_EIG_APPLY,
+                 PC_EIG_REFRESH, PC_OTHER, PC_COUNT };
+const char* kProfNames[PC_COUNT] = {"gram X^T X (implicit Toeplitz)", "X^T y", "V^T b / beta (dense)", "Z = X V (leverages)",
+                                    "R = X beta (LOO residuals)", "predict X coef", "eig: pair Gram", "eig: rotate rows",
+                                    "eig: refresh (Vt Vt^T, Vt G)", "other"};
+constexpr int kProfMaxTimed = 512;
+struct ProfState {
+  bool on = false;
+  std::mutex mu;
+  cudaEvent_t ev[PC_COUNT][kProfMaxTimed][2];
+  bool created[PC_COUNT][kProfMaxTimed] = {};
+  int n_timed[PC_COUNT] = {};
+  int64_t n_all[PC_COUNT] = {};
+  double flops_timed[PC_COUNT] = {}, flops_all[PC_COUNT] = {};
+} g_prof;
+thread_local int g_prof_class = PC_OTHER;
+struct ProfScope {
+  int prev;
+  explicit ProfScope(int c) : prev(g_prof_class) { g_prof_class = c; }
+  ~ProfScope() { g_prof_class = prev; }
+};
+
+// returns slot (>=0) if this launch is timed; records the start event
+int prof_begin(double flops, cudaStream_t st) {
+  if (!g_prof.on) return -1;
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  const int c = g_prof_class;
+  g_prof.n_all[c]++;
+  g_prof.flops_all[c] += flops;
+  if (g_prof.n_timed[c] >= kProfMaxTimed) return -1;
+  const int slot = g_prof.n_timed[c]++;
+  if (!g_prof.created[c][slot]) {
+    cudaEventCreate(&g_prof.ev[c][slot][0]);
+    cudaEventCreate(&g_prof.ev[c][slot][1]);
+    g_prof.created[c][slot] = true;
+  }
+  g_prof.flops_timed[c] += flops;
+  cudaEventRecord(g_prof.ev[c][slot][0], st);
+  return slot;
+}
+void prof_end(int slot, cudaStream_t st) {
+  if (slot < 0) return;
+  cudaEventRecord(g_prof.ev[g_prof_class][slot][1], st);
+}
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
@@ -105,11 +153,13 @@ int run_contract(const mvb_operand& A, const mvb_operand& B, int M, int N, int K
   }
   const bool tc = (dtype == MVB_F32) && !force_simt();
   if (tc) {
-    mvb::TcGemmParams p;
+    mvb::TcGemmParams p = mvb::tc_gemm_defaults();
     p.A = {(const float*)A.base, A.roff, A.koff, A.rows, A.contig};
     p.B = {(const float*)B.base, B.roff, B.koff, B.rows, B.contig};
     p.M = M; p.N = N; p.K = K; p.C = (float*)out; p.ldc = ld; p.c_split_stride = stride; p.symmetric = symmetric; p.dbg = 0;
+    const int slot = prof_begin(2.0 * M * (double)N * K * (symmetric ? 0.5 : 1.0), st);
     MVB_CUDA(mvb::tc_gemm_launch(p, pl.splits, N > 128 ? 256 : 128, st));
+    prof_end(slot, st);
     g_launches.fetch_add(1, std::memory_order_relaxed);
   } else {
     mvb::GOp<T> a{(const T*)A.base, A.roff, A.koff, A.rows}, b{(const T*)B.base, B.roff, B.koff, B.rows};
@@ -189,9 +239,10 @@ int trf_stats_impl(const mvb_design* d, const T* y, int F, int fit_intercept, T*
   }
   mvb_operand xc{d->xp, w.col_off, w.row_off, (int)p, 1};
   mvb_operand yc{y, w.ycol_off, w.yrow_off, F, 1};
-  int rc = run_contract<T>(xc, xc, (int)p, (int)p, (int)n, G, p, 1, w.contract_ws, w.contract_bytes, st);
+  int rc;
+  { ProfScope ps(PC_GRAM); rc = run_contract<T>(xc, xc, (int)p, (int)p, (int)n, G, p, 1, w.contract_ws, w.contract_bytes, st); }
   if (rc) return rc;
-  rc = run_contract<T>(xc, yc, (int)p, F, (int)n, XtY, F, 0, w.contract_ws, w.contract_bytes, st);
+  { ProfScope ps(PC_XTY); rc = run_contract<T>(xc, yc, (int)p, F, (int)n, XtY, F, 0, w.contract_ws, w.contract_bytes, st); }
   if (rc) return rc;
   if (fit_intercept) {
     mvb::centre_moments_kernel<T><<<grid_for(p * p + p * F), 256, 0, st>>>(G, p, XtY, F, w.mu64, w.ybar64, (double)n);
@@ -202,12 +253,33 @@ int trf_stats_impl(const mvb_design* d, const T* y, int F, int fit_intercept, T*
 
 // ---- eigensolver -------------------------------------------------------------------------------------
 constexpr int kMaxSweeps = 40;
+constexpr int kBlockJacobiMinP = 160;   // fp32 problems at least this large go to the tensor-core block Jacobi
+
+inline bool use_block_jacobi(int p, int dtype) { return dtype == MVB_F32 && p >= kBlockJacobiMinP && !force_simt(); }
+
+size_t eigh_ws_bytes(int batch, int p, int dtype) {
+  size_t b = (size_t)batch * kMaxSweeps * sizeof(unsigned int) + 256;
+  if (use_block_jacobi(p, dtype)) b = std::max(b, mvb::bj::make_plan(p).bytes);
+  return b;
+}
 
 template <typename T>
 int eigh_impl(T* A, T* Vt, T* lam, int batch, int p, void* ws, size_t ws_bytes, cudaStream_t st) {
-  const size_t need = (size_t)batch * kMaxSweeps * sizeof(unsigned int);
+  constexpr int dtype = sizeof(T) == 4 ? MVB_F32 : MVB_F64;
+  const size_t need = eigh_ws_bytes(batch, p, dtype);
   if (ws_bytes < need) return fail(MVB_E_WORKSPACE, "eigh: workspace %zu < %zu", ws_bytes, need);
-  MVB_CUDA(cudaMemsetAsync(ws, 0, need, st));
+  if (use_block_jacobi(p, dtype)) {
+    for (int b = 0; b < batch; ++b) {
+      cudaError_t err = cudaSuccess;
+      mvb::bj::Hooks hooks{[](int cls, double flops, cudaStream_t s_) { g_prof_class = PC_EIG_GRAM + cls; return prof_begin(flops, s_); },
+                           [](int slot, cudaStream_t s_) { prof_end(slot, s_); g_prof_class = PC_OTHER; }};
+      const int n = mvb::bj::solve((const float*)A + (size_t)b * p * p, (float*)Vt + (size_t)b * p * p, (float*)lam + (size_t)b * p, p, ws, st, &err, &hooks);
+      if (n < 0) return fail(MVB_E_CUDA, "block Jacobi eigensolver failed: %s", cudaGetErrorString(err));
+      g_launches.fetch_add(n, std::memory_order_relaxed);
+    }
+    return MVB_OK;
+  }
+  MVB_CUDA(cudaMemsetAsync(ws, 0, (size_t)batch * kMaxSweeps * sizeof(unsigned int), st));
   int cluster = 1;
   if (p > 96) cluster = 8;
   int threads = p <= 64 ? 256 : 1024;
@@ -263,7 +335,7 @@ void carve_solve(Arena& ar, const mvb_design* d, int F, int A, SolveWs& w) {
   w.mb = ar.take<double>(AF);
   w.loss_partial = ar.take<double>((size_t)w.slabs * AF);
   w.loss64 = ar.take<double>(AF);
-  w.eig_bytes = (size_t)kMaxSweeps * sizeof(unsigned int);
+  w.eig_bytes = eigh_ws_bytes(1, (int)p, dt);
   w.eig_ws = ar.take<char>(w.eig_bytes);
   size_t cb = 0;
   cb = std::max(cb, plan_contract((int)p, F, (int)p, dt, 0).ws_elems);
@@ -319,14 +391,14 @@ int ridge_solve_impl(const mvb_design* d, const T* y, int F, T* G, const T* XtY,
   mvb::iota_offsets_kernel<<<grid_for(p), 256, 0, st>>>(w.iota_F, p, F);     // j * F
   MVB_LAUNCHED();
   mvb_operand opXtYt{XtY, w.iota_1, w.iota_F, F, 0};                       // rows f (contiguous), contraction j (stride F)
-  rc = run_contract<T>(opVt, opXtYt, (int)p, F, (int)p, Vtb, F, 0, w.contract_ws, w.contract_bytes, st);
+  { ProfScope ps(PC_SMALL); rc = run_contract<T>(opVt, opXtYt, (int)p, F, (int)p, Vtb, F, 0, w.contract_ws, w.contract_bytes, st); }
   if (rc) return rc;
   // 4. theta_t[(a,f)][k] = w[a][k] Vtb[k][f];  beta_all[(a,f)][j] = sum_k theta_t[(a,f)][k] Vt[k][j]
   mvb::theta_kernel<T><<<grid_for(AF * p), 256, 0, st>>>(wt, Vtb, A, F, (int)p, theta);
   MVB_LAUNCHED();
   mvb_operand opTheta{theta, w.iota_p, w.iota_1, (int)AF, dense_mode(p, (int)p, theta, sizeof(T))};
   mvb_operand opVcols{Vt, w.iota_1, w.iota_p, (int)p, 0};                  // rows j (contiguous), contraction k (stride p)
-  rc = run_contract<T>(opTheta, opVcols, (int)AF, (int)p, (int)p, beta, p, 0, w.contract_ws, w.contract_bytes, st);
+  { ProfScope ps(PC_SMALL); rc = run_contract<T>(opTheta, opVcols, (int)AF, (int)p, (int)p, beta, p, 0, w.contract_ws, w.contract_bytes, st); }
   if (rc) return rc;
   // 5. centring terms: cz[k] = <Vt[k], mu>,  mb[(a,f)] = <beta_all[(a,f)], mu>
   mvb::matvec_rows_kernel<T><<<cdiv(p * 32, 256), 256, 0, st>>>(Vt, p, p, w.mu64, w.cz);
@@ -335,13 +407,13 @@ int ridge_solve_impl(const mvb_design* d, const T* y, int F, T* G, const T* XtY,
   MVB_LAUNCHED();
   // 6. Z = X_t V  (implicit design rows x eigenvectors), leverages -> d = 1 - h - c0
   mvb_operand opRows{d->xp, w.row_off, w.col_off, (int)n, 0};              // rows i (t contiguous), contraction j
-  rc = run_contract<T>(opRows, opVt, (int)n, (int)p, (int)p, ZR, p, 0, w.contract_ws, w.contract_bytes, st);
+  { ProfScope ps(PC_LEVERAGE_Z); rc = run_contract<T>(opRows, opVt, (int)n, (int)p, (int)p, ZR, p, 0, w.contract_ws, w.contract_bytes, st); }
   if (rc) return rc;
   mvb::leverage_kernel<T><<<cdiv(n, 64), 256, 0, st>>>(ZR, n, (int)p, p, w.cz, wt, A, fit_intercept ? 1.0 / (double)n : 0.0, dd);
   MVB_LAUNCHED();
   // 7. fitted values for every (alpha, target): R = X_t beta_all^T
   mvb_operand opBeta{beta, w.iota_p, w.iota_1, (int)AF, dense_mode(p, (int)p, beta, sizeof(T))};
-  rc = run_contract<T>(opRows, opBeta, (int)n, (int)AF, (int)p, ZR, AF, 0, w.contract_ws, w.contract_bytes, st);
+  { ProfScope ps(PC_RESIDUAL); rc = run_contract<T>(opRows, opBeta, (int)n, (int)AF, (int)p, ZR, AF, 0, w.contract_ws, w.contract_bytes, st); }
   if (rc) return rc;
   // 8. LOO losses, alpha selection, coefficients
   {
@@ -382,7 +454,8 @@ int predict_impl(const mvb_design* d, const T* coef, const T* intercept, int F, 
   MVB_LAUNCHED();
   mvb_operand opRows{d->xp, row_off, col_off, (int)n, 0};
   mvb_operand opCoef{coef, iota_p, iota_1, F, dense_mode(p, (int)p, coef, sizeof(T))};
-  int rc = run_contract<T>(opRows, opCoef, (int)n, F, (int)p, P, F, 0, cws, cb, st);
+  int rc;
+  { ProfScope ps(PC_PREDICT); rc = run_contract<T>(opRows, opCoef, (int)n, F, (int)p, P, F, 0, cws, cb, st); }
   if (rc) return rc;
   dim3 grid(cdiv(d->n_time, 32), cdiv(F, 32), d->n_trials), block(32, 8);
   mvb::predict_layout_kernel<T><<<grid, block, 0, st>>>(P, d->n_trials, F, d->n_time, F, intercept, yhat);
@@ -398,6 +471,28 @@ extern "C" {
 int mvb_version(void) { return 100; }
 const char* mvb_last_error(void) { return g_err; }
 int64_t mvb_launch_count(void) { return g_launches.load(); }
+
+void mvb_profile_reset(void) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  for (int c = 0; c < PC_COUNT; ++c) { g_prof.n_timed[c] = 0; g_prof.n_all[c] = 0; g_prof.flops_timed[c] = 0; g_prof.flops_all[c] = 0; }
+  g_prof.on = true;
+}
+void mvb_profile_disable(void) { g_prof.on = false; }
+int mvb_profile_read(double* ms_timed, double* flops_timed, double* flops_all, int64_t* n_timed, int64_t* n_all, int max_classes) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  const int nc = max_classes < PC_COUNT ? max_classes : PC_COUNT;
+  for (int c = 0; c < nc; ++c) {
+    double ms = 0;
+    for (int i = 0; i < g_prof.n_timed[c]; ++i) {
+      float t = 0.f;
+      if (cudaEventSynchronize(g_prof.ev[c][i][1]) == cudaSuccess && cudaEventElapsedTime(&t, g_prof.ev[c][i][0], g_prof.ev[c][i][1]) == cudaSuccess) ms += t;
+    }
+    ms_timed[c] = ms; flops_timed[c] = g_prof.flops_timed[c]; flops_all[c] = g_prof.flops_all[c];
+    n_timed[c] = g_prof.n_timed[c]; n_all[c] = g_prof.n_all[c];
+  }
+  return nc;
+}
+const char* mvb_profile_name(int cls) { return (cls >= 0 && cls < PC_COUNT) ? kProfNames[cls] : ""; }
 
 int mvb_scaler_fit(const void* X, int64_t R, int64_t K, int dtype, void* mean, void* var, void* scale, void* stream) {
   if (!X || !mean || !var || !scale || R < 1 || K < 1) return fail(MVB_E_ARG, "scaler_fit: bad argument");
@@ -476,10 +571,7 @@ int mvb_trf_stats(const mvb_design* d, const void* y, int n_targets, int fit_int
   return trf_stats_impl<double>(d, (const double*)y, n_targets, fit_intercept, (double*)G, (double*)XtY, (double*)mu, (double*)ybar, ws, ws_bytes, st);
 }
 
-size_t mvb_eigh_workspace_bytes(int batch, int p, int dtype) {
-  (void)p; (void)dtype;
-  return (size_t)batch * kMaxSweeps * sizeof(unsigned int) + 256;
-}
+size_t mvb_eigh_workspace_bytes(int batch, int p, int dtype) { return eigh_ws_bytes(batch, p, dtype); }
 
 int mvb_eigh(void* A, void* Vt, void* lam, int batch, int p, int dtype, void* ws, size_t ws_bytes, void* stream) {
   if (!A || !Vt || !lam || batch < 1 || p < 1 || !ws) return fail(MVB_E_ARG, "eigh: bad argument");

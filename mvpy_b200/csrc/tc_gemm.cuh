@@ -43,7 +43,20 @@ struct TcGemmParams {
   int64_t c_split_stride;
   int symmetric;          // 1: A==B; tiles strictly above the diagonal are skipped and mirrored
   int dbg;                // profiling only: 1 = skip operand staging, 2 = skip MMA issue (results invalid)
+  // ---- batching (independent problems in one launch; blockIdx.z = batch * splits + split) ----
+  int batch;                          // >= 1
+  int64_t a_roff_batch, b_roff_batch; // per-batch stride (in entries) into the roff tables, 0 = shared
+  int64_t a_koff_batch, b_koff_batch; // same for the koff tables
+  int64_t c_batch_stride;             // per-batch offset of C (elements), used when c_roff == nullptr
+  const int64_t* c_roff;              // optional [batch][M] element offsets of the output rows
+  const unsigned int* skip_flag;      // optional: the whole launch is a no-op when *skip_flag != 0
 };
+
+inline TcGemmParams tc_gemm_defaults() {
+  TcGemmParams p{};
+  p.batch = 1;
+  return p;
+}
 
 namespace tc {
 
@@ -255,6 +268,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
   const int m0 = blockIdx.y * BM;
   const int n0 = blockIdx.x * BN;
   if (p.symmetric && n0 > m0 + BM - 1) return;  // strictly above the diagonal: mirrored by the lower tile
+  if (p.skip_flag && *p.skip_flag) return;
+  const int splits = gridDim.z / p.batch;
+  const int batch_id = blockIdx.z / splits, split_id = blockIdx.z - batch_id * splits;
+  GatherOperand opA = p.A, opB = p.B;
+  opA.roff += batch_id * p.a_roff_batch; opA.koff += batch_id * p.a_koff_batch;
+  opB.roff += batch_id * p.b_roff_batch; opB.koff += batch_id * p.b_koff_batch;
 
   uint8_t* stage_base[2] = {smem, smem + C_::STAGE};
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::BAR_OFF);  // [0],[1]: buffer free; [2]: all MMAs done
@@ -277,8 +296,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int r = threadIdx.x; r < BM + BN; r += NTHREADS) {
-    if (r < BM) sroffA[r] = (m0 + r < p.A.rows) ? p.A.roff[m0 + r] : 0;
-    else sroffB[r - BM] = (n0 + r - BM < p.B.rows) ? p.B.roff[n0 + r - BM] : 0;
+    if (r < BM) sroffA[r] = (m0 + r < opA.rows) ? opA.roff[m0 + r] : 0;
+    else sroffB[r - BM] = (n0 + r - BM < opB.rows) ? opB.roff[n0 + r - BM] : 0;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -287,17 +306,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
 
   // K range of this split
   const int nkb_total = (p.K + BK - 1) / BK;
-  const int splits = gridDim.z;
   const int kb_per = (nkb_total + splits - 1) / splits;
-  const int kb_begin = blockIdx.z * kb_per;
+  const int kb_begin = split_id * kb_per;
   const int kb_end = min(nkb_total, kb_begin + kb_per);
   const int nkb = max(0, kb_end - kb_begin);
 
   Loader<BM, A_MODE> la;
   Loader<BN, B_MODE> lb;
   if (nkb > 0) {
-    la.fetch(p.A, sroffA, m0, kb_begin * BK, p.K);
-    lb.fetch(p.B, sroffB, n0, kb_begin * BK, p.K);
+    la.fetch(opA, sroffA, m0, kb_begin * BK, p.K);
+    lb.fetch(opB, sroffB, n0, kb_begin * BK, p.K);
   }
   constexpr int NACC = BN / 2;                 // columns per thread: warps 0-3 low half, 4-7 high half
   const int q = warp & 3;                      // TMEM lane quarter this warp may access
@@ -339,8 +357,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
       if (chunk_last) mma_commit(smem_u32(&bars[2]));
     }
     if (it + 1 < nkb && p.dbg != 1) {  // next stage's global loads fly while this stage's MMAs run
-      la.fetch(p.A, sroffA, m0, (kb_begin + it + 1) * BK, p.K);
-      lb.fetch(p.B, sroffB, n0, (kb_begin + it + 1) * BK, p.K);
+      la.fetch(opA, sroffA, m0, (kb_begin + it + 1) * BK, p.K);
+      lb.fetch(opB, sroffB, n0, (kb_begin + it + 1) * BK, p.K);
     }
     if (chunk_last) {
       mbar_wait(smem_u32(&bars[2]), (uint32_t)(n_drained & 1));
@@ -362,13 +380,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
   // ---- epilogue: register accumulators -> global ------------------------------------------------
   {
     const int gm = m0 + q * 32 + lane;
-    float* Cz = p.C + (int64_t)blockIdx.z * p.c_split_stride;
+    float* Cz = p.C + (int64_t)split_id * p.c_split_stride;
+    const int64_t crow_off = (gm < p.M) ? (p.c_roff ? p.c_roff[(int64_t)batch_id * p.M + gm]
+                                                     : (int64_t)batch_id * p.c_batch_stride + (int64_t)gm * p.ldc)
+                                        : 0;
     if (gm < p.M) {
 #pragma unroll
       for (int cc = 0; cc < NACC / 32; ++cc) {
         const int c0 = col_half * NACC + cc * 32;
         if (n0 + c0 < p.N) {
-          float* crow = Cz + (int64_t)gm * p.ldc + n0 + c0;
+          float* crow = Cz + crow_off + n0 + c0;
           const int nvalid = min(32, p.N - (n0 + c0));
           if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
 #pragma unroll
@@ -408,7 +429,7 @@ inline cudaError_t launch_variant(const TcGemmParams& p, int k_splits, cudaStrea
   cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, AM, BMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg<BN>::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, k_splits);
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, k_splits * (p.batch > 0 ? p.batch : 1));
   tc_gemm_kernel<BN, AM, BMODE><<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, st>>>(p);
   return cudaGetLastError();
 }

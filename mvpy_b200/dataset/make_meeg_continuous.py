@@ -116,8 +116,17 @@ def make_meeg_continuous(n_trials: int = 120, n_channels: int = 64, t_padding: f
     n_fft = 1 << (Sp.shape[-1] + 1).bit_length()
     FS = torch.fft.rfft(Sp, n=n_fft, dim=-1)
     FB = torch.fft.rfft(beta, n=n_fft, dim=-1)
-    y = torch.stack([torch.fft.irfft(FS[:, i, ...] * FB[:, i, None, ...], n=n_fft, dim=-1)[..., :S.shape[-1]]
-                     for i in range(n_src)], dim=0).sum(0).swapaxes(0, 1)
+    n_keep = S.shape[-1]
+    if n_src * n_trials * n_channels * n_keep * 4 <= (2 << 30):
+        y = torch.stack([torch.fft.irfft(FS[:, i, ...] * FB[:, i, None, ...], n=n_fft, dim=-1)[..., :n_keep]
+                         for i in range(n_src)], dim=0).sum(0).swapaxes(0, 1)
+    else:
+        # same sum, accumulated source by source: the stacked form needs n_src x the output size in RAM
+        # (~10 GB at 306 channels, ~91 GB at config 5 -- SURVEY.md section 8d)
+        y = torch.zeros((n_channels, n_trials, n_keep), device=device)
+        for i in range(n_src):
+            y += torch.fft.irfft(FS[:, i, ...] * FB[:, i, None, ...], n=n_fft, dim=-1)[..., :n_keep]
+        y = y.swapaxes(0, 1)
     y = y / y.std()
 
     X = S[:, n_background:, s_pad:]

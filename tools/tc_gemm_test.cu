@@ -44,7 +44,7 @@ static double run_case(const char* name, const HostOp& A, const HostOp& B, int M
   size_t csz = (size_t)M * N;
   CK(cudaMalloc(&dC, csz * splits * sizeof(float)));
   CK(cudaMemset(dC, 0xFF, csz * splits * sizeof(float)));  // NaN fill: unwritten cells show up
-  mvb::TcGemmParams p;
+  mvb::TcGemmParams p = mvb::tc_gemm_defaults();
   p.A = {dA, dAr, dAk, M, A.lanes_along_k};
   p.B = {dB, dBr, dBk, N, B.lanes_along_k};
   p.M = M; p.N = N; p.K = K; p.C = dC; p.ldc = N; p.c_split_stride = (int64_t)csz; p.symmetric = symmetric; p.dbg = 0;
@@ -139,7 +139,7 @@ int main(int argc, char** argv) {
       float* dA = to_dev(A.base); int64_t* dAr = to_dev(A.roff); int64_t* dAk = to_dev(A.koff);
       float* dB = to_dev(B.base); int64_t* dBr = to_dev(B.roff); int64_t* dBk = to_dev(B.koff);
       float* dC; CK(cudaMalloc(&dC, (size_t)M * N * 4));
-      mvb::TcGemmParams p;
+      mvb::TcGemmParams p = mvb::tc_gemm_defaults();
       p.A = {dA, dAr, dAk, M, A.lanes_along_k}; p.B = {dB, dBr, dBk, N, B.lanes_along_k};
       p.M = M; p.N = N; p.K = K; p.C = dC; p.ldc = N; p.c_split_stride = 0; p.symmetric = 0;
       for (int dbg = 0; dbg < 3; ++dbg)
