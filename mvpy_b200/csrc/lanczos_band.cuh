@@ -1,0 +1,277 @@
+// lanczos_band.cuh -- orthogonal reduction of the centred Gram to block-tridiagonal form on the tensor cores.
+//
+//   Gp = Qt^T T Qt,   Qt orthogonal (rows = basis vectors),  T block tridiagonal with 128 x 128 blocks.
+//
+// Why: the LOO sweep needs (G + alpha I)^-1 applied to every design row for the whole alpha grid
+// (mvpy/estimators/ridgecv.py:230-251).  The reference gets that from a full SVD; any orthogonal Q with banded
+// Q^T G Q serves equally well -- (G + aI)^-1 = Q (T + aI)^-1 Q^T, and block-tridiagonal systems are solved by a
+// block Cholesky recurrence -- and costs ~6 p^3 tensor-core flops instead of an eigensolver.
+//
+// Method: block Lanczos with full re-orthogonalisation (block Arnoldi on a symmetric matrix), block size 128:
+//   W = Q_j G;  H = W Q_{0..j}^T (its last two blocks ARE T_jj and T_{j,j-1});  W -= H Q_{0..j} (twice);
+//   Q_{j+1} = orthonormalised rows of W (SVQB: eigendecomposition of the 128 x 128 Gram W W^T, twice).
+// Because every new block is orthonormal, orthogonal to all previous blocks and spans the residual W, T is block
+// tridiagonal for any such choice -- rank-deficient residuals simply get noise directions, which is still a valid
+// orthogonal completion.  Every step is a launch of the split-TF32 tcgen05 contraction core (tc_gemm.cuh) or a
+// small helper kernel; nothing synchronises with the host.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tc_gemm.cuh"
+#include "jacobi_block.cuh"   // small_eig_kernel (128 x 128 symmetric eigensolver in shared memory)
+
+namespace mvb {
+namespace lb {
+
+constexpr int NB = 128;   // block size (= one MMA M tile, = small_eig size)
+static_assert(NB == bj::PR, "block size must match the shared-memory eigensolver");
+
+struct Plan {
+  int p, P, nblk;
+  size_t bytes;
+  size_t off_Gp, off_Wt, off_Wt2, off_H, off_S, off_J, off_M, off_lam, off_rowP, off_row128, off_iota, off_part, off_ctl;
+  size_t part_elems;
+};
+
+inline Plan make_plan(int p) {
+  Plan pl{};
+  pl.p = p;
+  pl.nblk = (p + NB - 1) / NB;
+  if (pl.nblk < 1) pl.nblk = 1;
+  pl.P = pl.nblk * NB;
+  const size_t P = pl.P;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { off = (off + 255) / 256 * 256; size_t o = off; off += bytes; return o; };
+  pl.off_Gp = take(P * P * 4);
+  pl.off_Wt = take(NB * P * 4);
+  pl.off_Wt2 = take(NB * P * 4);
+  pl.off_H = take(NB * P * 4);
+  pl.off_S = take(NB * NB * 4);
+  pl.off_J = take(NB * NB * 4);
+  pl.off_M = take(NB * NB * 4);
+  pl.off_lam = take(NB * 4);
+  pl.off_rowP = take(P * 8);
+  pl.off_row128 = take(NB * 8);
+  pl.off_iota = take(P * 8);
+  pl.part_elems = (size_t)64 * NB * (P > 4096 ? 4096 : P);     // split-K partials (see gemm())
+  if (pl.part_elems < (size_t)8 * NB * P) pl.part_elems = (size_t)8 * NB * P;
+  pl.off_part = take(pl.part_elems * 4);
+  pl.off_ctl = take(sizeof(bj::Ctl));
+  pl.bytes = off + 256;
+  return pl;
+}
+
+// Gp = [[G, 0], [0, diag(pad)]], pad entries distinct and of the scale of G's diagonal
+__global__ void pad_gram_kernel(const float* __restrict__ G, int p, int P, float* Gp, const float* diag_scale) {
+  const int64_t total = (int64_t)P * P;
+  const float g0 = fabsf(diag_scale[0]) > 0.f ? fabsf(diag_scale[0]) : 1.f;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / P, c = e - r * P;
+    float v = 0.f;
+    if (r < p && c < p) v = G[r * p + c];
+    else if (r == c) v = g0 * (1.f + 0.01f * (float)(r - p));
+    Gp[e] = v;
+  }
+}
+
+// mean of G's diagonal (single block)
+__global__ void diag_mean_kernel(const float* __restrict__ G, int p, float* out) {
+  __shared__ float red[256];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < p; i += blockDim.x) s += G[(int64_t)i * p + i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) out[0] = red[0] / (float)p;
+}
+
+__global__ void tables_kernel(int P, int64_t* rowP, int64_t* row128, int64_t* iota) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+    rowP[i] = (int64_t)i * P; iota[i] = i;
+    if (i < NB) row128[i] = (int64_t)i * NB;
+  }
+}
+
+// deterministic pseudo-random start block (hash of the element index), uniform in (-1, 1)
+__global__ void random_block_kernel(float* W, int64_t n, uint32_t seed) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t x = (uint32_t)e * 2654435761u + seed;
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    W[e] = (float)(x >> 8) * (2.0f / 16777216.0f) - 1.0f;
+  }
+}
+
+__global__ void sub_kernel(float* __restrict__ W, const float* __restrict__ W2, int64_t n) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) W[e] -= W2[e];
+}
+
+// out[z-sum] : reduce split-K partials (fixed order)
+__global__ void reduce_parts_kernel(const float* __restrict__ part, int splits, int64_t stride, int M, int N, float* out, int64_t ldo) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = e / N, n = e - m * N;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[z * stride + e];
+    out[m * ldo + n] = s;
+  }
+}
+
+// eigenvalues of the sorted small-eig output: lam_r = J_r S J_r^T ; Mmat = diag(lam^-1/2) J  (SVQB scaling)
+__global__ void svqb_scale_kernel(const float* __restrict__ S, const float* __restrict__ J, float* Mmat, float* lam_out) {
+  __shared__ float lam[NB];
+  __shared__ float lmax;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < NB; r += blockDim.x / 32) {
+    // lam_r = sum_c J[r][c] * (S J_r)[c]
+    float acc = 0.f;
+    for (int c = lane; c < NB; c += 32) {
+      float t = 0.f;
+      for (int k = 0; k < NB; ++k) t += S[c * NB + k] * J[r * NB + k];
+      acc += J[r * NB + c] * t;
+    }
+    acc = bj::wsum(acc);
+    if (lane == 0) lam[r] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { float m = 0.f; for (int r = 0; r < NB; ++r) m = fmaxf(m, lam[r]); lmax = m; }
+  __syncthreads();
+  const float floor_ = fmaxf(lmax * 1e-12f, 1e-36f);
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    const int r = e / NB;
+    Mmat[e] = J[e] * rsqrtf(fmaxf(lam[r], floor_));
+  }
+  if (lam_out) for (int r = threadIdx.x; r < NB; r += blockDim.x) lam_out[r] = lam[r];
+}
+
+// T blocks out of the first H of iteration j: Tdiag[j] = sym(H[:, j]), Tsub[j] = H[:, j-1]
+__global__ void extract_T_kernel(const float* __restrict__ H, int P, int j, float* Tdiag, float* Tsub) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < NB * NB; e += gridDim.x * blockDim.x) {
+    const int r = e / NB, c = e % NB;
+    Tdiag[(int64_t)j * NB * NB + e] = 0.5f * (H[(int64_t)r * P + j * NB + c] + H[(int64_t)c * P + j * NB + r]);
+    if (j > 0) Tsub[(int64_t)j * NB * NB + e] = H[(int64_t)r * P + (j - 1) * NB + c];
+  }
+}
+
+struct Ctx {
+  Plan pl; char* base; cudaStream_t st; int launches; cudaError_t err;
+  const bj::Hooks* hooks;
+  float* f(size_t off) const { return (float*)(base + off); }
+  int64_t* i64(size_t off) const { return (int64_t*)(base + off); }
+};
+
+// C[M x N] (ld ldc) = A(M x K) * B(N x K)^T with automatic split-K for skinny outputs
+inline bool gemm(Ctx& cx, const GatherOperand& A, const GatherOperand& B, int M, int N, int K, float* C, int64_t ldc) {
+  const int bn = N > 128 ? 256 : 128;
+  const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
+  int splits = 1;
+  if (tiles < 148) splits = (148 + tiles - 1) / tiles;
+  const int kchunks = (K + 32 * tc::DRAIN - 1) / (32 * tc::DRAIN);
+  if (splits > kchunks) splits = kchunks;
+  if (splits > 64) splits = 64;
+  while (splits > 1 && (size_t)splits * M * N > cx.pl.part_elems) --splits;
+  TcGemmParams g = tc_gemm_defaults();
+  g.A = A; g.B = B; g.M = M; g.N = N; g.K = K;
+  if (splits > 1) { g.C = cx.f(cx.pl.off_part); g.ldc = N; g.c_split_stride = (int64_t)M * N; }
+  else { g.C = C; g.ldc = ldc; }
+  const int slot = cx.hooks ? cx.hooks->begin(2, 2.0 * M * (double)N * K, cx.st) : -1;
+  cx.err = tc_gemm_launch(g, splits, bn, cx.st);
+  if (cx.hooks) cx.hooks->end(slot, cx.st);
+  ++cx.launches;
+  if (cx.err != cudaSuccess) return false;
+  if (splits > 1) {
+    reduce_parts_kernel<<<148 * 4, 256, 0, cx.st>>>(cx.f(cx.pl.off_part), splits, (int64_t)M * N, M, N, C, ldc);
+    ++cx.launches;
+  }
+  return true;
+}
+
+// Orthonormalise the 128 rows of `src` (ld P) into `dst` (ld P):  dst = diag(lam^-1/2) J src,  J,lam = eig(src src^T)
+inline bool svqb(Ctx& cx, const float* src, float* dst) {
+  const Plan& pl = cx.pl;
+  const int P = pl.P;
+  int64_t *rowP = cx.i64(pl.off_rowP), *row128 = cx.i64(pl.off_row128), *iota = cx.i64(pl.off_iota);
+  float *S = cx.f(pl.off_S), *J = cx.f(pl.off_J), *Mm = cx.f(pl.off_M);
+  bj::Ctl* ctl = (bj::Ctl*)(cx.base + pl.off_ctl);
+  GatherOperand a{src, rowP, iota, NB, 2};
+  if (!gemm(cx, a, a, NB, NB, P, S, NB)) return false;
+  bj::small_eig_kernel<<<1, 1024, bj::SMALL_EIG_SMEM, cx.st>>>(S, J, 1e-7f, 1.f, 10, ctl, 0); ++cx.launches;
+  svqb_scale_kernel<<<1, 1024, 0, cx.st>>>(S, J, Mm, nullptr); ++cx.launches;
+  GatherOperand m{Mm, row128, iota, NB, 2};
+  GatherOperand w{src, iota, rowP, P, 0};          // rows = columns c of src, contraction over its 128 rows
+  return gemm(cx, m, w, NB, P, NB, dst, P);
+}
+
+// W (128 x P) -= (W Q^T) Q  against the first nq rows of Qt
+inline bool reorth(Ctx& cx, float* W, const float* Qt, int nq) {
+  const Plan& pl = cx.pl;
+  const int P = pl.P;
+  int64_t *rowP = cx.i64(pl.off_rowP), *iota = cx.i64(pl.off_iota);
+  float *H = cx.f(pl.off_H), *W2 = cx.f(pl.off_Wt2);
+  GatherOperand w{W, rowP, iota, NB, 2}, q{Qt, rowP, iota, nq, 2};
+  if (!gemm(cx, w, q, NB, nq, P, H, P)) return false;
+  GatherOperand h{H, rowP, iota, NB, 2}, qc{Qt, iota, rowP, P, 0};
+  if (!gemm(cx, h, qc, NB, P, nq, W2, P)) return false;
+  sub_kernel<<<148 * 2, 256, 0, cx.st>>>(W, W2, (int64_t)NB * P); ++cx.launches;
+  return true;
+}
+
+// Enqueue the reduction.  G: p x p.  Outputs: Qt (P x P), Tdiag / Tsub ([nblk][128][128]; Tsub[j] = T_{j,j-1}).
+// Returns #launches or -1 (err set).
+inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, void* ws, cudaStream_t st, cudaError_t* err,
+                  const bj::Hooks* hooks = nullptr) {
+  Ctx cx{make_plan(p), (char*)ws, st, 0, cudaSuccess, hooks};
+  const Plan& pl = cx.pl;
+  const int P = pl.P, nb = pl.nblk;
+  float *Gp = cx.f(pl.off_Gp), *Wt = cx.f(pl.off_Wt), *H = cx.f(pl.off_H);
+  int64_t *rowP = cx.i64(pl.off_rowP), *row128 = cx.i64(pl.off_row128), *iota = cx.i64(pl.off_iota);
+  bj::Ctl* ctl = (bj::Ctl*)(cx.base + pl.off_ctl);
+#define LB_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { *err = e_; return -1; } } while (0)
+#define LB_OK(x) do { if (!(x)) { *err = cx.err; return -1; } } while (0)
+  static bool attr_set = false;
+  if (!attr_set) {
+    LB_CK(cudaFuncSetAttribute(bj::small_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bj::SMALL_EIG_SMEM));
+    attr_set = true;
+  }
+  LB_CK(cudaMemsetAsync(ctl, 0, sizeof(bj::Ctl), st));
+  tables_kernel<<<64, 256, 0, st>>>(P, rowP, row128, iota); ++cx.launches;
+  diag_mean_kernel<<<1, 256, 0, st>>>(G, p, cx.f(pl.off_lam)); ++cx.launches;
+  pad_gram_kernel<<<148 * 8, 256, 0, st>>>(G, p, P, Gp, cx.f(pl.off_lam)); ++cx.launches;
+  // Q_0: orthonormalised pseudo-random block
+  random_block_kernel<<<148 * 2, 256, 0, st>>>(Wt, (int64_t)NB * P, 0x9e3779b9u); ++cx.launches;
+  LB_OK(svqb(cx, Wt, Qt));
+  LB_OK(svqb(cx, Qt, Wt));
+  LB_CK(cudaMemcpyAsync(Qt, Wt, (size_t)NB * P * 4, cudaMemcpyDeviceToDevice, st));
+  for (int j = 0; j < nb; ++j) {
+    const float* Qj = Qt + (size_t)j * NB * P;
+    // W = Q_j Gp ;  H = W Q_{0..j}^T  -> T_jj, T_{j,j-1}
+    GatherOperand qj{Qj, rowP, iota, NB, 2}, g{Gp, rowP, iota, P, 2};
+    LB_OK(gemm(cx, qj, g, NB, P, P, Wt, P));
+    const int nq = (j + 1) * NB;
+    {
+      GatherOperand w{Wt, rowP, iota, NB, 2}, q{Qt, rowP, iota, nq, 2};
+      LB_OK(gemm(cx, w, q, NB, nq, P, H, P));
+      extract_T_kernel<<<16, 256, 0, st>>>(H, P, j, Tdiag, Tsub); ++cx.launches;
+    }
+    if (j == nb - 1) break;
+    // full re-orthogonalisation (twice), reusing the H just computed for the first pass
+    {
+      float* W2 = cx.f(pl.off_Wt2);
+      GatherOperand h{H, rowP, iota, NB, 2}, qc{Qt, iota, rowP, P, 0};
+      LB_OK(gemm(cx, h, qc, NB, P, nq, W2, P));
+      sub_kernel<<<148 * 2, 256, 0, st>>>(Wt, W2, (int64_t)NB * P); ++cx.launches;
+    }
+    LB_OK(reorth(cx, Wt, Qt, nq));
+    float* Qn = Qt + (size_t)(j + 1) * NB * P;
+    LB_OK(svqb(cx, Wt, Qn));
+    LB_OK(reorth(cx, Qn, Qt, nq));
+    LB_OK(svqb(cx, Qn, Wt));
+    LB_CK(cudaMemcpyAsync(Qn, Wt, (size_t)NB * P * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  LB_CK(cudaGetLastError());
+#undef LB_CK
+#undef LB_OK
+  return cx.launches;
+}
+
+}  // namespace lb
+}  // namespace mvb

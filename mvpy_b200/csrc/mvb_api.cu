@@ -11,6 +11,8 @@
 #include "mvb_kernels.cuh"
 #include "tc_gemm.cuh"
 #include "jacobi_block.cuh"
+#include "lanczos_band.cuh"
+#include "band_loo.cuh"
 
 namespace {
 
@@ -45,7 +47,7 @@ enum ProfClass { PC_GRAM = 0, PC_XTY, PC_SMALL, PC_LEVERAGE_Z, PC_RESIDUAL, PC_P
                  PC_EIG_REFRESH, PC_OTHER, PC_COUNT };
 const char* kProfNames[PC_COUNT] = {"gram X^T X (implicit Toeplitz)", "X^T y", "V^T b / beta (dense)", "Z = X V (leverages)",
                                     "R = X beta (LOO residuals)", "predict X coef", "eig: pair Gram", "eig: rotate rows",
-                                    "eig: refresh (Vt Vt^T, Vt G)", "other"};
+                                    "eig refresh / band reduction (block Lanczos)", "other"};
 constexpr int kProfMaxTimed = 512;
 struct ProfState {
   bool on = false;
@@ -351,6 +353,250 @@ __global__ void to_double_kernel(const T* __restrict__ in, int64_t n, double* ou
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (double)in[i];
 }
 
+
+// ---- band path: block-tridiagonal reduction + block-Cholesky LOO sweep (fp32, large p) ---------------------
+int band_min_p() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MVB_BAND_MIN_P");
+    v = e ? atoi(e) : 1024;
+    if (v < 128) v = 128;
+  }
+  return v;
+}
+inline bool use_band(int64_t p, int dtype) { return dtype == MVB_F32 && p >= band_min_p() && !force_simt(); }
+
+struct BandWs {
+  int64_t *row_off, *col_off, *yrow_off, *iota, *rowP, *tab128, *rowUb, *iota_F, *iota_p;
+  float *Qt, *Tdiag, *Tsub, *Minv, *Nmat, *Pb, *Z, *h, *U0, *U1, *C1, *C2, *Ct, *Ub, *Xb, *beta, *dd;
+  double *mu64, *ybar64, *cz, *mb, *loss_partial, *loss64;
+  void* lanczos_ws; void* contract_ws; size_t contract_bytes;
+  int slabs, P, nb;
+};
+
+void carve_band(Arena& ar, const mvb_design* d, int F, int A, BandWs& w) {
+  const int64_t n = (int64_t)d->n_trials * d->n_time, p = (int64_t)d->n_feat * d->n_lag;
+  const int64_t AF = (int64_t)A * F;
+  const mvb::lb::Plan lp = mvb::lb::make_plan((int)p);
+  const int64_t P = lp.P, nb = lp.nblk;
+  w.P = (int)P; w.nb = (int)nb;
+  w.slabs = (int)std::min<int64_t>(128, std::max<int64_t>(1, n / 128));
+  const int64_t rows_max = std::max<int64_t>(n, F);
+  w.row_off = ar.take<int64_t>(n);
+  w.col_off = ar.take<int64_t>(p);
+  w.yrow_off = ar.take<int64_t>(n);
+  w.iota = ar.take<int64_t>(std::max<int64_t>(P, AF) + 256);
+  w.rowP = ar.take<int64_t>(std::max<int64_t>(std::max<int64_t>(P, n), AF));
+  w.tab128 = ar.take<int64_t>(std::max<int64_t>((int64_t)A * nb * 128, (int64_t)A * rows_max));
+  w.rowUb = ar.take<int64_t>(AF);
+  w.iota_F = ar.take<int64_t>(p);
+  w.iota_p = ar.take<int64_t>(std::max<int64_t>(p, AF));
+  w.Qt = ar.take<float>(P * P);
+  w.Tdiag = ar.take<float>(nb * 128 * 128);
+  w.Tsub = ar.take<float>(nb * 128 * 128);
+  w.Minv = ar.take<float>((int64_t)A * nb * 128 * 128);
+  w.Nmat = ar.take<float>((int64_t)A * nb * 128 * 128);
+  w.Pb = ar.take<float>((int64_t)A * nb * 128 * 128);
+  w.Z = ar.take<float>(n * std::max<int64_t>(P, AF));
+  w.h = ar.take<float>((int64_t)A * n);
+  w.U0 = ar.take<float>((int64_t)A * rows_max * 128);
+  w.U1 = ar.take<float>((int64_t)A * rows_max * 128);
+  w.C1 = ar.take<float>((int64_t)A * rows_max * 128);
+  w.C2 = ar.take<float>((int64_t)A * rows_max * 128);
+  w.Ct = ar.take<float>((int64_t)F * P);
+  w.Ub = ar.take<float>(AF * P);
+  w.Xb = ar.take<float>(AF * P);
+  w.beta = ar.take<float>(AF * p);
+  w.dd = ar.take<float>(n * A);
+  w.mu64 = ar.take<double>(P);
+  w.ybar64 = ar.take<double>(F);
+  w.cz = ar.take<double>(P);
+  w.mb = ar.take<double>(AF);
+  w.loss_partial = ar.take<double>((size_t)w.slabs * AF);
+  w.loss64 = ar.take<double>(AF);
+  w.lanczos_ws = ar.take<char>(lp.bytes);
+  size_t cb = 0;
+  cb = std::max(cb, plan_contract((int)F, (int)P, (int)p, MVB_F32, 0).ws_elems);
+  cb = std::max(cb, plan_contract((int)AF, (int)p, (int)P, MVB_F32, 0).ws_elems);
+  cb = std::max(cb, plan_contract((int)n, (int)P, (int)p, MVB_F32, 0).ws_elems);
+  cb = std::max(cb, plan_contract((int)n, (int)AF, (int)p, MVB_F32, 0).ws_elems);
+  w.contract_bytes = cb * 4;
+  w.contract_ws = ar.take<char>(w.contract_bytes);
+}
+
+__global__ void sub_cols_kernel(float* __restrict__ Z, int64_t rows, int64_t cols, const double* __restrict__ c) {
+  const int64_t total = rows * cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    Z[e] = (float)((double)Z[e] - c[e % cols]);
+}
+__global__ void pad_double_kernel(const float* __restrict__ in, int64_t n_in, int64_t n_out, double* out) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_out; e += (int64_t)gridDim.x * blockDim.x)
+    out[e] = e < n_in ? (double)in[e] : 0.0;
+}
+// d[i][a] = 1 - c0 - h[a][i]
+__global__ void leverage_to_d_kernel(const float* __restrict__ h, int64_t n, int A, float c0, float* d) {
+  const int64_t total = n * A;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / A; const int a = (int)(e - i * A);
+    d[e] = 1.f - c0 - h[(int64_t)a * n + i];
+  }
+}
+
+// batched (over alpha) 128-wide contraction  C[a][r][0..128) = sum_c Aop(a; r, c) * Bop(a; *, c)
+int band_gemm(const mvb::GatherOperand& A, int64_t a_roff_batch, const mvb::GatherOperand& B, int64_t b_roff_batch,
+              int64_t b_koff_batch, int rows, int batch, float* C, int cls, cudaStream_t st) {
+  mvb::TcGemmParams g = mvb::tc_gemm_defaults();
+  g.A = A; g.B = B; g.M = rows; g.N = 128; g.K = 128; g.C = C; g.ldc = 128; g.batch = batch;
+  g.a_roff_batch = a_roff_batch; g.b_roff_batch = b_roff_batch; g.b_koff_batch = b_koff_batch;
+  g.c_batch_stride = (int64_t)rows * 128;
+  g_prof_class = cls;
+  const int slot = prof_begin(2.0 * rows * 128.0 * 128.0 * batch, st);
+  MVB_CUDA(mvb::tc_gemm_launch(g, 1, 128, st));
+  prof_end(slot, st);
+  g_prof_class = PC_OTHER;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return MVB_OK;
+}
+
+int ridge_solve_band(const mvb_design* d, const float* y, int F, float* G, const float* XtY, const float* mu, const float* ybar,
+                     const float* alphas, int A, int fit_intercept, int per_target, float* coef, float* intercept,
+                     float* alpha_out, int32_t* best, float* loss, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int64_t n = (int64_t)d->n_trials * d->n_time, p = (int64_t)d->n_feat * d->n_lag;
+  const int64_t AF = (int64_t)A * F;
+  const int Tn = d->n_time;
+  Arena ar(ws, ws_bytes);
+  BandWs w;
+  carve_band(ar, d, F, A, w);
+  if (!ar.ok()) return fail(MVB_E_WORKSPACE, "ridge_solve(band): workspace %zu < %zu", ws_bytes, ar.off);
+  const int64_t P = w.P, nb = w.nb;
+  const int64_t rows_max = std::max<int64_t>(n, F);
+
+  mvb::design_offsets_kernel<<<grid_for(n + p), 256, 0, st>>>(d->trial_idx, d->n_trials, Tn, d->trial_stride, d->feat_idx,
+                                                            d->n_feat, d->n_lag, d->feat_stride, (int64_t)F * Tn,
+                                                            w.row_off, w.col_off, w.yrow_off);
+  MVB_LAUNCHED();
+  const int64_t n_iota = std::max<int64_t>(P, AF) + 256;
+  mvb::iota_offsets_kernel<<<grid_for(n_iota), 256, 0, st>>>(w.iota, n_iota, 1);                 MVB_LAUNCHED();
+  const int64_t n_rowP = std::max<int64_t>(std::max<int64_t>(P, n), AF);
+  mvb::iota_offsets_kernel<<<grid_for(n_rowP), 256, 0, st>>>(w.rowP, n_rowP, P);                 MVB_LAUNCHED();   // e * P
+  const int64_t n_tab = std::max<int64_t>((int64_t)A * nb * 128, (int64_t)A * rows_max);
+  mvb::iota_offsets_kernel<<<grid_for(n_tab), 256, 0, st>>>(w.tab128, n_tab, 128);               MVB_LAUNCHED();   // e * 128
+  mvb::iota_offsets_kernel<<<grid_for(p), 256, 0, st>>>(w.iota_F, p, F);                         MVB_LAUNCHED();   // j * F
+  const int64_t n_ip = std::max<int64_t>(p, AF);
+  mvb::iota_offsets_kernel<<<grid_for(n_ip), 256, 0, st>>>(w.iota_p, n_ip, p);                   MVB_LAUNCHED();   // e * p
+  pad_double_kernel<<<grid_for(P), 256, 0, st>>>(mu, p, P, w.mu64);                                MVB_LAUNCHED();
+  pad_double_kernel<<<grid_for(F), 256, 0, st>>>(ybar, F, F, w.ybar64);                            MVB_LAUNCHED();
+
+  // 1. Gp = Qt^T T Qt
+  {
+    cudaError_t err = cudaSuccess;
+    mvb::bj::Hooks hooks{[](int, double flops, cudaStream_t s_) { g_prof_class = PC_EIG_REFRESH; return prof_begin(flops, s_); },
+                         [](int slot, cudaStream_t s_) { prof_end(slot, s_); g_prof_class = PC_OTHER; }};
+    const int nl = mvb::lb::reduce(G, (int)p, w.Qt, w.Tdiag, w.Tsub, w.lanczos_ws, st, &err, &hooks);
+    if (nl < 0) return fail(MVB_E_CUDA, "band reduction failed: %s", cudaGetErrorString(err));
+    g_launches.fetch_add(nl, std::memory_order_relaxed);
+  }
+  // 2. block Cholesky per alpha -> Minv, N, Pb
+  {
+    static bool attr_set = false;
+    if (!attr_set) {
+      MVB_CUDA(cudaFuncSetAttribute(mvb::bl::block_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mvb::bl::CHOL_SMEM));
+      attr_set = true;
+    }
+    mvb::bl::block_chol_kernel<<<A, 1024, mvb::bl::CHOL_SMEM, st>>>(w.Tdiag, w.Tsub, (int)nb, alphas, w.Minv, w.Nmat, w.Pb);
+    MVB_LAUNCHED();
+  }
+  // 3. Z = X_t Qt^T (implicit design rows x basis vectors), centred: Z -= Qt mu
+  const int qmode = dense_mode(P, (int)p, w.Qt, 4);
+  mvb_operand opRows{d->xp, w.row_off, w.col_off, (int)n, 0};
+  mvb_operand opQt{w.Qt, w.rowP, w.iota, (int)P, qmode};
+  int rc;
+  { ProfScope ps(PC_LEVERAGE_Z); rc = run_contract<float>(opRows, opQt, (int)n, (int)P, (int)p, w.Z, P, 0, w.contract_ws, w.contract_bytes, st); }
+  if (rc) return rc;
+  mvb::matvec_rows_kernel<float><<<cdiv(P * 32, 256), 256, 0, st>>>(w.Qt, P, P, w.mu64, w.cz);    MVB_LAUNCHED();
+  sub_cols_kernel<<<grid_for(n * P), 256, 0, st>>>(w.Z, n, P, w.cz);                                MVB_LAUNCHED();
+  // 4. forward substitution over the blocks for every (alpha, row): h = sum_j |u_j|^2
+  MVB_CUDA(cudaMemsetAsync(w.h, 0, (size_t)A * n * 4, st));
+  {
+    float* Ucur = w.U0; float* Uprev = w.U1;
+    for (int j = 0; j < nb; ++j) {
+      mvb::GatherOperand az{w.Z, w.rowP, w.iota + (int64_t)j * 128, (int)n, 2};
+      mvb::GatherOperand bm{w.Minv, w.tab128 + (int64_t)j * 128, w.iota, 128, 2};
+      rc = band_gemm(az, 0, bm, nb * 128, 0, (int)n, A, w.C1, PC_OTHER, st);
+      if (rc) return rc;
+      if (j > 0) {
+        mvb::GatherOperand au{Uprev, w.tab128, w.iota, (int)n, 2};
+        mvb::GatherOperand bn{w.Nmat, w.tab128 + (int64_t)j * 128, w.iota, 128, 2};
+        rc = band_gemm(au, n, bn, nb * 128, 0, (int)n, A, w.C2, PC_OTHER, st);
+        if (rc) return rc;
+      }
+      mvb::bl::recur_update_kernel<<<cdiv((int64_t)A * n * 32, 256), 256, 0, st>>>(w.C1, j > 0 ? w.C2 : nullptr, (int64_t)A * n, Ucur, 128, w.h);
+      MVB_LAUNCHED();
+      std::swap(Ucur, Uprev);
+    }
+  }
+  leverage_to_d_kernel<<<grid_for(n * A), 256, 0, st>>>(w.h, n, A, fit_intercept ? 1.f / (float)n : 0.f, w.dd);   MVB_LAUNCHED();
+  // 5. beta for every alpha:  Ct[f] = Qt b_f ;  L u = Ct ;  L^T x = u ;  beta = Qt^T x
+  {
+    mvb_operand opB{XtY, w.iota, w.iota_F, F, 0};            // rows f (contiguous), contraction j (stride F)
+    { ProfScope ps(PC_SMALL); rc = run_contract<float>(opB, opQt, F, (int)P, (int)p, w.Ct, P, 0, w.contract_ws, w.contract_bytes, st); }
+    if (rc) return rc;
+    // forward
+    for (int j = 0; j < nb; ++j) {
+      mvb::GatherOperand ac{w.Ct, w.rowP, w.iota + (int64_t)j * 128, F, 2};
+      mvb::GatherOperand bm{w.Minv, w.tab128 + (int64_t)j * 128, w.iota, 128, 2};
+      rc = band_gemm(ac, 0, bm, nb * 128, 0, F, A, w.C1, PC_OTHER, st);
+      if (rc) return rc;
+      if (j > 0) {
+        mvb::GatherOperand au{w.Ub, w.rowP, w.iota + (int64_t)(j - 1) * 128, F, 2};
+        mvb::GatherOperand bn{w.Nmat, w.tab128 + (int64_t)j * 128, w.iota, 128, 2};
+        rc = band_gemm(au, F, bn, nb * 128, 0, F, A, w.C2, PC_OTHER, st);
+        if (rc) return rc;
+      }
+      // Ub[a][f][j*128 ..] = C1 - C2 : rows (a,f) have ld P in Ub but C1 is [a][f][128]
+      mvb::bl::recur_update_kernel<<<cdiv(AF * 32, 256), 256, 0, st>>>(w.C1, j > 0 ? w.C2 : nullptr, AF, w.Ub + (int64_t)j * 128, P, nullptr);
+      MVB_LAUNCHED();
+    }
+    // backward: x_j = Minv_j^T u_j - Pb_j^T x_{j+1}
+    for (int j = (int)nb - 1; j >= 0; --j) {
+      mvb::GatherOperand au{w.Ub, w.rowP, w.iota + (int64_t)j * 128, F, 2};
+      mvb::GatherOperand bmt{w.Minv, w.iota, w.tab128 + (int64_t)j * 128, 128, 0};     // transposed read: rows r, contraction c
+      rc = band_gemm(au, F, bmt, 0, nb * 128, F, A, w.C1, PC_OTHER, st);
+      if (rc) return rc;
+      if (j < nb - 1) {
+        mvb::GatherOperand ax{w.Xb, w.rowP, w.iota + (int64_t)(j + 1) * 128, F, 2};
+        mvb::GatherOperand bpt{w.Pb, w.iota, w.tab128 + (int64_t)j * 128, 128, 0};
+        rc = band_gemm(ax, F, bpt, 0, nb * 128, F, A, w.C2, PC_OTHER, st);
+        if (rc) return rc;
+      }
+      mvb::bl::recur_update_kernel<<<cdiv(AF * 32, 256), 256, 0, st>>>(w.C1, j < nb - 1 ? w.C2 : nullptr, AF, w.Xb + (int64_t)j * 128, P, nullptr);
+      MVB_LAUNCHED();
+    }
+    // beta_all[(a,f)][jj] = sum_k Xb[(a,f)][k] Qt[k][jj]
+    mvb_operand opX{w.Xb, w.rowP, w.iota, (int)AF, 2};
+    mvb_operand opQc{w.Qt, w.iota, w.rowP, (int)p, 0};        // rows jj (contiguous), contraction k (stride P)
+    { ProfScope ps(PC_SMALL); rc = run_contract<float>(opX, opQc, (int)AF, (int)p, (int)P, w.beta, p, 0, w.contract_ws, w.contract_bytes, st); }
+    if (rc) return rc;
+  }
+  mvb::matvec_rows_kernel<float><<<cdiv(AF * 32, 256), 256, 0, st>>>(w.beta, AF, p, w.mu64, w.mb);   MVB_LAUNCHED();
+  // 6. fitted values for every (alpha, target): R = X_t beta_all^T, LOO losses, selection, coefficients
+  mvb_operand opBeta{w.beta, w.iota_p, w.iota, (int)AF, dense_mode(p, (int)p, w.beta, 4)};
+  { ProfScope ps(PC_RESIDUAL); rc = run_contract<float>(opRows, opBeta, (int)n, (int)AF, (int)p, w.Z, AF, 0, w.contract_ws, w.contract_bytes, st); }
+  if (rc) return rc;
+  {
+    dim3 grid(cdiv(AF, 128), w.slabs);
+    mvb::loo_loss_kernel<float><<<grid, 128, 0, st>>>(w.Z, n, A, F, AF, y, w.yrow_off, (int64_t)Tn, w.ybar64, w.mb, w.dd, w.loss_partial);
+    MVB_LAUNCHED();
+    mvb::select_alpha_kernel<float><<<1, 256, 0, st>>>(w.loss_partial, w.slabs, A, F, 1.0 / (double)n, alphas, per_target, loss, best,
+                                                       alpha_out, w.loss64);
+    MVB_LAUNCHED();
+    mvb::gather_coef_kernel<float><<<grid_for((int64_t)F * p), 256, 0, st>>>(w.beta, F, p, best, per_target, w.ybar64, w.mb, fit_intercept,
+                                                                              coef, intercept);
+    MVB_LAUNCHED();
+  }
+  return MVB_OK;
+}
+
 template <typename T>
 int ridge_solve_impl(const mvb_design* d, const T* y, int F, T* G, const T* XtY, const T* mu, const T* ybar,
                      const T* alphas, int A, int fit_intercept, int per_target, T* coef, T* intercept, T* alpha_out,
@@ -358,6 +604,12 @@ int ridge_solve_impl(const mvb_design* d, const T* y, int F, T* G, const T* XtY,
   const int64_t n = (int64_t)d->n_trials * d->n_time, p = (int64_t)d->n_feat * d->n_lag;
   const int64_t AF = (int64_t)A * F;
   const int Tn = d->n_time;
+  if constexpr (sizeof(T) == 4) {
+    if (use_band(p, MVB_F32))
+      return ridge_solve_band(d, (const float*)y, F, (float*)G, (const float*)XtY, (const float*)mu, (const float*)ybar,
+                              (const float*)alphas, A, fit_intercept, per_target, (float*)coef, (float*)intercept, (float*)alpha_out,
+                              best, (float*)loss, ws, ws_bytes, st);
+  }
   Arena ar(ws, ws_bytes);
   SolveWs w;
   carve_solve<T>(ar, d, F, A, w);
@@ -584,6 +836,8 @@ int mvb_eigh(void* A, void* Vt, void* lam, int batch, int p, int dtype, void* ws
 size_t mvb_ridge_solve_workspace_bytes(const mvb_design* d, int n_targets, int n_alphas) {
   if (!design_ok(d) || n_targets < 1 || n_alphas < 1) return 0;
   Arena ar(nullptr, 0);
+  const int64_t p = (int64_t)d->n_feat * d->n_lag;
+  if (use_band(p, d->dtype)) { BandWs bw; carve_band(ar, d, n_targets, n_alphas, bw); return ar.off + 256; }
   SolveWs w;
   if (d->dtype == MVB_F32) carve_solve<float>(ar, d, n_targets, n_alphas, w); else carve_solve<double>(ar, d, n_targets, n_alphas, w);
   return ar.off + 256;
