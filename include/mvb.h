@@ -107,6 +107,15 @@ int mvb_trf_stats(const mvb_design* d, const void* y, int n_targets, int fit_int
 size_t mvb_eigh_workspace_bytes(int batch, int p, int dtype);
 int mvb_eigh(void* A, void* Vt, void* lam, int batch, int p, int dtype, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- orthogonal reduction to block-tridiagonal form (fp32, tensor cores) ---------------------------
+ * Large-p replacement for the decomposition in ridgecv.py:218: G (p x p, symmetric) is padded to
+ * P = mvb_band_padded(p) (multiple of 128) and reduced to  Gp = Qt^T T Qt  with Qt (P x P) orthogonal
+ * (rows = basis vectors) and T block tridiagonal: Tdiag[j], Tsub[j] = T_{j,j-1} ([P/128][128][128]).
+ * mvb_ridge_solve uses it internally (block-Cholesky LOO sweep) when p >= 512.                    */
+int mvb_band_padded(int p);
+size_t mvb_band_reduce_workspace_bytes(int p);
+int mvb_band_reduce(const void* G, int p, void* Qt, void* Tdiag, void* Tsub, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- exact leave-one-out ridge over an alpha grid --------------------------------------------------
  * replaces _RidgeCV_torch.fit after the decomposition (ridgecv.py:223-301): per-row leverages,
  * LOO residuals, loss (A x F), alpha selection (first minimum; shared or per target), coefficients

@@ -60,6 +60,9 @@ _SIGNATURES = {
     'mvb_ridge_solve': (c_int, [POINTER(mvb_design), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_size_t, c_void_p]),
+    'mvb_band_padded': (c_int, [c_int]),
+    'mvb_band_reduce_workspace_bytes': (c_size_t, [c_int]),
+    'mvb_band_reduce': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'mvb_trf_predict_workspace_bytes': (c_size_t, [POINTER(mvb_design), c_int]),
     'mvb_trf_predict': (c_int, [POINTER(mvb_design), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'mvb_score': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
@@ -298,6 +301,19 @@ def eigh(A: torch.Tensor):
     ws = _workspace(lib.mvb_eigh_workspace_bytes(b, p, dtype_code(A)), A.device)
     check(lib.mvb_eigh(_ptr(A), _ptr(Vt), _ptr(lam), b, p, dtype_code(A), _ptr(ws), ws.numel(), _stream(A)), 'mvb_eigh')
     return Vt, lam
+
+
+def band_reduce(G: torch.Tensor):
+    """G (p, p) fp32 symmetric -> Qt (P, P), Tdiag, Tsub (P/128, 128, 128) with pad(G) = Qt^T T Qt."""
+    p = G.shape[0]
+    lib = load()
+    P = lib.mvb_band_padded(p)
+    Qt = torch.zeros((P, P), dtype=G.dtype, device=G.device)
+    Td = torch.zeros((P // 128, 128, 128), dtype=G.dtype, device=G.device)
+    Ts = torch.zeros_like(Td)
+    ws = _workspace(lib.mvb_band_reduce_workspace_bytes(p), G.device)
+    check(lib.mvb_band_reduce(_ptr(G), p, _ptr(Qt), _ptr(Td), _ptr(Ts), _ptr(ws), ws.numel(), _stream(G)), 'mvb_band_reduce')
+    return Qt, Td, Ts
 
 
 def contract(a_base, a_roff, a_koff, a_contig, b_base, b_roff, b_koff, b_contig, M, N, K, symmetric=False) -> torch.Tensor:

@@ -85,7 +85,8 @@ constexpr int SLD = PR + 1;   // padded leading dimension of S (conflict-free co
 constexpr int SMALL_EIG_SMEM = PR * SLD * 4 + PR * PR * 4;
 
 __global__ void __launch_bounds__(1024) small_eig_kernel(const float* __restrict__ S_all, float* __restrict__ J_all,
-                                                         float tol_rot, float tol_count, int max_inner, Ctl* ctl, int sweep) {
+                                                         float tol_rot, float tol_count, int max_inner, Ctl* ctl, int sweep,
+                                                         float* __restrict__ lam_out = nullptr) {
   if (ctl->done) return;
   extern __shared__ __align__(16) unsigned char sm_raw[];
   float* J = reinterpret_cast<float*>(sm_raw);                         // [PR][PR]
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(1024) small_eig_kernel(const float* __restrict
     const int k = e / PR, c = e % PR;
     Jg[rank[k] * PR + c] = J[e];
   }
+  if (lam_out && threadIdx.x < PR) lam_out[(int64_t)blockIdx.x * PR + rank[threadIdx.x]] = lam[threadIdx.x];
 }
 
 // end of a sweep: an odd number of steps left the data in W1 -> copy it back so every sweep ends in W0

@@ -17,6 +17,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "tc_gemm.cuh"
 #include "jacobi_block.cuh"   // small_eig_kernel (128 x 128 symmetric eigensolver in shared memory)
 
@@ -49,7 +50,7 @@ inline Plan make_plan(int p) {
   pl.off_S = take(NB * NB * 4);
   pl.off_J = take(NB * NB * 4);
   pl.off_M = take(NB * NB * 4);
-  pl.off_lam = take(NB * 4);
+  pl.off_lam = take((NB + 8) * 4);
   pl.off_rowP = take(P * 8);
   pl.off_row128 = take(NB * 8);
   pl.off_iota = take(P * 8);
@@ -116,31 +117,43 @@ __global__ void reduce_parts_kernel(const float* __restrict__ part, int splits, 
   }
 }
 
-// eigenvalues of the sorted small-eig output: lam_r = J_r S J_r^T ; Mmat = diag(lam^-1/2) J  (SVQB scaling)
-__global__ void svqb_scale_kernel(const float* __restrict__ S, const float* __restrict__ J, float* Mmat, float* lam_out) {
-  __shared__ float lam[NB];
+// Mmat = diag(lam^-1/2) J  (SVQB scaling; lam sorted like the rows of J, floored far below fp32 noise).
+// guard != nullptr: no-op when guard->done is set (the Newton-Schulz matrix already in Mmat stands); clears the flag.
+__global__ void svqb_scale_kernel(const float* __restrict__ J, const float* __restrict__ lam, float* Mmat, bj::Ctl* guard) {
   __shared__ float lmax;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < NB; r += blockDim.x / 32) {
-    // lam_r = sum_c J[r][c] * (S J_r)[c]
-    float acc = 0.f;
-    for (int c = lane; c < NB; c += 32) {
-      float t = 0.f;
-      for (int k = 0; k < NB; ++k) t += S[c * NB + k] * J[r * NB + k];
-      acc += J[r * NB + c] * t;
-    }
-    acc = bj::wsum(acc);
-    if (lane == 0) lam[r] = acc;
+  if (guard) {
+    const unsigned int skip = guard->done;
+    __syncthreads();
+    if (threadIdx.x == 0) guard->done = 0;
+    if (skip) return;
   }
-  __syncthreads();
   if (threadIdx.x == 0) { float m = 0.f; for (int r = 0; r < NB; ++r) m = fmaxf(m, lam[r]); lmax = m; }
   __syncthreads();
   const float floor_ = fmaxf(lmax * 1e-12f, 1e-36f);
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) Mmat[e] = J[e] * rsqrtf(fmaxf(lam[e / NB], floor_));
+}
+
+// Mmat = 1.5 I - 0.5 S  (one Newton-Schulz orthonormalisation step, valid when the rows are already nearly
+// orthonormal).  Sets guard->done = 1 when max|S - I| < 0.05, else 0 -> the caller's eigen-based SVQB then runs.
+__global__ void ns_matrix_kernel(const float* __restrict__ S, float* Mmat, bj::Ctl* guard) {
+  __shared__ float red[32];
+  float dev = 0.f;
   for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-    const int r = e / NB;
-    Mmat[e] = J[e] * rsqrtf(fmaxf(lam[r], floor_));
+    const int r = e / NB, c = e % NB;
+    const float sym = 0.5f * (S[e] + S[c * NB + r]);
+    const float d = sym - (r == c ? 1.f : 0.f);
+    dev = fmaxf(dev, fabsf(d));
+    Mmat[e] = (r == c ? 1.f : 0.f) - 0.5f * d;
   }
-  if (lam_out) for (int r = threadIdx.x; r < NB; r += blockDim.x) lam_out[r] = lam[r];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dev = fmaxf(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dev;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    guard->done = (m < 0.05f) ? 1u : 0u;      // NaN compares false -> the robust path runs
+  }
 }
 
 // T blocks out of the first H of iteration j: Tdiag[j] = sym(H[:, j]), Tsub[j] = H[:, j-1]
@@ -152,9 +165,14 @@ __global__ void extract_T_kernel(const float* __restrict__ H, int P, int j, floa
   }
 }
 
+// developer knobs (environment, read per call): second orthonormalisation pass, small-eig tolerance / sweeps
+inline int knob_i(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+inline float knob_f(const char* name, float dflt) { const char* e = getenv(name); return e ? (float)atof(e) : dflt; }
+
 struct Ctx {
   Plan pl; char* base; cudaStream_t st; int launches; cudaError_t err;
   const bj::Hooks* hooks;
+  int polish_ns = 1; float eig_tol = 1e-6f; int eig_sweeps = 8; int reorth3 = 1;
   float* f(size_t off) const { return (float*)(base + off); }
   int64_t* i64(size_t off) const { return (int64_t*)(base + off); }
 };
@@ -194,10 +212,29 @@ inline bool svqb(Ctx& cx, const float* src, float* dst) {
   bj::Ctl* ctl = (bj::Ctl*)(cx.base + pl.off_ctl);
   GatherOperand a{src, rowP, iota, NB, 2};
   if (!gemm(cx, a, a, NB, NB, P, S, NB)) return false;
-  bj::small_eig_kernel<<<1, 1024, bj::SMALL_EIG_SMEM, cx.st>>>(S, J, 1e-7f, 1.f, 10, ctl, 0); ++cx.launches;
-  svqb_scale_kernel<<<1, 1024, 0, cx.st>>>(S, J, Mm, nullptr); ++cx.launches;
+  bj::small_eig_kernel<<<1, 1024, bj::SMALL_EIG_SMEM, cx.st>>>(S, J, cx.eig_tol, 1.f, cx.eig_sweeps, ctl, 0, cx.f(pl.off_lam) + 8); ++cx.launches;
+  svqb_scale_kernel<<<1, 1024, 0, cx.st>>>(J, cx.f(pl.off_lam) + 8, Mm, nullptr); ++cx.launches;
   GatherOperand m{Mm, row128, iota, NB, 2};
   GatherOperand w{src, iota, rowP, P, 0};          // rows = columns c of src, contraction over its 128 rows
+  return gemm(cx, m, w, NB, P, NB, dst, P);
+}
+
+// second orthonormalisation pass for rows that SVQB already made orthonormal to ~1e-3: dst = (1.5 I - 0.5 src src^T) src
+inline bool ns_polish(Ctx& cx, const float* src, float* dst) {
+  if (!cx.polish_ns) return svqb(cx, src, dst);
+  const Plan& pl = cx.pl;
+  const int P = pl.P;
+  int64_t *rowP = cx.i64(pl.off_rowP), *row128 = cx.i64(pl.off_row128), *iota = cx.i64(pl.off_iota);
+  float *S = cx.f(pl.off_S), *J = cx.f(pl.off_J), *Mm = cx.f(pl.off_M);
+  bj::Ctl* ctl = (bj::Ctl*)(cx.base + pl.off_ctl);
+  GatherOperand a{src, rowP, iota, NB, 2};
+  if (!gemm(cx, a, a, NB, NB, P, S, NB)) return false;
+  ns_matrix_kernel<<<1, 1024, 0, cx.st>>>(S, Mm, ctl); ++cx.launches;
+  // robust fallback (rank-deficient residual blocks): both kernels are no-ops while ctl->done is set
+  bj::small_eig_kernel<<<1, 1024, bj::SMALL_EIG_SMEM, cx.st>>>(S, J, cx.eig_tol, 1.f, cx.eig_sweeps, ctl, 0, cx.f(pl.off_lam) + 8); ++cx.launches;
+  svqb_scale_kernel<<<1, 1024, 0, cx.st>>>(J, cx.f(pl.off_lam) + 8, Mm, ctl); ++cx.launches;
+  GatherOperand m{Mm, row128, iota, NB, 2};
+  GatherOperand w{src, iota, rowP, P, 0};
   return gemm(cx, m, w, NB, P, NB, dst, P);
 }
 
@@ -220,6 +257,8 @@ inline bool reorth(Ctx& cx, float* W, const float* Qt, int nq) {
 inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, void* ws, cudaStream_t st, cudaError_t* err,
                   const bj::Hooks* hooks = nullptr) {
   Ctx cx{make_plan(p), (char*)ws, st, 0, cudaSuccess, hooks};
+  cx.polish_ns = knob_i("MVB_LB_POLISH_NS", 1); cx.eig_tol = knob_f("MVB_LB_EIG_TOL", 1e-6f);
+  cx.eig_sweeps = knob_i("MVB_LB_EIG_SWEEPS", 8); cx.reorth3 = knob_i("MVB_LB_REORTH3", 1);
   const Plan& pl = cx.pl;
   const int P = pl.P, nb = pl.nblk;
   float *Gp = cx.f(pl.off_Gp), *Wt = cx.f(pl.off_Wt), *H = cx.f(pl.off_H);
@@ -239,7 +278,7 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
   // Q_0: orthonormalised pseudo-random block
   random_block_kernel<<<148 * 2, 256, 0, st>>>(Wt, (int64_t)NB * P, 0x9e3779b9u); ++cx.launches;
   LB_OK(svqb(cx, Wt, Qt));
-  LB_OK(svqb(cx, Qt, Wt));
+  LB_OK(ns_polish(cx, Qt, Wt));
   LB_CK(cudaMemcpyAsync(Qt, Wt, (size_t)NB * P * 4, cudaMemcpyDeviceToDevice, st));
   for (int j = 0; j < nb; ++j) {
     const float* Qj = Qt + (size_t)j * NB * P;
@@ -263,8 +302,8 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
     LB_OK(reorth(cx, Wt, Qt, nq));
     float* Qn = Qt + (size_t)(j + 1) * NB * P;
     LB_OK(svqb(cx, Wt, Qn));
-    LB_OK(reorth(cx, Qn, Qt, nq));
-    LB_OK(svqb(cx, Qn, Wt));
+    if (cx.reorth3) LB_OK(reorth(cx, Qn, Qt, nq));
+    LB_OK(ns_polish(cx, Qn, Wt));
     LB_CK(cudaMemcpyAsync(Qn, Wt, (size_t)NB * P * 4, cudaMemcpyDeviceToDevice, st));
   }
   LB_CK(cudaGetLastError());

@@ -356,12 +356,9 @@ __global__ void to_double_kernel(const T* __restrict__ in, int64_t n, double* ou
 
 // ---- band path: block-tridiagonal reduction + block-Cholesky LOO sweep (fp32, large p) ---------------------
 int band_min_p() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MVB_BAND_MIN_P");
-    v = e ? atoi(e) : 1024;
-    if (v < 128) v = 128;
-  }
+  const char* e = getenv("MVB_BAND_MIN_P");
+  int v = e ? atoi(e) : 512;
+  if (v < 128) v = 128;
   return v;
 }
 inline bool use_band(int64_t p, int dtype) { return dtype == MVB_F32 && p >= band_min_p() && !force_simt(); }
@@ -831,6 +828,19 @@ int mvb_eigh(void* A, void* Vt, void* lam, int batch, int p, int dtype, void* ws
   if (dtype == MVB_F32) return eigh_impl<float>((float*)A, (float*)Vt, (float*)lam, batch, p, ws, ws_bytes, st);
   if (dtype == MVB_F64) return eigh_impl<double>((double*)A, (double*)Vt, (double*)lam, batch, p, ws, ws_bytes, st);
   return fail(MVB_E_UNSUPPORTED, "eigh: dtype %d", dtype);
+}
+
+int mvb_band_padded(int p) { return p < 1 ? 0 : mvb::lb::make_plan(p).P; }
+size_t mvb_band_reduce_workspace_bytes(int p) { return p < 1 ? 0 : mvb::lb::make_plan(p).bytes + 256; }
+
+int mvb_band_reduce(const void* G, int p, void* Qt, void* Tdiag, void* Tsub, void* ws, size_t ws_bytes, void* stream) {
+  if (!G || p < 1 || !Qt || !Tdiag || !Tsub || !ws) return fail(MVB_E_ARG, "band_reduce: bad argument");
+  if (ws_bytes < mvb::lb::make_plan(p).bytes) return fail(MVB_E_WORKSPACE, "band_reduce: workspace %zu < %zu", ws_bytes, mvb::lb::make_plan(p).bytes);
+  cudaError_t err = cudaSuccess;
+  const int nl = mvb::lb::reduce((const float*)G, p, (float*)Qt, (float*)Tdiag, (float*)Tsub, ws, (cudaStream_t)stream, &err, nullptr);
+  if (nl < 0) return fail(MVB_E_CUDA, "band reduction failed: %s", cudaGetErrorString(err));
+  g_launches.fetch_add(nl, std::memory_order_relaxed);
+  return MVB_OK;
 }
 
 size_t mvb_ridge_solve_workspace_bytes(const mvb_design* d, int n_targets, int n_alphas) {
