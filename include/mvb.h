@@ -115,6 +115,9 @@ int mvb_eigh(void* A, void* Vt, void* lam, int batch, int p, int dtype, void* ws
 int mvb_band_padded(int p);
 size_t mvb_band_reduce_workspace_bytes(int p);
 int mvb_band_reduce(const void* G, int p, void* Qt, void* Tdiag, void* Tsub, void* ws, size_t ws_bytes, void* stream);
+/* diagnostics (synchronising): host_out[0] = residual blocks that needed the eigen-based orthonormalisation instead of
+ * Cholesky QR, host_out[1] = blocks whose polish fell back from Newton-Schulz, during the last reduction in `ws`. */
+int mvb_band_reduce_counters(const void* ws, int p, unsigned int* host_out);
 
 /* ---- exact leave-one-out ridge over an alpha grid --------------------------------------------------
  * replaces _RidgeCV_torch.fit after the decomposition (ridgecv.py:223-301): per-row leverages,

@@ -63,6 +63,7 @@ _SIGNATURES = {
     'mvb_band_padded': (c_int, [c_int]),
     'mvb_band_reduce_workspace_bytes': (c_size_t, [c_int]),
     'mvb_band_reduce': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'mvb_band_reduce_counters': (c_int, [c_void_p, c_int, c_void_p]),
     'mvb_trf_predict_workspace_bytes': (c_size_t, [POINTER(mvb_design), c_int]),
     'mvb_trf_predict': (c_int, [POINTER(mvb_design), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'mvb_score': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
@@ -303,7 +304,7 @@ def eigh(A: torch.Tensor):
     return Vt, lam
 
 
-def band_reduce(G: torch.Tensor):
+def band_reduce(G: torch.Tensor, counters: bool = False):
     """G (p, p) fp32 symmetric -> Qt (P, P), Tdiag, Tsub (P/128, 128, 128) with pad(G) = Qt^T T Qt."""
     p = G.shape[0]
     lib = load()
@@ -313,6 +314,10 @@ def band_reduce(G: torch.Tensor):
     Ts = torch.zeros_like(Td)
     ws = _workspace(lib.mvb_band_reduce_workspace_bytes(p), G.device)
     check(lib.mvb_band_reduce(_ptr(G), p, _ptr(Qt), _ptr(Td), _ptr(Ts), _ptr(ws), ws.numel(), _stream(G)), 'mvb_band_reduce')
+    if counters:
+        out = (ctypes.c_uint * 2)()
+        check(lib.mvb_band_reduce_counters(_ptr(ws), p, out), 'mvb_band_reduce_counters')
+        return Qt, Td, Ts, (int(out[0]), int(out[1]))
     return Qt, Td, Ts
 
 

@@ -133,6 +133,68 @@ __global__ void svqb_scale_kernel(const float* __restrict__ J, const float* __re
   for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) Mmat[e] = J[e] * rsqrtf(fmaxf(lam[e / NB], floor_));
 }
 
+// Fast path of the block orthonormalisation: Mmat = L^-1 with S = L L^T (Cholesky QR), all in shared memory.
+// Valid when S is well conditioned: sets guard->done = 1 when every pivot exceeds pivot_tol * max diag(S), else 0 so
+// that the eigen-based SVQB (robust for rank-deficient residual blocks) runs instead.  guard->rot[2] counts fallbacks.
+constexpr int CLD = NB + 1;
+constexpr int CHOL_ORTH_SMEM = 2 * NB * CLD * 4;
+__global__ void __launch_bounds__(1024) chol_orth_kernel(const float* __restrict__ S, float* __restrict__ Mmat, float pivot_tol,
+                                                         bj::Ctl* guard) {
+  extern __shared__ float csm[];
+  float* Cm = csm;               // S -> L (lower)
+  float* Li = csm + NB * CLD;    // L^-1
+  __shared__ float s_min, s_max;
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    const int r = e / NB, c = e % NB;
+    Cm[r * CLD + c] = 0.5f * (S[e] + S[c * NB + r]);
+    Li[r * CLD + c] = 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    for (int r = 0; r < NB; ++r) m = fmaxf(m, Cm[r * CLD + r]);
+    s_max = m; s_min = m;
+  }
+  __syncthreads();
+  const float floor_ = fmaxf(s_max * 1e-10f, 1e-36f);
+  for (int k = 0; k < NB; ++k) {
+    const float piv = Cm[k * CLD + k];
+    const float d = sqrtf(fmaxf(piv, floor_));
+    __syncthreads();
+    if (threadIdx.x == 0) { Cm[k * CLD + k] = d; s_min = fminf(s_min, piv); }
+    for (int i = k + 1 + threadIdx.x; i < NB; i += blockDim.x) Cm[i * CLD + k] /= d;
+    __syncthreads();
+    const int m = NB - 1 - k;                       // trailing size
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+      const int i = k + 1 + e / m, jj = k + 1 + e % m;
+      if (jj <= i) Cm[i * CLD + jj] -= Cm[i * CLD + k] * Cm[jj * CLD + k];
+    }
+    __syncthreads();
+  }
+  // Li = L^-1 (lower): column c solved by 8 cooperating lanes (forward substitution)
+  {
+    const int c = threadIdx.x >> 3, sub = threadIdx.x & 7;      // 128 columns x 8 lanes
+    for (int i = 0; i < NB; ++i) {
+      float acc = 0.f;
+      if (i >= c) {
+        for (int k = c + sub; k < i; k += 8) acc += Cm[i * CLD + k] * Li[k * CLD + c];
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (sub == 0) Li[i * CLD + c] = (i < c) ? 0.f : (((i == c) ? 1.f : 0.f) - acc) / Cm[i * CLD + i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) Mmat[e] = Li[(e / NB) * CLD + (e % NB)];
+  if (threadIdx.x == 0) {
+    const bool ok = s_min > pivot_tol * s_max;     // NaN compares false -> robust path
+    guard->done = ok ? 1u : 0u;
+    if (!ok) atomicAdd(&guard->rot[2], 1u);
+  }
+}
+
 // Mmat = 1.5 I - 0.5 S  (one Newton-Schulz orthonormalisation step, valid when the rows are already nearly
 // orthonormal).  Sets guard->done = 1 when max|S - I| < 0.05, else 0 -> the caller's eigen-based SVQB then runs.
 __global__ void ns_matrix_kernel(const float* __restrict__ S, float* Mmat, bj::Ctl* guard) {
@@ -153,6 +215,7 @@ __global__ void ns_matrix_kernel(const float* __restrict__ S, float* Mmat, bj::C
     float m = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
     guard->done = (m < 0.05f) ? 1u : 0u;      // NaN compares false -> the robust path runs
+    if (!(m < 0.05f)) atomicAdd(&guard->rot[3], 1u);
   }
 }
 
@@ -172,7 +235,7 @@ inline float knob_f(const char* name, float dflt) { const char* e = getenv(name)
 struct Ctx {
   Plan pl; char* base; cudaStream_t st; int launches; cudaError_t err;
   const bj::Hooks* hooks;
-  int polish_ns = 1; float eig_tol = 1e-6f; int eig_sweeps = 8; int reorth3 = 1;
+  int polish_ns = 1; float eig_tol = 1e-6f; int eig_sweeps = 8; int reorth3 = 1; int reorth2 = 1; float chol_tol = 1e-4f;
   float* f(size_t off) const { return (float*)(base + off); }
   int64_t* i64(size_t off) const { return (int64_t*)(base + off); }
 };
@@ -212,8 +275,15 @@ inline bool svqb(Ctx& cx, const float* src, float* dst) {
   bj::Ctl* ctl = (bj::Ctl*)(cx.base + pl.off_ctl);
   GatherOperand a{src, rowP, iota, NB, 2};
   if (!gemm(cx, a, a, NB, NB, P, S, NB)) return false;
-  bj::small_eig_kernel<<<1, 1024, bj::SMALL_EIG_SMEM, cx.st>>>(S, J, cx.eig_tol, 1.f, cx.eig_sweeps, ctl, 0, cx.f(pl.off_lam) + 8); ++cx.launches;
-  svqb_scale_kernel<<<1, 1024, 0, cx.st>>>(J, cx.f(pl.off_lam) + 8, Mm, nullptr); ++cx.launches;
+  if (cx.chol_tol > 0.f) {
+    // Cholesky QR when the block is well conditioned; otherwise the two kernels below do the eigen-based SVQB
+    chol_orth_kernel<<<1, 1024, CHOL_ORTH_SMEM, cx.st>>>(S, Mm, cx.chol_tol, ctl); ++cx.launches;
+    bj::small_eig_kernel<<<1, 1024, bj::SMALL_EIG_SMEM, cx.st>>>(S, J, cx.eig_tol, 1.f, cx.eig_sweeps, ctl, 0, cx.f(pl.off_lam) + 8); ++cx.launches;
+    svqb_scale_kernel<<<1, 1024, 0, cx.st>>>(J, cx.f(pl.off_lam) + 8, Mm, ctl); ++cx.launches;
+  } else {
+    bj::small_eig_kernel<<<1, 1024, bj::SMALL_EIG_SMEM, cx.st>>>(S, J, cx.eig_tol, 1.f, cx.eig_sweeps, ctl, 0, cx.f(pl.off_lam) + 8); ++cx.launches;
+    svqb_scale_kernel<<<1, 1024, 0, cx.st>>>(J, cx.f(pl.off_lam) + 8, Mm, nullptr); ++cx.launches;
+  }
   GatherOperand m{Mm, row128, iota, NB, 2};
   GatherOperand w{src, iota, rowP, P, 0};          // rows = columns c of src, contraction over its 128 rows
   return gemm(cx, m, w, NB, P, NB, dst, P);
@@ -259,6 +329,7 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
   Ctx cx{make_plan(p), (char*)ws, st, 0, cudaSuccess, hooks};
   cx.polish_ns = knob_i("MVB_LB_POLISH_NS", 1); cx.eig_tol = knob_f("MVB_LB_EIG_TOL", 1e-6f);
   cx.eig_sweeps = knob_i("MVB_LB_EIG_SWEEPS", 8); cx.reorth3 = knob_i("MVB_LB_REORTH3", 1);
+  cx.reorth2 = knob_i("MVB_LB_REORTH2", 1); cx.chol_tol = knob_f("MVB_LB_CHOL_TOL", 1e-4f);
   const Plan& pl = cx.pl;
   const int P = pl.P, nb = pl.nblk;
   float *Gp = cx.f(pl.off_Gp), *Wt = cx.f(pl.off_Wt), *H = cx.f(pl.off_H);
@@ -269,6 +340,7 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
   static bool attr_set = false;
   if (!attr_set) {
     LB_CK(cudaFuncSetAttribute(bj::small_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bj::SMALL_EIG_SMEM));
+    LB_CK(cudaFuncSetAttribute(chol_orth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_ORTH_SMEM));
     attr_set = true;
   }
   LB_CK(cudaMemsetAsync(ctl, 0, sizeof(bj::Ctl), st));
@@ -299,7 +371,7 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
       LB_OK(gemm(cx, h, qc, NB, P, nq, W2, P));
       sub_kernel<<<148 * 2, 256, 0, st>>>(Wt, W2, (int64_t)NB * P); ++cx.launches;
     }
-    LB_OK(reorth(cx, Wt, Qt, nq));
+    if (cx.reorth2) LB_OK(reorth(cx, Wt, Qt, nq));
     float* Qn = Qt + (size_t)(j + 1) * NB * P;
     LB_OK(svqb(cx, Wt, Qn));
     if (cx.reorth3) LB_OK(reorth(cx, Qn, Qt, nq));

@@ -843,6 +843,15 @@ int mvb_band_reduce(const void* G, int p, void* Qt, void* Tdiag, void* Tsub, voi
   return MVB_OK;
 }
 
+int mvb_band_reduce_counters(const void* ws, int p, unsigned int* host_out) {
+  if (!ws || p < 1 || !host_out) return fail(MVB_E_ARG, "band_reduce_counters: bad argument");
+  const mvb::lb::Plan pl = mvb::lb::make_plan(p);
+  mvb::bj::Ctl ctl;
+  MVB_CUDA(cudaMemcpy(&ctl, (const char*)ws + pl.off_ctl, sizeof(ctl), cudaMemcpyDeviceToHost));   // synchronising: diagnostics only
+  host_out[0] = ctl.rot[2]; host_out[1] = ctl.rot[3];
+  return MVB_OK;
+}
+
 size_t mvb_ridge_solve_workspace_bytes(const mvb_design* d, int n_targets, int n_alphas) {
   if (!design_ok(d) || n_targets < 1 || n_alphas < 1) return 0;
   Arena ar(nullptr, 0);

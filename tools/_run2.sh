@@ -1,3 +1,2 @@
-python tools/band_check.py 3 8 > gpurun_out/bc_guard.log 2>&1
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_cfg2_band2.json 2> gpurun_out/bench_cfg2_band2.err
+python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_cfg2_band3.json 2> gpurun_out/bench_cfg2_band3.err

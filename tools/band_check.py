@@ -53,7 +53,7 @@ def run(C, F=64, oracle=True):
     torch.cuda.synchronize()
     L.band_reduce(G)
     e0 = ev()
-    Qt, Td, Ts = L.band_reduce(G)
+    Qt, Td, Ts, cnt = L.band_reduce(G, counters=True)
     e1 = ev()
     torch.cuda.synchronize()
     t_red = e0.elapsed_time(e1)
@@ -71,7 +71,7 @@ def run(C, F=64, oracle=True):
     Tex = Q64 @ Gp @ Q64.T
     mask = torch.ones(P // 128, P // 128, device=dev).tril(-2) + torch.ones(P // 128, P // 128, device=dev).triu(2)
     offband = (Tex * mask.repeat_interleave(128, 0).repeat_interleave(128, 1)).abs().max().item() / Gp.abs().max().item()
-    msg = f'C={C} p={p} P={P}: reduce {t_red:.1f} ms  orth={orth:.1e} rec={rec:.1e} offband={offband:.1e}'
+    msg = f'C={C} p={p} P={P}: reduce {t_red:.1f} ms  orth={orth:.1e} rec={rec:.1e} offband={offband:.1e} fallbacks(chol,ns)={cnt}'
     del Q64, T, Tex, Gp
     print(msg, flush=True)
     msg = '   '
