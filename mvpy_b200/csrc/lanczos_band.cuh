@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <algorithm>
 #include "tc_gemm.cuh"
 #include "jacobi_block.cuh"   // small_eig_kernel (128 x 128 symmetric eigensolver in shared memory)
 
@@ -244,12 +245,9 @@ struct Ctx {
 inline bool gemm(Ctx& cx, const GatherOperand& A, const GatherOperand& B, int M, int N, int K, float* C, int64_t ldc) {
   const int bn = N > 128 ? 256 : 128;
   const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
-  int splits = 1;
-  if (tiles < 148) splits = (148 + tiles - 1) / tiles;
-  const int kchunks = (K + 32 * tc::DRAIN - 1) / (32 * tc::DRAIN);
-  if (splits > kchunks) splits = kchunks;
-  if (splits > 64) splits = 64;
-  while (splits > 1 && (size_t)splits * M * N > cx.pl.part_elems) --splits;
+  int max_splits = (int)std::min<size_t>(64, cx.pl.part_elems / ((size_t)M * N));
+  if (max_splits < 1) max_splits = 1;
+  const int splits = tc_choose_splits(tiles, (K + tc::BK - 1) / tc::BK, max_splits);
   TcGemmParams g = tc_gemm_defaults();
   g.A = A; g.B = B; g.M = M; g.N = N; g.K = K;
   if (splits > 1) { g.C = cx.f(cx.pl.off_part); g.ldc = N; g.c_split_stride = (int64_t)M * N; }

@@ -132,9 +132,13 @@ SplitPlan plan_contract(int M, int N, int K, int dtype, int symmetric) {
   const int kblocks = cdiv(K, bk);
   const int target = tc ? 148 : 296;
   int s = 1;
-  if (tiles < target) s = (int)((target + tiles - 1) / tiles);
-  if (s > kblocks) s = kblocks;
-  if (s > 64) s = 64;
+  if (tc) {
+    s = mvb::tc_choose_splits(tiles, cdiv(K, 32), 64);
+  } else {
+    if (tiles < target) s = (int)((target + tiles - 1) / tiles);
+    if (s > kblocks) s = kblocks;
+    if (s > 64) s = 64;
+  }
   if (s < 1) s = 1;
   pl.splits = s;
   pl.ws_elems = s > 1 ? (size_t)s * M * N : 0;

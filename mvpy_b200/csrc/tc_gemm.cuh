@@ -454,6 +454,21 @@ inline cudaError_t launch_a(const TcGemmParams& p, int k_splits, cudaStream_t st
 
 }  // namespace tc
 
+// Split-K factor for `tiles` output tiles of `nkb` BK-stages each on `sms` SMs (one CTA per SM): minimise
+// waves x (stages per CTA + fixed per-CTA cost) -- e.g. 51 tiles split 3 ways is 153 CTAs = two waves for 3% more
+// parallelism, while 5 ways fills two waves almost completely.
+inline int tc_choose_splits(int64_t tiles, int nkb, int max_splits, int sms = 148) {
+  int best = 1;
+  double best_cost = 1e300;
+  for (int s = 1; s <= max_splits; ++s) {
+    if (s > 1 && s > nkb / tc::DRAIN) break;                 // keep at least one accumulation chunk per split
+    const int64_t waves = (tiles * s + sms - 1) / sms;
+    const double cost = (double)waves * ((double)((nkb + s - 1) / s) + 8.0) + 0.25 * s;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
 // Launch helper.  bn = 256 for wide outputs, 128 otherwise; k_splits partial sums go to
 // C + z * c_split_stride (caller reduces them).
 inline cudaError_t tc_gemm_launch(const TcGemmParams& p, int k_splits, int bn, cudaStream_t st) {
