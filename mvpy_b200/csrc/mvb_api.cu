@@ -243,8 +243,10 @@ int trf_stats_impl(const mvb_design* d, const T* y, int F, int fit_intercept, T*
                                                              fit_intercept, ybar, w.ybar64);
     MVB_LAUNCHED();
   }
-  mvb_operand xc{d->xp, w.col_off, w.row_off, (int)p, 1};
-  mvb_operand yc{y, w.ycol_off, w.yrow_off, F, 1};
+  // design columns as tile rows: consecutive lags are consecutive samples (mode 0), and so are consecutive k (t)
+  mvb_operand xc{d->xp, w.col_off, w.row_off, (int)p, 0};
+  const bool y_vec = sizeof(T) == 4 && Tn % 4 == 0 && ((uintptr_t)y & 15) == 0;
+  mvb_operand yc{y, w.ycol_off, w.yrow_off, F, y_vec ? 2 : 1};
   int rc;
   { ProfScope ps(PC_GRAM); rc = run_contract<T>(xc, xc, (int)p, (int)p, (int)n, G, p, 1, w.contract_ws, w.contract_bytes, st); }
   if (rc) return rc;

@@ -142,9 +142,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 __device__ __forceinline__ float rn_tf32(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+// lo = x - hi is exact in fp32 and carries <= 13 significant bits; the tensor core reads its top 11 (truncation).  Because
+// hi is rounded to nearest, lo is symmetric around zero, so that truncation is unbiased and <= 2^-21 |x|: rounding lo
+// explicitly (two more integer ops per element in the staging loop, which is issue-bound) buys nothing measurable.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = rn_tf32(x);
-  lo = rn_tf32(x - hi);
+  lo = x - hi;
 }
 
 template <int BN>
@@ -206,13 +209,27 @@ struct Loader {
         kok[j] = kg < K;
         ko[j] = kok[j] ? op.koff[kg] : 0;
       }
+      // the warp's four k are usually consecutive in memory as well (lags of one feature, samples of one trial):
+      // one address per row, the loads use immediate offsets (warp-uniform branch)
+      const bool kcontig = kok[3] && (ko[1] - ko[0]) == 1 && (ko[2] - ko[0]) == 2 && (ko[3] - ko[0]) == 3;
+      if (kcontig) {
 #pragma unroll
-      for (int rg = 0; rg < ROWS / 32; ++rg) {
-        const int r = rg * 32 + lane;
-        const bool rok = row0 + r < op.rows;
-        const float* src = op.base + sroff[r];
+        for (int rg = 0; rg < ROWS / 32; ++rg) {
+          const int r = rg * 32 + lane;
+          const bool rok = row0 + r < op.rows;
+          const float* src = op.base + (sroff[r] + ko[0]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[rg * 4 + j] = (rok && kok[j]) ? __ldg(src + ko[j]) : 0.f;
+          for (int j = 0; j < 4; ++j) v[rg * 4 + j] = rok ? __ldg(src + j) : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int rg = 0; rg < ROWS / 32; ++rg) {
+          const int r = rg * 32 + lane;
+          const bool rok = row0 + r < op.rows;
+          const float* src = op.base + sroff[r];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[rg * 4 + j] = (rok && kok[j]) ? __ldg(src + ko[j]) : 0.f;
+        }
       }
     }
   }
