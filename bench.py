@@ -180,8 +180,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from mvpy_b200 import _dist
+
     def step_device():
-        _, sc = mv.crossvalidation.cross_val_score(pipe, Xd, yd, cv=N_FOLDS)
+        # each rank owns a whole cross-validation unit (the Shapley / hierarchical sharding unit): the folds inside it
+        # run locally, exactly as they do inside a sharded shapley_score
+        with _dist.sharded_region():
+            _, sc = mv.crossvalidation.cross_val_score(pipe, Xd, yd, cv=N_FOLDS)
         if world > 1:
             out = torch.empty((world,) + tuple(sc.shape), dtype=sc.dtype, device=dev)
             dist.all_gather_into_tensor(out, sc.contiguous())
@@ -189,7 +194,12 @@ def main():
         return sc
 
     def step_host():
-        val, sc = mv.crossvalidation.cross_val_score(pipe, Xh, yh, cv=N_FOLDS)      # h2d inside, results back on host
+        with _dist.sharded_region():
+            val, sc = mv.crossvalidation.cross_val_score(pipe, Xh, yh, cv=N_FOLDS)  # h2d inside, results back on host
+        if world > 1:                                                                # the one collective: gather of score shards
+            out = torch.empty((world,) + tuple(sc.shape), dtype=sc.dtype, device=dev)
+            dist.all_gather_into_tensor(out, sc.to(dev).contiguous())
+            sc = out.cpu()
         return val, sc
 
     # ---- TF32 peak on this box (cuBLAS, allow_tf32), measured like MEASURED_PEAKS.json's bf16 figure ----
