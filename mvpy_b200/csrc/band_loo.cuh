@@ -24,7 +24,7 @@ constexpr int CHOL_SMEM = 3 * NB * LD * 4;
 // out[r][c] (global, ld NB) = sum_k X[r][k] * Y[k][c] for shared-memory X, Y (ld LD); 1024 threads, 4x4 per thread.
 // tri: 0 full; 1: X lower-triangular (k <= r); 2: Y lower-triangular (k >= c)
 __device__ __forceinline__ void smem_matmul(const float* X, const float* Y, float* out_g, float* out_s, int tri, float sign,
-                                            const float* add_s) {
+                                            const float* add_s, float* neg_g = nullptr, int neg_ld = 0) {
   const int tr = (threadIdx.x >> 5) * 4, tcn = (threadIdx.x & 31) * 4;
   float acc[4][4];
 #pragma unroll
@@ -53,12 +53,14 @@ __device__ __forceinline__ void smem_matmul(const float* X, const float* Y, floa
       if (add_s) v += add_s[(tr + i) * LD + tcn + j];
       if (out_g) out_g[(tr + i) * NB + tcn + j] = v;
       if (out_s) out_s[(tr + i) * LD + tcn + j] = v;
+      if (neg_g) neg_g[(tr + i) * neg_ld + tcn + j] = -v;
     }
 }
 
 // one CTA per alpha
 __global__ void __launch_bounds__(1024) block_chol_kernel(const float* __restrict__ Tdiag, const float* __restrict__ Tsub, int nblk,
-                                                          const float* __restrict__ alphas, float* Minv, float* Nmat, float* Pb) {
+                                                          const float* __restrict__ alphas, float* Minv, float* Nmat, float* Pb,
+                                                          float* MN /* [A][nblk][128][256]: row c = [Minv_j[c][:], -N_j[c][:]] */) {
   extern __shared__ float sm[];
   float* Cm = sm;                  // A_j + aI - W W^T  -> L_j -> (scratch)
   float* Wm = sm + NB * LD;        // W_j
@@ -168,8 +170,15 @@ __global__ void __launch_bounds__(1024) block_chol_kernel(const float* __restric
     }
     __syncthreads();
     // outputs: Minv_j = Li ; N_j = Li W (Li lower-triangular)
-    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) Minv_a[(int64_t)j * NB * NB + e] = Li[(e / NB) * LD + (e % NB)];
-    if (j > 0) smem_matmul(Li, Wm, N_a + (int64_t)j * NB * NB, nullptr, 1, 1.f, nullptr);
+    float* MN_aj = MN + ((int64_t)a * nblk + j) * NB * 2 * NB;
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+      const float v = Li[(e / NB) * LD + (e % NB)];
+      Minv_a[(int64_t)j * NB * NB + e] = v;
+      MN_aj[(e / NB) * 2 * NB + (e % NB)] = v;
+      if (j == 0) MN_aj[(e / NB) * 2 * NB + NB + (e % NB)] = 0.f;
+    }
+    // N_j = Li W, plus its negated copy for the fused forward substitution  u_j = [Minv_j | -N_j] [z_j ; u_{j-1}]
+    if (j > 0) smem_matmul(Li, Wm, N_a + (int64_t)j * NB * NB, nullptr, 1, 1.f, nullptr, MN_aj + NB, 2 * NB);
     __syncthreads();
   }
 }

@@ -147,7 +147,7 @@ SplitPlan plan_contract(int M, int N, int K, int dtype, int symmetric) {
 
 template <typename T>
 int run_contract(const mvb_operand& A, const mvb_operand& B, int M, int N, int K, T* C, int64_t ldc, int symmetric,
-                 void* ws, size_t ws_bytes, cudaStream_t st) {
+                 void* ws, size_t ws_bytes, cudaStream_t st, int c_block_cols = 0, int64_t c_block_stride = 0) {
   if (M <= 0 || N <= 0) return MVB_OK;
   constexpr int dtype = sizeof(T) == 4 ? MVB_F32 : MVB_F64;
   const SplitPlan pl = plan_contract(M, N, K, dtype, symmetric);
@@ -163,6 +163,7 @@ int run_contract(const mvb_operand& A, const mvb_operand& B, int M, int N, int K
     p.A = {(const float*)A.base, A.roff, A.koff, A.rows, A.contig};
     p.B = {(const float*)B.base, B.roff, B.koff, B.rows, B.contig};
     p.M = M; p.N = N; p.K = K; p.C = (float*)out; p.ldc = ld; p.c_split_stride = stride; p.symmetric = symmetric; p.dbg = 0;
+    if (pl.splits == 1) { p.c_block_cols = c_block_cols; p.c_block_stride = c_block_stride; }   // partials stay row-major
     const int slot = prof_begin(2.0 * M * (double)N * K * (symmetric ? 0.5 : 1.0), st);
     MVB_CUDA(mvb::tc_gemm_launch(p, pl.splits, N > 128 ? 256 : 128, st));
     prof_end(slot, st);
@@ -170,11 +171,13 @@ int run_contract(const mvb_operand& A, const mvb_operand& B, int M, int N, int K
   } else {
     mvb::GOp<T> a{(const T*)A.base, A.roff, A.koff, A.rows}, b{(const T*)B.base, B.roff, B.koff, B.rows};
     dim3 grid(cdiv(N, 64), cdiv(M, 64), pl.splits);
+    if (c_block_cols > 0 && pl.splits == 1) return fail(MVB_E_UNSUPPORTED, "contract: column-blocked output needs the tensor-core path");
     mvb::simt_contract_kernel<T><<<grid, 256, 0, st>>>(a, b, M, N, K, out, ld, stride, symmetric);
     MVB_LAUNCHED();
   }
   if (pl.splits > 1) {
-    mvb::reduce_splits_kernel<T><<<grid_for((int64_t)M * N), 256, 0, st>>>(out, pl.splits, stride, M, N, ld, C, ldc);
+    mvb::reduce_splits_kernel<T><<<grid_for((int64_t)M * N), 256, 0, st>>>(out, pl.splits, stride, M, N, ld, C, ldc, c_block_cols,
+                                                                              c_block_stride);
     MVB_LAUNCHED();
   }
   return MVB_OK;
@@ -370,8 +373,8 @@ int band_min_p() {
 inline bool use_band(int64_t p, int dtype) { return dtype == MVB_F32 && p >= band_min_p() && !force_simt(); }
 
 struct BandWs {
-  int64_t *row_off, *col_off, *yrow_off, *iota, *rowP, *tab128, *rowUb, *iota_F, *iota_p;
-  float *Qt, *Tdiag, *Tsub, *Minv, *Nmat, *Pb, *Z, *h, *U0, *U1, *C1, *C2, *Ct, *Ub, *Xb, *beta, *dd;
+  int64_t *row_off, *col_off, *yrow_off, *iota, *rowP, *tab128, *tab256, *kofs, *rowUb, *iota_F, *iota_p;
+  float *Qt, *Tdiag, *Tsub, *Minv, *Nmat, *Pb, *MN, *Z, *h, *U0, *U1, *C1, *C2, *Ct, *Ub, *Xb, *beta, *dd;
   double *mu64, *ybar64, *cz, *mb, *loss_partial, *loss64;
   void* lanczos_ws; void* contract_ws; size_t contract_bytes;
   int slabs, P, nb;
@@ -391,6 +394,8 @@ void carve_band(Arena& ar, const mvb_design* d, int F, int A, BandWs& w) {
   w.iota = ar.take<int64_t>(std::max<int64_t>(P, AF) + 256);
   w.rowP = ar.take<int64_t>(std::max<int64_t>(std::max<int64_t>(P, n), AF));
   w.tab128 = ar.take<int64_t>(std::max<int64_t>((int64_t)A * nb * 128, (int64_t)A * rows_max));
+  w.tab256 = ar.take<int64_t>((int64_t)A * nb * 128);
+  w.kofs = ar.take<int64_t>((int64_t)nb * A * 256);
   w.rowUb = ar.take<int64_t>(AF);
   w.iota_F = ar.take<int64_t>(p);
   w.iota_p = ar.take<int64_t>(std::max<int64_t>(p, AF));
@@ -400,12 +405,13 @@ void carve_band(Arena& ar, const mvb_design* d, int F, int A, BandWs& w) {
   w.Minv = ar.take<float>((int64_t)A * nb * 128 * 128);
   w.Nmat = ar.take<float>((int64_t)A * nb * 128 * 128);
   w.Pb = ar.take<float>((int64_t)A * nb * 128 * 128);
-  w.Z = ar.take<float>(n * std::max<int64_t>(P, AF));
-  w.h = ar.take<float>((int64_t)A * n);
-  w.U0 = ar.take<float>((int64_t)A * rows_max * 128);
-  w.U1 = ar.take<float>((int64_t)A * rows_max * 128);
-  w.C1 = ar.take<float>((int64_t)A * rows_max * 128);
-  w.C2 = ar.take<float>((int64_t)A * rows_max * 128);
+  w.MN = ar.take<float>((int64_t)A * nb * 128 * 256);
+  w.Z = ar.take<float>(n * std::max<int64_t>(P, AF));        // column-blocked [nb][n][128] for the sweep, later R (n x AF)
+  w.h = ar.take<float>((int64_t)2 * A * n);                   // two column halves of sum_j |u_j|^2
+  w.U0 = ar.take<float>((int64_t)A * n * 128);
+  w.U1 = ar.take<float>((int64_t)A * n * 128);
+  w.C1 = ar.take<float>((int64_t)A * F * 128);
+  w.C2 = ar.take<float>((int64_t)A * F * 128);
   w.Ct = ar.take<float>((int64_t)F * P);
   w.Ub = ar.take<float>(AF * P);
   w.Xb = ar.take<float>(AF * P);
@@ -427,22 +433,47 @@ void carve_band(Arena& ar, const mvb_design* d, int F, int A, BandWs& w) {
   w.contract_ws = ar.take<char>(w.contract_bytes);
 }
 
-__global__ void sub_cols_kernel(float* __restrict__ Z, int64_t rows, int64_t cols, const double* __restrict__ c) {
-  const int64_t total = rows * cols;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
-    Z[e] = (float)((double)Z[e] - c[e % cols]);
+// column-blocked Z [nb][rows][128]: Z[blk][r][c] -= cz[blk * 128 + c]
+__global__ void sub_cols_blocked_kernel(float* __restrict__ Z, int64_t rows, int64_t nb, const double* __restrict__ c) {
+  const int64_t total = nb * rows * 128;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t blk = e / (rows * 128);
+    Z[e] = (float)((double)Z[e] - c[blk * 128 + (e & 127)]);
+  }
+}
+// k offsets (relative to Zblk) of the fused forward substitution operand [ z_j | u_{j-1}(alpha) ], table [nb][A][256]:
+// u_{j-1} lives in U1 for odd j and in U0 for even j (ping-pong); off_u0 / off_u1 = element distance of U0 / U1 from Zblk
+__global__ void sweep_koff_kernel(int64_t* __restrict__ kofs, int nb, int A, int64_t n, int64_t off_u0, int64_t off_u1) {
+  const int64_t total = (int64_t)nb * A * 256;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(e & 255);
+    const int64_t ja = e >> 8;
+    const int64_t j = ja / A, a = ja - j * A;
+    if (k < 128) kofs[e] = j * n * 128 + k;
+    else kofs[e] = ((j & 1) ? off_u0 : off_u1) + a * n * 128 + (k - 128);
+  }
 }
 __global__ void pad_double_kernel(const float* __restrict__ in, int64_t n_in, int64_t n_out, double* out) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_out; e += (int64_t)gridDim.x * blockDim.x)
     out[e] = e < n_in ? (double)in[e] : 0.0;
 }
 // d[i][a] = 1 - c0 - h[a][i]
-__global__ void leverage_to_d_kernel(const float* __restrict__ h, int64_t n, int A, float c0, float* d) {
+__global__ void leverage_to_d_kernel(const float* __restrict__ h, int64_t n, int A, float c0, float* d, int halves) {
   const int64_t total = n * A;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = e / A; const int a = (int)(e - i * A);
-    d[e] = 1.f - c0 - h[(int64_t)a * n + i];
+    float hv = h[(int64_t)a * n + i];
+    if (halves == 2) hv += h[(int64_t)(A + a) * n + i];
+    d[e] = 1.f - c0 - hv;
   }
+}
+
+// helper stream for work that is independent of the caller's stream for a while (forked / joined with events)
+cudaStream_t side_stream() {
+  static cudaStream_t s = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] { cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); });
+  return s;
 }
 
 // batched (over alpha) 128-wide contraction  C[a][r][0..128) = sum_c Aop(a; r, c) * Bop(a; *, c)
@@ -499,46 +530,59 @@ int ridge_solve_band(const mvb_design* d, const float* y, int F, float* G, const
     if (nl < 0) return fail(MVB_E_CUDA, "band reduction failed: %s", cudaGetErrorString(err));
     g_launches.fetch_add(nl, std::memory_order_relaxed);
   }
-  // 2. block Cholesky per alpha -> Minv, N, Pb
+  // 2. block Cholesky per alpha -> Minv, N, Pb, [Minv | -N].  Only 20 CTAs and independent of Z: runs on a side stream
+  //    concurrently with the Z contraction and joins before the substitution sweep.
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   {
     static bool attr_set = false;
     if (!attr_set) {
       MVB_CUDA(cudaFuncSetAttribute(mvb::bl::block_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mvb::bl::CHOL_SMEM));
       attr_set = true;
     }
-    mvb::bl::block_chol_kernel<<<A, 1024, mvb::bl::CHOL_SMEM, st>>>(w.Tdiag, w.Tsub, (int)nb, alphas, w.Minv, w.Nmat, w.Pb);
+    cudaStream_t side = side_stream();
+    MVB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    MVB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    MVB_CUDA(cudaEventRecord(ev_fork, st));
+    MVB_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+    mvb::bl::block_chol_kernel<<<A, 1024, mvb::bl::CHOL_SMEM, side>>>(w.Tdiag, w.Tsub, (int)nb, alphas, w.Minv, w.Nmat, w.Pb, w.MN);
     MVB_LAUNCHED();
+    MVB_CUDA(cudaEventRecord(ev_join, side));
   }
-  // 3. Z = X_t Qt^T (implicit design rows x basis vectors), centred: Z -= Qt mu
+  // 3. Z = X_t Qt^T (implicit design rows x basis vectors) in column blocks [nb][n][128], centred: Z -= Qt mu
   const int qmode = dense_mode(P, (int)p, w.Qt, 4);
   mvb_operand opRows{d->xp, w.row_off, w.col_off, (int)n, 0};
   mvb_operand opQt{w.Qt, w.rowP, w.iota, (int)P, qmode};
   int rc;
-  { ProfScope ps(PC_LEVERAGE_Z); rc = run_contract<float>(opRows, opQt, (int)n, (int)P, (int)p, w.Z, P, 0, w.contract_ws, w.contract_bytes, st); }
+  { ProfScope ps(PC_LEVERAGE_Z); rc = run_contract<float>(opRows, opQt, (int)n, (int)P, (int)p, w.Z, P, 0, w.contract_ws, w.contract_bytes, st, 128, n * 128); }
   if (rc) return rc;
   mvb::matvec_rows_kernel<float><<<cdiv(P * 32, 256), 256, 0, st>>>(w.Qt, P, P, w.mu64, w.cz);    MVB_LAUNCHED();
-  sub_cols_kernel<<<grid_for(n * P), 256, 0, st>>>(w.Z, n, P, w.cz);                                MVB_LAUNCHED();
-  // 4. forward substitution over the blocks for every (alpha, row): h = sum_j |u_j|^2
-  MVB_CUDA(cudaMemsetAsync(w.h, 0, (size_t)A * n * 4, st));
+  sub_cols_blocked_kernel<<<grid_for(n * P), 256, 0, st>>>(w.Z, n, nb, w.cz);                        MVB_LAUNCHED();
+  MVB_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+  MVB_CUDA(cudaEventDestroy(ev_fork));
+  MVB_CUDA(cudaEventDestroy(ev_join));
+  // 4. forward substitution over the blocks for every (alpha, row) as ONE K = 256 contraction per block:
+  //    u_j = [Minv_j | -N_j] [z_j ; u_{j-1}],  h += |u_j|^2 in the epilogue (two column halves, added at the end)
+  MVB_CUDA(cudaMemsetAsync(w.h, 0, (size_t)2 * A * n * 4, st));
   {
-    float* Ucur = w.U0; float* Uprev = w.U1;
+    sweep_koff_kernel<<<grid_for(nb * A * 256), 256, 0, st>>>(w.kofs, (int)nb, A, n, w.U0 - w.Z, w.U1 - w.Z);   MVB_LAUNCHED();
+    mvb::iota_offsets_kernel<<<grid_for((int64_t)A * nb * 128), 256, 0, st>>>(w.tab256, (int64_t)A * nb * 128, 256);   MVB_LAUNCHED();
     for (int j = 0; j < nb; ++j) {
-      mvb::GatherOperand az{w.Z, w.rowP, w.iota + (int64_t)j * 128, (int)n, 2};
-      mvb::GatherOperand bm{w.Minv, w.tab128 + (int64_t)j * 128, w.iota, 128, 2};
-      rc = band_gemm(az, 0, bm, nb * 128, 0, (int)n, A, w.C1, PC_OTHER, st);
-      if (rc) return rc;
-      if (j > 0) {
-        mvb::GatherOperand au{Uprev, w.tab128, w.iota, (int)n, 2};
-        mvb::GatherOperand bn{w.Nmat, w.tab128 + (int64_t)j * 128, w.iota, 128, 2};
-        rc = band_gemm(au, n, bn, nb * 128, 0, (int)n, A, w.C2, PC_OTHER, st);
-        if (rc) return rc;
-      }
-      mvb::bl::recur_update_kernel<<<cdiv((int64_t)A * n * 32, 256), 256, 0, st>>>(w.C1, j > 0 ? w.C2 : nullptr, (int64_t)A * n, Ucur, 128, w.h);
-      MVB_LAUNCHED();
-      std::swap(Ucur, Uprev);
+      mvb::TcGemmParams g = mvb::tc_gemm_defaults();
+      g.A = mvb::GatherOperand{w.Z, w.tab128, w.kofs + (int64_t)j * A * 256, (int)n, 2};      // rows r -> r * 128
+      g.B = mvb::GatherOperand{w.MN, w.tab256 + (int64_t)j * 128, w.iota, 128, 2};
+      g.M = (int)n; g.N = 128; g.K = j > 0 ? 256 : 128; g.ldc = 128; g.batch = A;
+      g.a_koff_batch = 256; g.b_roff_batch = nb * 128;
+      g.C = (j & 1) ? w.U1 : w.U0;
+      g.c_batch_stride = n * 128;
+      g.rowsq = w.h;
+      g_prof_class = PC_OTHER;
+      const int slot = prof_begin(2.0 * n * 128.0 * g.K * A, st);
+      MVB_CUDA(mvb::tc_gemm_launch(g, 1, 128, st));
+      prof_end(slot, st);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
     }
   }
-  leverage_to_d_kernel<<<grid_for(n * A), 256, 0, st>>>(w.h, n, A, fit_intercept ? 1.f / (float)n : 0.f, w.dd);   MVB_LAUNCHED();
+  leverage_to_d_kernel<<<grid_for(n * A), 256, 0, st>>>(w.h, n, A, fit_intercept ? 1.f / (float)n : 0.f, w.dd, 2);   MVB_LAUNCHED();
   // 5. beta for every alpha:  Ct[f] = Qt b_f ;  L u = Ct ;  L^T x = u ;  beta = Qt^T x
   {
     mvb_operand opB{XtY, w.iota, w.iota_F, F, 0};            // rows f (contiguous), contraction j (stride F)

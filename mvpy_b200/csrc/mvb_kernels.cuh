@@ -197,13 +197,14 @@ __global__ void __launch_bounds__(256) simt_contract_kernel(GOp<T> A, GOp<T> B, 
 // out[m][n] = sum_z part[z][m][n]   (round-to-nearest adds of split-K partials, fixed order)
 template <typename T>
 __global__ void reduce_splits_kernel(const T* __restrict__ part, int splits, int64_t split_stride, int M, int N,
-                                     int64_t ld_part, T* out, int64_t ld_out) {
+                                     int64_t ld_part, T* out, int64_t ld_out, int block_cols = 0, int64_t block_stride = 0) {
   const int64_t total = (int64_t)M * N;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = i / N, n = i - m * N;
     typename Acc<T>::type s = 0;
     for (int z = 0; z < splits; ++z) s += part[z * split_stride + m * ld_part + n];
-    out[m * ld_out + n] = (T)s;
+    if (block_cols > 0) out[(n / block_cols) * block_stride + m * block_cols + (n % block_cols)] = (T)s;   // column-blocked C
+    else out[m * ld_out + n] = (T)s;
   }
 }
 

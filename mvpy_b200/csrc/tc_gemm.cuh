@@ -50,6 +50,11 @@ struct TcGemmParams {
   int64_t c_batch_stride;             // per-batch offset of C (elements), used when c_roff == nullptr
   const int64_t* c_roff;              // optional [batch][M] element offsets of the output rows
   const unsigned int* skip_flag;      // optional: the whole launch is a no-op when *skip_flag != 0
+  // ---- output options ----
+  int c_block_cols;                   // > 0: C is stored in column blocks, [N / c_block_cols][M][c_block_cols]
+  int64_t c_block_stride;             //      elements between consecutive column blocks (>= M * c_block_cols)
+  float* rowsq;                       // optional [2][batch][M]: += sum over this thread's columns of C[m][n]^2
+                                      // (one output tile wide only: N <= BN; split-K not allowed)
 };
 
 inline TcGemmParams tc_gemm_defaults() {
@@ -401,12 +406,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
     const int64_t crow_off = (gm < p.M) ? (p.c_roff ? p.c_roff[(int64_t)batch_id * p.M + gm]
                                                      : (int64_t)batch_id * p.c_batch_stride + (int64_t)gm * p.ldc)
                                         : 0;
+    if (gm < p.M && p.rowsq) {
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < NACC; ++j)
+        if (n0 + col_half * NACC + j < p.N) sq += acc[j] * acc[j];
+      p.rowsq[((int64_t)col_half * p.batch + batch_id) * p.M + gm] += sq;
+    }
     if (gm < p.M) {
 #pragma unroll
       for (int cc = 0; cc < NACC / 32; ++cc) {
         const int c0 = col_half * NACC + cc * 32;
         if (n0 + c0 < p.N) {
           float* crow = Cz + crow_off + n0 + c0;
+          if (p.c_block_cols > 0) {
+            const int cg = n0 + c0;   // 32-aligned, so the group never straddles a column block (block width % 32 == 0)
+            crow = Cz + (int64_t)(cg / p.c_block_cols) * p.c_block_stride + (int64_t)gm * p.c_block_cols + (cg % p.c_block_cols);
+          }
           const int nvalid = min(32, p.N - (n0 + c0));
           if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
 #pragma unroll
