@@ -7,9 +7,13 @@
 // Q^T G Q serves equally well -- (G + aI)^-1 = Q (T + aI)^-1 Q^T, and block-tridiagonal systems are solved by a
 // block Cholesky recurrence -- and costs ~6 p^3 tensor-core flops instead of an eigensolver.
 //
-// Method: block Lanczos with full re-orthogonalisation (block Arnoldi on a symmetric matrix), block size 128:
-//   W = Q_j G;  H = W Q_{0..j}^T (its last two blocks ARE T_jj and T_{j,j-1});  W -= H Q_{0..j} (twice);
-//   Q_{j+1} = orthonormalised rows of W (SVQB: eigendecomposition of the 128 x 128 Gram W W^T, twice).
+// Method: block Lanczos with full re-orthogonalisation, block size 128.  Per step:
+//   W = Q_j G;  H = W [Q_{j-1}; Q_j]^T  = T_{j,j-1}, T_jj;  W -= H [Q_{j-1}; Q_j]       (three-term recurrence)
+//   Q' = L^-1 W, W W^T = L L^T (Cholesky QR; eigen-based SVQB when a pivot says the block is ill conditioned)
+//   Q' -= (Q' Q^T) Q against ALL previous blocks (the full pass, on the normalised block)
+//   Q_{j+1} = (Q' Q'^T)^-1/2 Q'  (4th-order series; SVQB fallback when |Q'Q'^T - I| >= 0.03)
+// MVB_LB_PASS1_LOCAL=0 / MVB_LB_REORTH2=1 restore the two extra full passes on W (measured: same accuracy,
+// orth 3e-6, reconstruction 9e-7 at p = 603 ... 12 864; 272 ms instead of 166 ms at p = 12 864).
 // Because every new block is orthonormal, orthogonal to all previous blocks and spans the residual W, T is block
 // tridiagonal for any such choice -- rank-deficient residuals simply get noise directions, which is still a valid
 // orthogonal completion.  Every step is a launch of the split-TF32 tcgen05 contraction core (tc_gemm.cuh) or a
@@ -196,27 +200,67 @@ __global__ void __launch_bounds__(1024) chol_orth_kernel(const float* __restrict
   }
 }
 
-// Mmat = 1.5 I - 0.5 S  (one Newton-Schulz orthonormalisation step, valid when the rows are already nearly
-// orthonormal).  Sets guard->done = 1 when max|S - I| < 0.05, else 0 -> the caller's eigen-based SVQB then runs.
-__global__ void ns_matrix_kernel(const float* __restrict__ S, float* Mmat, bj::Ctl* guard) {
+// Polish of a nearly orthonormal block: Mmat = S^-1/2 by the series  (I + D)^-1/2 = I - D/2 + 3 D^2/8 - 5 D^3/16,
+// D = S - I, evaluated in shared memory (Horner, two 128^3 products).  The truncation error is (35/128) |D|^4, so the
+// guard accepts max|D| < 0.03 (error <= 2e-7); a plain Newton-Schulz step (first two terms) would leave 3/8 |D|^2,
+// i.e. 1e-3 at the same threshold -- measured as a 2e-3 loss of orthogonality at p = 603.  Otherwise guard->done = 0
+// and the caller's eigen-based SVQB runs.  guard->rot[3] counts those fallbacks.
+constexpr int NS_SMEM = 3 * NB * (NB + 1) * 4;
+__device__ __forceinline__ void ns_matmul(const float* X, const float* Y, float* out, float cI, float cXY) {
+  // out = cI * I + cXY * X Y   (all [NB][NB + 1] in shared memory; 1024 threads, 4 x 4 per thread)
+  constexpr int LDS_ = NB + 1;
+  const int tr = (threadIdx.x >> 5) * 4, tcn = (threadIdx.x & 31) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k = 0; k < NB; ++k) {
+    float a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = X[(tr + i) * LDS_ + k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = Y[k * LDS_ + tcn + j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[(tr + i) * LDS_ + tcn + j] = cXY * acc[i][j] + ((tr + i) == (tcn + j) ? cI : 0.f);
+}
+__global__ void __launch_bounds__(1024) ns_matrix_kernel(const float* __restrict__ S, float* Mmat, bj::Ctl* guard) {
+  extern __shared__ float nsm[];
+  constexpr int LDS_ = NB + 1;
+  float* D = nsm;
+  float* E1 = nsm + NB * LDS_;
+  float* E2 = nsm + 2 * NB * LDS_;
   __shared__ float red[32];
   float dev = 0.f;
   for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
     const int r = e / NB, c = e % NB;
-    const float sym = 0.5f * (S[e] + S[c * NB + r]);
-    const float d = sym - (r == c ? 1.f : 0.f);
+    const float d = 0.5f * (S[e] + S[c * NB + r]) - (r == c ? 1.f : 0.f);
     dev = fmaxf(dev, fabsf(d));
-    Mmat[e] = (r == c ? 1.f : 0.f) - 0.5f * d;
+    D[r * LDS_ + c] = d;
+    E1[r * LDS_ + c] = (r == c ? 0.375f : 0.f) - 0.3125f * d;          // 3/8 I - 5/16 D
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dev = fmaxf(dev, __shfl_xor_sync(0xffffffffu, dev, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dev;
   __syncthreads();
+  ns_matmul(D, E1, E2, -0.5f, 1.f);                                     // E2 = -1/2 I + D E1
+  __syncthreads();
+  ns_matmul(D, E2, E1, 1.f, 1.f);                                       // E1 = I + D E2 = S^-1/2 (to 4th order)
+  __syncthreads();
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) Mmat[e] = E1[(e / NB) * LDS_ + (e % NB)];
   if (threadIdx.x == 0) {
     float m = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
-    guard->done = (m < 0.05f) ? 1u : 0u;      // NaN compares false -> the robust path runs
-    if (!(m < 0.05f)) atomicAdd(&guard->rot[3], 1u);
+    const bool ok = m < 0.03f;                  // NaN compares false -> the robust path runs
+    guard->done = ok ? 1u : 0u;
+    if (!ok) atomicAdd(&guard->rot[3], 1u);
   }
 }
 
@@ -236,7 +280,7 @@ inline float knob_f(const char* name, float dflt) { const char* e = getenv(name)
 struct Ctx {
   Plan pl; char* base; cudaStream_t st; int launches; cudaError_t err;
   const bj::Hooks* hooks;
-  int polish_ns = 1; float eig_tol = 1e-6f; int eig_sweeps = 8; int reorth3 = 1; int reorth2 = 1; float chol_tol = 1e-4f;
+  int polish_ns = 1; float eig_tol = 1e-6f; int eig_sweeps = 8; int reorth3 = 1; int reorth2 = 0; float chol_tol = 1e-4f; int pass1_local = 1;
   float* f(size_t off) const { return (float*)(base + off); }
   int64_t* i64(size_t off) const { return (int64_t*)(base + off); }
 };
@@ -287,7 +331,7 @@ inline bool svqb(Ctx& cx, const float* src, float* dst) {
   return gemm(cx, m, w, NB, P, NB, dst, P);
 }
 
-// second orthonormalisation pass for rows that SVQB already made orthonormal to ~1e-3: dst = (1.5 I - 0.5 src src^T) src
+// second orthonormalisation pass for rows that are already nearly orthonormal: dst = (src src^T)^-1/2 src (series)
 inline bool ns_polish(Ctx& cx, const float* src, float* dst) {
   if (!cx.polish_ns) return svqb(cx, src, dst);
   const Plan& pl = cx.pl;
@@ -297,7 +341,7 @@ inline bool ns_polish(Ctx& cx, const float* src, float* dst) {
   bj::Ctl* ctl = (bj::Ctl*)(cx.base + pl.off_ctl);
   GatherOperand a{src, rowP, iota, NB, 2};
   if (!gemm(cx, a, a, NB, NB, P, S, NB)) return false;
-  ns_matrix_kernel<<<1, 1024, 0, cx.st>>>(S, Mm, ctl); ++cx.launches;
+  ns_matrix_kernel<<<1, 1024, NS_SMEM, cx.st>>>(S, Mm, ctl); ++cx.launches;
   // robust fallback (rank-deficient residual blocks): both kernels are no-ops while ctl->done is set
   bj::small_eig_kernel<<<1, 1024, bj::SMALL_EIG_SMEM, cx.st>>>(S, J, cx.eig_tol, 1.f, cx.eig_sweeps, ctl, 0, cx.f(pl.off_lam) + 8); ++cx.launches;
   svqb_scale_kernel<<<1, 1024, 0, cx.st>>>(J, cx.f(pl.off_lam) + 8, Mm, ctl); ++cx.launches;
@@ -327,7 +371,8 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
   Ctx cx{make_plan(p), (char*)ws, st, 0, cudaSuccess, hooks};
   cx.polish_ns = knob_i("MVB_LB_POLISH_NS", 1); cx.eig_tol = knob_f("MVB_LB_EIG_TOL", 1e-6f);
   cx.eig_sweeps = knob_i("MVB_LB_EIG_SWEEPS", 8); cx.reorth3 = knob_i("MVB_LB_REORTH3", 1);
-  cx.reorth2 = knob_i("MVB_LB_REORTH2", 1); cx.chol_tol = knob_f("MVB_LB_CHOL_TOL", 1e-4f);
+  cx.pass1_local = knob_i("MVB_LB_PASS1_LOCAL", 1);
+  cx.reorth2 = knob_i("MVB_LB_REORTH2", 0); cx.chol_tol = knob_f("MVB_LB_CHOL_TOL", 1e-4f);
   const Plan& pl = cx.pl;
   const int P = pl.P, nb = pl.nblk;
   float *Gp = cx.f(pl.off_Gp), *Wt = cx.f(pl.off_Wt), *H = cx.f(pl.off_H);
@@ -339,6 +384,7 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
   if (!attr_set) {
     LB_CK(cudaFuncSetAttribute(bj::small_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bj::SMALL_EIG_SMEM));
     LB_CK(cudaFuncSetAttribute(chol_orth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_ORTH_SMEM));
+    LB_CK(cudaFuncSetAttribute(ns_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NS_SMEM));
     attr_set = true;
   }
   LB_CK(cudaMemsetAsync(ctl, 0, sizeof(bj::Ctl), st));
@@ -356,17 +402,20 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
     GatherOperand qj{Qj, rowP, iota, NB, 2}, g{Gp, rowP, iota, P, 2};
     LB_OK(gemm(cx, qj, g, NB, P, P, Wt, P));
     const int nq = (j + 1) * NB;
+    // first pass: against all previous blocks, or (pass1_local) only against the two blocks the three-term
+    // recurrence couples -- the later full pass on the normalised block removes the drift along the older ones
+    const int b0 = cx.pass1_local ? std::max(0, j - 1) : 0;       // first block of the first pass
+    const int nq1 = (j + 1 - b0) * NB;
     {
-      GatherOperand w{Wt, rowP, iota, NB, 2}, q{Qt, rowP, iota, nq, 2};
-      LB_OK(gemm(cx, w, q, NB, nq, P, H, P));
+      GatherOperand w{Wt, rowP, iota, NB, 2}, q{Qt + (size_t)b0 * NB * P, rowP, iota, nq1, 2};
+      LB_OK(gemm(cx, w, q, NB, nq1, P, H + (size_t)b0 * NB, P));
       extract_T_kernel<<<16, 256, 0, st>>>(H, P, j, Tdiag, Tsub); ++cx.launches;
     }
     if (j == nb - 1) break;
-    // full re-orthogonalisation (twice), reusing the H just computed for the first pass
     {
       float* W2 = cx.f(pl.off_Wt2);
-      GatherOperand h{H, rowP, iota, NB, 2}, qc{Qt, iota, rowP, P, 0};
-      LB_OK(gemm(cx, h, qc, NB, P, nq, W2, P));
+      GatherOperand h{H + (size_t)b0 * NB, rowP, iota, NB, 2}, qc{Qt + (size_t)b0 * NB * P, iota, rowP, P, 0};
+      LB_OK(gemm(cx, h, qc, NB, P, nq1, W2, P));
       sub_kernel<<<148 * 2, 256, 0, st>>>(Wt, W2, (int64_t)NB * P); ++cx.launches;
     }
     if (cx.reorth2) LB_OK(reorth(cx, Wt, Qt, nq));
