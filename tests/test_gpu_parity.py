@@ -318,3 +318,92 @@ def test_contract_tensor_core_vs_fp64():
     vr, vk = (torch.arange(50) * p).cuda(), torch.arange(p).cuda()
     Z32 = mv._lib.contract(xp, row, col, 0, V, vr, vk, 1, n, 50, p)
     assert float((Z32.double() - Xt @ V.double().mT).abs().max()) / float((Xt @ V.double().mT).abs().max()) < 2e-6
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ragged / edge shapes through both solver routes, and size-independent properties at BASELINE configs[1] size
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('route', ['eigen', 'band'])
+@pytest.mark.parametrize('case', [
+    dict(N=9, C=2, T=37, F=1, lags=(-0.9, 0.3), fs=70, icpt=True, per_target=False),      # odd T, one target, both lag signs
+    dict(N=7, C=5, T=50, F=3, lags=(-0.5, 0.0), fs=60, icpt=False, per_target=True),      # no intercept, alpha per target
+    dict(N=11, C=3, T=64, F=4, lags=(0.0, 0.7), fs=64, icpt=True, per_target=True),       # causal-only lags
+])
+def test_trf_ragged_shapes_both_routes(case, route, monkeypatch):
+    """Sizes that are not multiples of any tile (p = 130 ... 155, n = 333 ... 704), intercept / per-target variants.
+    The band route (block-Lanczos reduction + block-Cholesky sweep) is forced for small p through MVB_BAND_MIN_P."""
+    mv, orc = _mv(), _orc()
+    monkeypatch.setenv('MVB_BAND_MIN_P', '128' if route == 'band' else '1000000')
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(case['N'], case['C'], case['T'], generator=g)
+    B = torch.randn(case['F'], case['C'], generator=g) * 0.6
+    y = torch.einsum('fc,nct->nft', B, X) + 0.8 * torch.randn(case['N'], case['F'], case['T'], generator=g) + 0.25
+    X = X + 0.1
+    alphas = torch.logspace(-3, 4, 12)
+    t_min, t_max = case['lags']
+    td = mv.estimators.TimeDelayed(t_min, t_max, case['fs'], alphas=alphas, fit_intercept=case['icpt'],
+                                   alpha_per_target=case['per_target'])
+    td.fit(X.cuda(), y.cuda())
+    win = orc.lag_window(t_min, t_max, case['fs'])
+    assert td.coef_.shape == (case['F'], case['C'], len(win))
+    if route == 'band':
+        assert case['C'] * len(win) >= 128
+    ref = orc.trf_fit(X.double(), y.double(), win, alphas.double(), fit_intercept=case['icpt'],
+                      alpha_per_target=case['per_target'], solver=orc.ridge_loo_fit_primal)
+    assert torch.equal(td.estimator.alpha_.cpu().double().reshape(-1), ref['alpha'].reshape(-1))     # same grid points chosen
+    ref_coef = ref['flat_coef'].numpy()
+    np.testing.assert_allclose(td.estimator.coef_.cpu().numpy(), ref_coef, rtol=1e-4, atol=1e-4 * np.abs(ref_coef).max())
+    yh = td.predict(X.cuda())
+    yh_ref = orc.trf_predict(X.double(), win, ref['flat_coef'], ref['intercept'])
+    np.testing.assert_allclose(yh.cpu().numpy(), yh_ref.numpy(), atol=2e-4)
+    r2 = mv.math.r2(y.cuda().movedim(0, -1), yh.movedim(0, -1))
+    r2_ref = orc.r2_last(orc.move_reduce_last(y.double(), (0,)), orc.move_reduce_last(yh_ref, (0,)))
+    np.testing.assert_allclose(r2.cpu().numpy(), r2_ref.numpy(), atol=1e-4)
+
+
+def test_cfg2_size_properties():
+    """BASELINE configs[1] size (n = 38 400 rows, p = 12 864 columns, 306 channels, 20 alphas): the oracle cannot run
+    here in seconds, so check properties that do not depend on size."""
+    mv = _mv()
+    torch.manual_seed(0)
+    X, y = mv.dataset.make_meeg_continuous(fs=200, n_features=64, n_channels=306)
+    X, y = X.cuda(), y.cuda()
+    alphas = torch.logspace(-5, 5, 20)
+    folds = list(mv.crossvalidation.KFold(5).split(X))
+    assert torch.equal(torch.cat([te for _, te in folds]).sort().values.cpu(), torch.arange(120))       # folds partition the trials
+    tr, te = folds[0]
+    sc = mv.preprocessing.Scaler().to_torch().fit(X[tr])
+    Xs_tr, Xs_te = sc.transform(X[tr]), sc.transform(X[te])
+    td = mv.estimators.TimeDelayed(-1.0, 0.0, 200, alphas=alphas)
+    td.fit(Xs_tr, y[tr])
+    assert td.coef_.shape == (306, 64, 201) and torch.isfinite(td.coef_).all()
+    assert float(td.estimator.alpha_) in [float(a) for a in alphas]
+    # 1. normal equations at the chosen alpha: (G + alpha I) beta = X_c^T y_c, with G, b rebuilt by the stats entry point
+    from mvpy_b200 import _lib
+    design = td._design(Xs_tr)
+    G, XtY, mu, ybar = _lib.trf_stats(design, y[tr].contiguous(), True)
+    beta = td.estimator.coef_.double()                                             # (F, p)
+    lhs = beta @ G.double() + float(td.estimator.alpha_) * beta
+    rel = ((lhs - XtY.double().T).norm() / XtY.double().norm()).item()
+    assert rel < 1e-4, rel
+    icpt = ybar.double() - beta @ mu.double()
+    np.testing.assert_allclose(td.intercept_.reshape(-1).cpu().numpy(), icpt.cpu().numpy(), atol=1e-5)
+    # 2. prediction is affine in the stimulus:  f(a + b) - f(0) = (f(a) - f(0)) + (f(b) - f(0))
+    a, b = Xs_te[:4], Xs_te[4:8]
+    f0 = td.predict(torch.zeros_like(a))
+    lin = (td.predict(a + b) - f0) - ((td.predict(a) - f0) + (td.predict(b) - f0))
+    assert lin.abs().max().item() < 5e-4 * td.predict(a).abs().max().item()
+    # 3. scoring: a perfect prediction scores r2 = pearson = 1; rescaling / shifting the prediction leaves pearson unchanged
+    yh = td.predict(Xs_te)
+    yt = y[te].movedim(0, -1)
+    assert torch.allclose(mv.math.r2(yt, yt), torch.ones(306, 400, device='cuda'))
+    r_a = mv.math.pearsonr(yt, yh.movedim(0, -1))
+    r_b = mv.math.pearsonr(yt, (3.0 * yh + 0.5).movedim(0, -1))
+    ok = torch.isfinite(r_a)
+    assert ok.float().mean() > 0.5 and (r_a[ok] - r_b[ok]).abs().max().item() < 1e-4
+    # 4. r2 against the training-mean baseline (validator.py:70-89) is finite everywhere and identical to the formula
+    yb = y[tr].mean(0, keepdim=True).movedim(0, -1)
+    r2 = mv.math.r2(yt, yh.movedim(0, -1), yb)
+    num = ((yt - yh.movedim(0, -1)).double() ** 2).sum(-1)
+    den = ((yt - yb).double() ** 2).sum(-1)
+    assert torch.isfinite(r2).all() and (r2.double() - (1 - num / den)).abs().max().item() < 1e-5
