@@ -111,7 +111,7 @@ int mvb_eigh(void* A, void* Vt, void* lam, int batch, int p, int dtype, void* ws
  * Large-p replacement for the decomposition in ridgecv.py:218: G (p x p, symmetric) is padded to
  * P = mvb_band_padded(p) (multiple of 128) and reduced to  Gp = Qt^T T Qt  with Qt (P x P) orthogonal
  * (rows = basis vectors) and T block tridiagonal: Tdiag[j], Tsub[j] = T_{j,j-1} ([P/128][128][128]).
- * mvb_ridge_solve uses it internally (block-Cholesky LOO sweep) when p >= 512.                    */
+ * mvb_ridge_solve uses it internally (block-Cholesky LOO sweep) when p >= 128 (fp32).                    */
 int mvb_band_padded(int p);
 size_t mvb_band_reduce_workspace_bytes(int p);
 int mvb_band_reduce(const void* G, int p, void* Qt, void* Tdiag, void* Tsub, void* ws, size_t ws_bytes, void* stream);

@@ -366,7 +366,7 @@ __global__ void to_double_kernel(const T* __restrict__ in, int64_t n, double* ou
 // ---- band path: block-tridiagonal reduction + block-Cholesky LOO sweep (fp32, large p) ---------------------
 int band_min_p() {
   const char* e = getenv("MVB_BAND_MIN_P");
-  int v = e ? atoi(e) : 512;
+  int v = e ? atoi(e) : 128;
   if (v < 128) v = 128;
   return v;
 }
