@@ -407,7 +407,7 @@ void carve_band(Arena& ar, const mvb_design* d, int F, int A, BandWs& w) {
   w.Pb = ar.take<float>((int64_t)A * nb * 128 * 128);
   w.MN = ar.take<float>((int64_t)A * nb * 128 * 256);
   w.Z = ar.take<float>(n * std::max<int64_t>(P, AF));        // column-blocked [nb][n][128] for the sweep, later R (n x AF)
-  w.h = ar.take<float>((int64_t)2 * A * n);                   // two column halves of sum_j |u_j|^2
+  w.h = ar.take<float>((int64_t)mvb::TC_ROWSQ_PARTS * A * n);   // column parts of sum_j |u_j|^2
   w.U0 = ar.take<float>((int64_t)A * n * 128);
   w.U1 = ar.take<float>((int64_t)A * n * 128);
   w.C1 = ar.take<float>((int64_t)A * F * 128);
@@ -462,8 +462,8 @@ __global__ void leverage_to_d_kernel(const float* __restrict__ h, int64_t n, int
   const int64_t total = n * A;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = e / A; const int a = (int)(e - i * A);
-    float hv = h[(int64_t)a * n + i];
-    if (halves == 2) hv += h[(int64_t)(A + a) * n + i];
+    float hv = 0.f;
+    for (int part = 0; part < halves; ++part) hv += h[((int64_t)part * A + a) * n + i];
     d[e] = 1.f - c0 - hv;
   }
 }
@@ -562,7 +562,7 @@ int ridge_solve_band(const mvb_design* d, const float* y, int F, float* G, const
   MVB_CUDA(cudaEventDestroy(ev_join));
   // 4. forward substitution over the blocks for every (alpha, row) as ONE K = 256 contraction per block:
   //    u_j = [Minv_j | -N_j] [z_j ; u_{j-1}],  h += |u_j|^2 in the epilogue (two column halves, added at the end)
-  MVB_CUDA(cudaMemsetAsync(w.h, 0, (size_t)2 * A * n * 4, st));
+  MVB_CUDA(cudaMemsetAsync(w.h, 0, (size_t)mvb::TC_ROWSQ_PARTS * A * n * 4, st));
   {
     sweep_koff_kernel<<<grid_for(nb * A * 256), 256, 0, st>>>(w.kofs, (int)nb, A, n, w.U0 - w.Z, w.U1 - w.Z);   MVB_LAUNCHED();
     mvb::iota_offsets_kernel<<<grid_for((int64_t)A * nb * 128), 256, 0, st>>>(w.tab256, (int64_t)A * nb * 128, 256);   MVB_LAUNCHED();
@@ -582,7 +582,7 @@ int ridge_solve_band(const mvb_design* d, const float* y, int F, float* G, const
       g_launches.fetch_add(1, std::memory_order_relaxed);
     }
   }
-  leverage_to_d_kernel<<<grid_for(n * A), 256, 0, st>>>(w.h, n, A, fit_intercept ? 1.f / (float)n : 0.f, w.dd, 2);   MVB_LAUNCHED();
+  leverage_to_d_kernel<<<grid_for(n * A), 256, 0, st>>>(w.h, n, A, fit_intercept ? 1.f / (float)n : 0.f, w.dd, mvb::TC_ROWSQ_PARTS);   MVB_LAUNCHED();
   // 5. beta for every alpha:  Ct[f] = Qt b_f ;  L u = Ct ;  L^T x = u ;  beta = Qt^T x
   {
     mvb_operand opB{XtY, w.iota, w.iota_F, F, 0};            // rows f (contiguous), contraction j (stride F)

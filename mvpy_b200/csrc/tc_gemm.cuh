@@ -53,7 +53,7 @@ struct TcGemmParams {
   // ---- output options ----
   int c_block_cols;                   // > 0: C is stored in column blocks, [N / c_block_cols][M][c_block_cols]
   int64_t c_block_stride;             //      elements between consecutive column blocks (>= M * c_block_cols)
-  float* rowsq;                       // optional [2][batch][M]: += sum over this thread's columns of C[m][n]^2
+  float* rowsq;                       // optional [TC_ROWSQ_PARTS][batch][M]: += sum over this thread's columns of C[m][n]^2
                                       // (one output tile wide only: N <= BN; split-K not allowed)
 };
 
@@ -63,12 +63,17 @@ inline TcGemmParams tc_gemm_defaults() {
   return p;
 }
 
+constexpr int TC_ROWSQ_PARTS = 4;      // = tc::NPART (column parts of the accumulator tile)
+
 namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 32;          // fp32 elements per stage along K
 constexpr int KC = BK / 4;      // 16-byte chunks per stage row
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 512;      // 16 warps: the staging loop is latency- and issue-bound, so two CTAs' worth of warps
+constexpr int NWARPS = NTHREADS / 32;
+constexpr int NPART = NTHREADS / 128;   // column parts of the accumulator tile (one per group of four warps)
+static_assert(NPART == TC_ROWSQ_PARTS, "rowsq layout");
 // The tensor core adds into its fp32 accumulator with truncation, which biases long sums (measured:
 // error grows linearly with K).  Every DRAIN stages the TMEM tile is therefore folded into fp32
 // registers with round-to-nearest adds and the next MMA restarts the TMEM accumulator from zero.
@@ -179,6 +184,7 @@ template <int ROWS, int MODE>
 struct Loader {
   static constexpr int NV = ROWS * BK / NTHREADS;
   static constexpr int LBO = ROWS * 16 + 16;
+  static constexpr int RG_PER = (ROWS / 32) / (NWARPS / 8);   // mode 0: 32-row groups per warp
   float v[NV];
 
   __device__ __forceinline__ void fetch(const GatherOperand& op, const int64_t* sroff, int row0, int k0, int K) {
@@ -208,9 +214,10 @@ struct Loader {
     } else {
       int64_t ko[4];
       bool kok[4];
+      const int kch = warp & 7, rg0 = (warp >> 3) * RG_PER;      // 8 k-chunks x (NWARPS / 8) row-group slices
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int kg = k0 + warp * 4 + j;
+        const int kg = k0 + kch * 4 + j;
         kok[j] = kg < K;
         ko[j] = kok[j] ? op.koff[kg] : 0;
       }
@@ -219,8 +226,8 @@ struct Loader {
       const bool kcontig = kok[3] && (ko[1] - ko[0]) == 1 && (ko[2] - ko[0]) == 2 && (ko[3] - ko[0]) == 3;
       if (kcontig) {
 #pragma unroll
-        for (int rg = 0; rg < ROWS / 32; ++rg) {
-          const int r = rg * 32 + lane;
+        for (int rg = 0; rg < RG_PER; ++rg) {
+          const int r = (rg0 + rg) * 32 + lane;
           const bool rok = row0 + r < op.rows;
           const float* src = op.base + (sroff[r] + ko[0]);
 #pragma unroll
@@ -228,8 +235,8 @@ struct Loader {
         }
       } else {
 #pragma unroll
-        for (int rg = 0; rg < ROWS / 32; ++rg) {
-          const int r = rg * 32 + lane;
+        for (int rg = 0; rg < RG_PER; ++rg) {
+          const int r = (rg0 + rg) * 32 + lane;
           const bool rok = row0 + r < op.rows;
           const float* src = op.base + sroff[r];
 #pragma unroll
@@ -267,15 +274,16 @@ struct Loader {
         *reinterpret_cast<float*>(lo_plane + off) = lo;
       }
     } else {
+      const int kch = warp & 7, rg0 = (warp >> 3) * RG_PER;
 #pragma unroll
-      for (int rg = 0; rg < ROWS / 32; ++rg) {
-        const int r = rg * 32 + lane;
+      for (int rg = 0; rg < RG_PER; ++rg) {
+        const int r = (rg0 + rg) * 32 + lane;
         float4 h, l;
         split_tf32(v[rg * 4 + 0], h.x, l.x);
         split_tf32(v[rg * 4 + 1], h.y, l.y);
         split_tf32(v[rg * 4 + 2], h.z, l.z);
         split_tf32(v[rg * 4 + 3], h.w, l.w);
-        const uint32_t off = warp * LBO + r * 16;
+        const uint32_t off = kch * LBO + r * 16;
         *reinterpret_cast<float4*>(hi_plane + off) = h;
         *reinterpret_cast<float4*>(lo_plane + off) = l;
       }
@@ -339,9 +347,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
     la.fetch(opA, sroffA, m0, kb_begin * BK, p.K);
     lb.fetch(opB, sroffB, n0, kb_begin * BK, p.K);
   }
-  constexpr int NACC = BN / 2;                 // columns per thread: warps 0-3 low half, 4-7 high half
+  constexpr int NACC = BN / NPART;             // columns per thread: warps 4i .. 4i+3 own column part i
   const int q = warp & 3;                      // TMEM lane quarter this warp may access
-  const int col_half = warp >> 2;
+  const int col_half = warp >> 2;              // column part index, 0 .. NPART-1
   float acc[NACC];
 #pragma unroll
   for (int j = 0; j < NACC; ++j) acc[j] = 0.f;
