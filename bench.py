@@ -289,7 +289,7 @@ def main():
                          f'the library hook on the launching stream inside the timed region; peak = TF32 dense peak measured '
                          f'here with cuBLAS ({tf32_peak:.0f} TFLOP/s) / 3 MMAs per fp32 product (split-TF32); '
                          f'MEASURED_PEAKS bf16 = {peaks.get("bf16_tflops")} burst / {peaks.get("bf16_tflops_sustained")} sustained; '
-                         f'traffic: see profiles/ (ncu --set full of the Gram launch: dram 638 MB vs 677 MB algorithmic)',
+                         f'traffic: see profiles/ (ncu --set full of the Gram launch: dram 635 MB vs 677 MB algorithmic)',
                     by_kernel={k: dict(ms=v['ms'], n=v['n'], tflops=(v['flops'] / (v['ms'] * 1e-3) * 1e-12 if v['ms'] > 0 else 0.0),
                                        frac=(v['flops'] / (v['ms'] * 1e-3) * 1e-12 / peak_eff if v['ms'] > 0 else 0.0))
                                for k, v in prof.items()})

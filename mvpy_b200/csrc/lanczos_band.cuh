@@ -291,7 +291,7 @@ inline bool gemm(Ctx& cx, const GatherOperand& A, const GatherOperand& B, int M,
   const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
   int max_splits = (int)std::min<size_t>(64, cx.pl.part_elems / ((size_t)M * N));
   if (max_splits < 1) max_splits = 1;
-  const int splits = tc_choose_splits(tiles, (K + tc::BK - 1) / tc::BK, max_splits);
+  const int splits = tc_choose_splits(tiles, (K + tc::BK - 1) / tc::BK, max_splits, (int64_t)M * N);
   TcGemmParams g = tc_gemm_defaults();
   g.A = A; g.B = B; g.M = M; g.N = N; g.K = K;
   if (splits > 1) { g.C = cx.f(cx.pl.off_part); g.ldc = N; g.c_split_stride = (int64_t)M * N; }

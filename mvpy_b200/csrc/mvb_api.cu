@@ -133,7 +133,7 @@ SplitPlan plan_contract(int M, int N, int K, int dtype, int symmetric) {
   const int target = tc ? 148 : 296;
   int s = 1;
   if (tc) {
-    s = mvb::tc_choose_splits(tiles, cdiv(K, 32), 64);
+    s = mvb::tc_choose_splits(tiles, cdiv(K, 32), 64, (int64_t)M * N);
   } else {
     if (tiles < target) s = (int)((target + tiles - 1) / tiles);
     if (s > kblocks) s = kblocks;

@@ -496,15 +496,17 @@ inline cudaError_t launch_a(const TcGemmParams& p, int k_splits, cudaStream_t st
 }  // namespace tc
 
 // Split-K factor for `tiles` output tiles of `nkb` BK-stages each on `sms` SMs (one CTA per SM): minimise
-// waves x (stages per CTA + fixed per-CTA cost) -- e.g. 51 tiles split 3 ways is 153 CTAs = two waves for 3% more
-// parallelism, while 5 ways fills two waves almost completely.
-inline int tc_choose_splits(int64_t tiles, int nkb, int max_splits, int sms = 148) {
+// waves x (stages per CTA + fixed per-CTA cost) + the HBM time of the partial sums (s writes + s reads + 1 write of
+// out_elems floats; one stage ~ 1 us, HBM ~ 6e6 bytes/us) -- e.g. 51 skinny tiles split 3 ways are 153 CTAs = two
+// waves for 3% more parallelism while 8 ways fill three waves, but a 0.66 GB Gram is never worth splitting.
+inline int tc_choose_splits(int64_t tiles, int nkb, int max_splits, int64_t out_elems, int sms = 148) {
   int best = 1;
   double best_cost = 1e300;
   for (int s = 1; s <= max_splits; ++s) {
     if (s > 1 && s > nkb / tc::DRAIN) break;                 // keep at least one accumulation chunk per split
     const int64_t waves = (tiles * s + sms - 1) / sms;
-    const double cost = (double)waves * ((double)((nkb + s - 1) / s) + 8.0) + 0.25 * s;
+    double cost = (double)waves * ((double)((nkb + s - 1) / s) + 8.0);
+    if (s > 1) cost += (2.0 * s + 1.0) * (double)out_elems * 4.0 / 6.0e6 + 3.0;
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
   }
   return best;
