@@ -293,6 +293,15 @@ def main():
                     by_kernel={k: dict(ms=v['ms'], n=v['n'], tflops=(v['flops'] / (v['ms'] * 1e-3) * 1e-12 if v['ms'] > 0 else 0.0),
                                        frac=(v['flops'] / (v['ms'] * 1e-3) * 1e-12 / peak_eff if v['ms'] > 0 else 0.0))
                                for k, v in prof.items()})
+    if roof is not None and args.workload == 'cfg2':
+        try:          # dram traffic of the Gram launch from the committed ncu --set full capture (per launch)
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+            for k, v in tr.items():
+                if k in roof['by_kernel']:
+                    roof['by_kernel'][k]['traffic'] = v['dram_bytes_per_launch']
+                    roof['by_kernel'][k]['algorithmic_bytes'] = v['algorithmic_bytes_per_launch']
+        except Exception:
+            pass
     cb = None
     if not args.no_cpu_baseline:
         cb, _ = cpu_baseline(X, y, alphas, args.workload)
