@@ -67,6 +67,24 @@ __global__ void __launch_bounds__(1024) block_chol_kernel(const float* __restric
   float* Li = sm + 2 * NB * LD;    // L_{j-1}^-1, then L_j^-1
   const int a = blockIdx.x;
   const float alpha = alphas[a];
+  // Pivot floor (modified Cholesky): T is the computed image of a PSD Gram, so for a (numerically) singular design its
+  // smallest eigenvalues are rounding noise of either sign, ~ eps * max diag(T).  Pivots below 8 eps * max diag are
+  // raised to it: the deficient directions get a finite, tiny weight instead of NaN -- what the reference's SVD does
+  // with its noise-level singular values (ridgecv.py:223-233) -- and well-conditioned designs never reach the floor.
+  __shared__ float s_tmax;
+  __shared__ int s_cmax;
+  {
+    __shared__ float red[32];
+    float m = 0.f;
+    for (int e = threadIdx.x; e < nblk * NB; e += blockDim.x) m = fmaxf(m, fabsf(Tdiag[(int64_t)(e / NB) * NB * NB + (e % NB) * (NB + 1)]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t = fmaxf(t, red[w]); s_tmax = t; }
+    __syncthreads();
+  }
+  const float pivot_floor = fmaxf(4.8e-7f * s_tmax, 1e-30f);
   float* Minv_a = Minv + (int64_t)a * nblk * NB * NB;
   float* N_a = Nmat + (int64_t)a * nblk * NB * NB;
   float* Pb_a = Pb + (int64_t)a * nblk * NB * NB;
@@ -138,9 +156,15 @@ __global__ void __launch_bounds__(1024) block_chol_kernel(const float* __restric
       }
     }
     __syncthreads();
-    // in-place Cholesky (lower) of Cm
+    // in-place modified Cholesky (lower) of Cm: pivot_k = max(C_kk, floor, max_i C_ik^2 / tmax) -- the third term
+    // (Gill-Murray) bounds |L_ik| by sqrt(tmax) when rounding made the matrix indefinite, so the factor cannot blow up
     for (int k = 0; k < NB; ++k) {
-      const float d = sqrtf(fmaxf(Cm[k * LD + k], 1e-30f));
+      if (threadIdx.x == 0) s_cmax = 0;
+      __syncthreads();
+      if (threadIdx.x > k && threadIdx.x < NB) atomicMax(&s_cmax, __float_as_int(fabsf(Cm[threadIdx.x * LD + k])));
+      __syncthreads();
+      const float cm = __int_as_float(s_cmax);
+      const float d = sqrtf(fmaxf(fmaxf(Cm[k * LD + k], pivot_floor), cm * cm / fmaxf(s_tmax, 1e-30f)));
       __syncthreads();
       if (threadIdx.x == 0) Cm[k * LD + k] = d;
       for (int i = k + 1 + threadIdx.x; i < NB; i += blockDim.x) Cm[i * LD + k] /= d;

@@ -86,8 +86,9 @@ constexpr int SMALL_EIG_SMEM = PR * SLD * 4 + PR * PR * 4;
 
 __global__ void __launch_bounds__(1024) small_eig_kernel(const float* __restrict__ S_all, float* __restrict__ J_all,
                                                          float tol_rot, float tol_count, int max_inner, Ctl* ctl, int sweep,
-                                                         float* __restrict__ lam_out = nullptr) {
-  if (ctl->done) return;
+                                                         float* __restrict__ lam_out = nullptr,
+                                                         const unsigned int* skip = nullptr) {
+  if (ctl->done || (skip && *skip)) return;
   extern __shared__ __align__(16) unsigned char sm_raw[];
   float* J = reinterpret_cast<float*>(sm_raw);                         // [PR][PR]
   float* S = reinterpret_cast<float*>(sm_raw + PR * PR * 4);           // [PR][SLD]

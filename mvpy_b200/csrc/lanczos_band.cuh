@@ -107,12 +107,15 @@ __global__ void random_block_kernel(float* W, int64_t n, uint32_t seed) {
   }
 }
 
-__global__ void sub_kernel(float* __restrict__ W, const float* __restrict__ W2, int64_t n) {
+__global__ void sub_kernel(float* __restrict__ W, const float* __restrict__ W2, int64_t n, const unsigned int* skip = nullptr) {
+  if (skip && *skip) return;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) W[e] -= W2[e];
 }
 
 // out[z-sum] : reduce split-K partials (fixed order)
-__global__ void reduce_parts_kernel(const float* __restrict__ part, int splits, int64_t stride, int M, int N, float* out, int64_t ldo) {
+__global__ void reduce_parts_kernel(const float* __restrict__ part, int splits, int64_t stride, int M, int N, float* out, int64_t ldo,
+                                    const unsigned int* skip = nullptr) {
+  if (skip && *skip) return;
   const int64_t total = (int64_t)M * N;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = e / N, n = e - m * N;
@@ -124,8 +127,10 @@ __global__ void reduce_parts_kernel(const float* __restrict__ part, int splits, 
 
 // Mmat = diag(lam^-1/2) J  (SVQB scaling; lam sorted like the rows of J, floored far below fp32 noise).
 // guard != nullptr: no-op when guard->done is set (the Newton-Schulz matrix already in Mmat stands); clears the flag.
-__global__ void svqb_scale_kernel(const float* __restrict__ J, const float* __restrict__ lam, float* Mmat, bj::Ctl* guard) {
+__global__ void svqb_scale_kernel(const float* __restrict__ J, const float* __restrict__ lam, float* Mmat, bj::Ctl* guard,
+                                  const unsigned int* skip = nullptr) {
   __shared__ float lmax;
+  if (skip && *skip) return;
   if (guard) {
     const unsigned int skip = guard->done;
     __syncthreads();
@@ -231,8 +236,12 @@ __device__ __forceinline__ void ns_matmul(const float* X, const float* Y, float*
 #pragma unroll
     for (int j = 0; j < 4; ++j) out[(tr + i) * LDS_ + tcn + j] = cXY * acc[i][j] + ((tr + i) == (tcn + j) ? cI : 0.f);
 }
-__global__ void __launch_bounds__(1024) ns_matrix_kernel(const float* __restrict__ S, float* Mmat, bj::Ctl* guard) {
+// `skip`: no-op when *skip != 0 (a later clean-up round of a block that is already finished).  On exit guard->sweeps
+// (the "block finished" flag the later rounds test) is 1 when the series was valid, 0 when the SVQB fallback runs.
+__global__ void __launch_bounds__(1024) ns_matrix_kernel(const float* __restrict__ S, float* Mmat, bj::Ctl* guard,
+                                                         const unsigned int* skip = nullptr) {
   extern __shared__ float nsm[];
+  if (skip && *skip) return;
   constexpr int LDS_ = NB + 1;
   float* D = nsm;
   float* E1 = nsm + NB * LDS_;
@@ -260,8 +269,15 @@ __global__ void __launch_bounds__(1024) ns_matrix_kernel(const float* __restrict
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
     const bool ok = m < 0.03f;                  // NaN compares false -> the robust path runs
     guard->done = ok ? 1u : 0u;
+    guard->sweeps = ok ? 1u : 0u;
     if (!ok) atomicAdd(&guard->rot[3], 1u);
   }
+}
+
+__global__ void latch_kernel(unsigned int* dst, const unsigned int* src) { if (threadIdx.x == 0) *dst = *src; }
+__global__ void copy_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n, const unsigned int* skip) {
+  if (skip && *skip) return;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) dst[e] = src[e];
 }
 
 // T blocks out of the first H of iteration j: Tdiag[j] = sym(H[:, j]), Tsub[j] = H[:, j-1]
@@ -280,29 +296,31 @@ inline float knob_f(const char* name, float dflt) { const char* e = getenv(name)
 struct Ctx {
   Plan pl; char* base; cudaStream_t st; int launches; cudaError_t err;
   const bj::Hooks* hooks;
-  int polish_ns = 1; float eig_tol = 1e-6f; int eig_sweeps = 8; int reorth3 = 1; int reorth2 = 0; float chol_tol = 1e-4f; int pass1_local = 1;
+  int polish_ns = 1; float eig_tol = 1e-6f; int eig_sweeps = 8; int reorth3 = 1; int reorth2 = 0; float chol_tol = 1e-4f; int pass1_local = 1; int extra_rounds = 2;
   float* f(size_t off) const { return (float*)(base + off); }
   int64_t* i64(size_t off) const { return (int64_t*)(base + off); }
 };
 
 // C[M x N] (ld ldc) = A(M x K) * B(N x K)^T with automatic split-K for skinny outputs
-inline bool gemm(Ctx& cx, const GatherOperand& A, const GatherOperand& B, int M, int N, int K, float* C, int64_t ldc) {
+inline bool gemm(Ctx& cx, const GatherOperand& A, const GatherOperand& B, int M, int N, int K, float* C, int64_t ldc,
+                 const unsigned int* skip = nullptr) {
   const int bn = N > 128 ? 256 : 128;
   const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
   int max_splits = (int)std::min<size_t>(64, cx.pl.part_elems / ((size_t)M * N));
   if (max_splits < 1) max_splits = 1;
   const int splits = tc_choose_splits(tiles, (K + tc::BK - 1) / tc::BK, max_splits, (int64_t)M * N);
   TcGemmParams g = tc_gemm_defaults();
-  g.A = A; g.B = B; g.M = M; g.N = N; g.K = K;
+  g.A = A; g.B = B; g.M = M; g.N = N; g.K = K; g.skip_flag = skip;
   if (splits > 1) { g.C = cx.f(cx.pl.off_part); g.ldc = N; g.c_split_stride = (int64_t)M * N; }
   else { g.C = C; g.ldc = ldc; }
-  const int slot = cx.hooks ? cx.hooks->begin(2, 2.0 * M * (double)N * K, cx.st) : -1;
+  const bool timed = cx.hooks && !skip;       // conditional (clean-up round) launches are normally no-ops: not profiled
+  const int slot = timed ? cx.hooks->begin(2, 2.0 * M * (double)N * K, cx.st) : -1;
   cx.err = tc_gemm_launch(g, splits, bn, cx.st);
-  if (cx.hooks) cx.hooks->end(slot, cx.st);
+  if (timed) cx.hooks->end(slot, cx.st);
   ++cx.launches;
   if (cx.err != cudaSuccess) return false;
   if (splits > 1) {
-    reduce_parts_kernel<<<148 * 4, 256, 0, cx.st>>>(cx.f(cx.pl.off_part), splits, (int64_t)M * N, M, N, C, ldc);
+    reduce_parts_kernel<<<148 * 4, 256, 0, cx.st>>>(cx.f(cx.pl.off_part), splits, (int64_t)M * N, M, N, C, ldc, skip);
     ++cx.launches;
   }
   return true;
@@ -332,7 +350,7 @@ inline bool svqb(Ctx& cx, const float* src, float* dst) {
 }
 
 // second orthonormalisation pass for rows that are already nearly orthonormal: dst = (src src^T)^-1/2 src (series)
-inline bool ns_polish(Ctx& cx, const float* src, float* dst) {
+inline bool ns_polish(Ctx& cx, const float* src, float* dst, const unsigned int* skip = nullptr) {
   if (!cx.polish_ns) return svqb(cx, src, dst);
   const Plan& pl = cx.pl;
   const int P = pl.P;
@@ -340,27 +358,27 @@ inline bool ns_polish(Ctx& cx, const float* src, float* dst) {
   float *S = cx.f(pl.off_S), *J = cx.f(pl.off_J), *Mm = cx.f(pl.off_M);
   bj::Ctl* ctl = (bj::Ctl*)(cx.base + pl.off_ctl);
   GatherOperand a{src, rowP, iota, NB, 2};
-  if (!gemm(cx, a, a, NB, NB, P, S, NB)) return false;
-  ns_matrix_kernel<<<1, 1024, NS_SMEM, cx.st>>>(S, Mm, ctl); ++cx.launches;
+  if (!gemm(cx, a, a, NB, NB, P, S, NB, skip)) return false;
+  ns_matrix_kernel<<<1, 1024, NS_SMEM, cx.st>>>(S, Mm, ctl, skip); ++cx.launches;
   // robust fallback (rank-deficient residual blocks): both kernels are no-ops while ctl->done is set
-  bj::small_eig_kernel<<<1, 1024, bj::SMALL_EIG_SMEM, cx.st>>>(S, J, cx.eig_tol, 1.f, cx.eig_sweeps, ctl, 0, cx.f(pl.off_lam) + 8); ++cx.launches;
-  svqb_scale_kernel<<<1, 1024, 0, cx.st>>>(J, cx.f(pl.off_lam) + 8, Mm, ctl); ++cx.launches;
+  bj::small_eig_kernel<<<1, 1024, bj::SMALL_EIG_SMEM, cx.st>>>(S, J, cx.eig_tol, 1.f, cx.eig_sweeps, ctl, 0, cx.f(pl.off_lam) + 8, skip); ++cx.launches;
+  svqb_scale_kernel<<<1, 1024, 0, cx.st>>>(J, cx.f(pl.off_lam) + 8, Mm, ctl, skip); ++cx.launches;
   GatherOperand m{Mm, row128, iota, NB, 2};
   GatherOperand w{src, iota, rowP, P, 0};
-  return gemm(cx, m, w, NB, P, NB, dst, P);
+  return gemm(cx, m, w, NB, P, NB, dst, P, skip);
 }
 
 // W (128 x P) -= (W Q^T) Q  against the first nq rows of Qt
-inline bool reorth(Ctx& cx, float* W, const float* Qt, int nq) {
+inline bool reorth(Ctx& cx, float* W, const float* Qt, int nq, const unsigned int* skip = nullptr) {
   const Plan& pl = cx.pl;
   const int P = pl.P;
   int64_t *rowP = cx.i64(pl.off_rowP), *iota = cx.i64(pl.off_iota);
   float *H = cx.f(pl.off_H), *W2 = cx.f(pl.off_Wt2);
   GatherOperand w{W, rowP, iota, NB, 2}, q{Qt, rowP, iota, nq, 2};
-  if (!gemm(cx, w, q, NB, nq, P, H, P)) return false;
+  if (!gemm(cx, w, q, NB, nq, P, H, P, skip)) return false;
   GatherOperand h{H, rowP, iota, NB, 2}, qc{Qt, iota, rowP, P, 0};
-  if (!gemm(cx, h, qc, NB, P, nq, W2, P)) return false;
-  sub_kernel<<<148 * 2, 256, 0, cx.st>>>(W, W2, (int64_t)NB * P); ++cx.launches;
+  if (!gemm(cx, h, qc, NB, P, nq, W2, P, skip)) return false;
+  sub_kernel<<<148 * 2, 256, 0, cx.st>>>(W, W2, (int64_t)NB * P, skip); ++cx.launches;
   return true;
 }
 
@@ -372,6 +390,7 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
   cx.polish_ns = knob_i("MVB_LB_POLISH_NS", 1); cx.eig_tol = knob_f("MVB_LB_EIG_TOL", 1e-6f);
   cx.eig_sweeps = knob_i("MVB_LB_EIG_SWEEPS", 8); cx.reorth3 = knob_i("MVB_LB_REORTH3", 1);
   cx.pass1_local = knob_i("MVB_LB_PASS1_LOCAL", 1);
+  cx.extra_rounds = cx.polish_ns ? std::min(4, std::max(0, knob_i("MVB_LB_EXTRA_ROUNDS", 2))) : 0;
   cx.reorth2 = knob_i("MVB_LB_REORTH2", 0); cx.chol_tol = knob_f("MVB_LB_CHOL_TOL", 1e-4f);
   const Plan& pl = cx.pl;
   const int P = pl.P, nb = pl.nblk;
@@ -424,6 +443,16 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
     if (cx.reorth3) LB_OK(reorth(cx, Qn, Qt, nq));
     LB_OK(ns_polish(cx, Qn, Wt));
     LB_CK(cudaMemcpyAsync(Qn, Wt, (size_t)NB * P * 4, cudaMemcpyDeviceToDevice, st));
+    // Clean-up rounds for hard blocks only.  When the polish had to fall back to the eigen-based SVQB (ctl->sweeps == 0:
+    // the block was ill conditioned, its weak directions were amplified together with their contamination along the
+    // previous blocks), re-orthogonalise and polish again; on ordinary steps every kernel below exits at once.
+    for (int r = 0; r < cx.extra_rounds; ++r) {
+      unsigned int* rs = &ctl->rot[8 + r];       // this round's skip flag: the "finished" state latched at its start
+      latch_kernel<<<1, 32, 0, st>>>(rs, &ctl->sweeps); ++cx.launches;
+      LB_OK(reorth(cx, Qn, Qt, nq, rs));
+      LB_OK(ns_polish(cx, Qn, Wt, rs));          // its ns_matrix_kernel rewrites ctl->sweeps for the next round
+      copy_kernel<<<148 * 2, 256, 0, st>>>(Qn, Wt, (int64_t)NB * P, rs); ++cx.launches;
+    }
   }
   LB_CK(cudaGetLastError());
 #undef LB_CK

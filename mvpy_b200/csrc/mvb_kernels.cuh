@@ -465,10 +465,11 @@ __global__ void select_alpha_kernel(const double* __restrict__ partial, int slab
   __syncthreads();
   if (per_target) {
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
+      // first minimum; a non-finite loss (numerically singular design at a vanishing alpha) never wins over a finite one
       int b = 0; T bv = (T)loss64[f];
       for (int a = 1; a < A; ++a) {
         const T v = (T)loss64[a * F + f];
-        if (v < bv) { bv = v; b = a; }
+        if (v < bv || (!(bv == bv) && v == v)) { bv = v; b = a; }
       }
       best[f] = b;
       alpha_out[f] = alphas[b];
@@ -480,7 +481,7 @@ __global__ void select_alpha_kernel(const double* __restrict__ partial, int slab
       double s = 0;
       for (int f = 0; f < F; ++f) s += (double)(T)loss64[a * F + f];
       const T v = (T)(s / F);
-      if (a == 0 || v < bv) { bv = v; b = a; }
+      if (a == 0 || v < bv || (!(bv == bv) && v == v)) { bv = v; b = a; }
     }
     best[0] = b;
     alpha_out[0] = alphas[b];

@@ -407,3 +407,33 @@ def test_cfg2_size_properties():
     num = ((yt - yh.movedim(0, -1)).double() ** 2).sum(-1)
     den = ((yt - yb).double() ** 2).sum(-1)
     assert torch.isfinite(r2).all() and (r2.double() - (1 - num / den)).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize('kind', ['ar1_0.99', 'duplicate_feature'])
+def test_ill_conditioned_designs(kind):
+    """Strongly autocorrelated stimulus (cond(G) ~ 1e5) and an exactly duplicated predictor (singular Gram): the chosen
+    alpha must match the fp64 oracle, predictions must agree, nothing may be NaN.  Exercises the on-device fallbacks of the
+    band route (eigen-based orthonormalisation + clean-up rounds, modified block Cholesky)."""
+    mv, orc = _mv(), _orc()
+    g = torch.Generator().manual_seed(11)
+    N, C, T, F = 20, 4, 150, 3
+    e = torch.randn(N, C, T, generator=g)
+    phi = 0.99 if kind == 'ar1_0.99' else 0.9
+    X = torch.zeros_like(e)
+    X[..., 0] = e[..., 0]
+    for i in range(1, T):
+        X[..., i] = phi * X[..., i - 1] + (1 - phi * phi) ** 0.5 * e[..., i]
+    if kind == 'duplicate_feature':
+        X[:, 3] = X[:, 2]
+    B = torch.randn(F, C, generator=g) * 0.5
+    y = torch.einsum('fc,nct->nft', B, X) + torch.randn(N, F, T, generator=g)
+    alphas = torch.logspace(-5, 5, 20)
+    td = mv.estimators.TimeDelayed(-0.6, 0.0, 100, alphas=alphas)          # 61 lags -> p = 244 (band route)
+    td.fit(X.cuda(), y.cuda())
+    assert torch.isfinite(td.coef_).all() and torch.isfinite(td.intercept_).all()
+    win = orc.lag_window(-0.6, 0.0, 100)
+    ref = orc.trf_fit(X.double(), y.double(), win, alphas.double(), solver=orc.ridge_loo_fit_primal)
+    assert float(td.estimator.alpha_) == float(ref['alpha'])
+    yh = td.predict(X.cuda()).cpu().double()
+    yh_ref = orc.trf_predict(X.double(), win, ref['flat_coef'], ref['intercept'])
+    assert ((yh - yh_ref).norm() / yh_ref.norm()).item() < 2e-4
