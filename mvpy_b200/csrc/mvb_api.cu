@@ -164,6 +164,9 @@ int run_contract(const mvb_operand& A, const mvb_operand& B, int M, int N, int K
     p.B = {(const float*)B.base, B.roff, B.koff, B.rows, B.contig};
     p.M = M; p.N = N; p.K = K; p.C = (float*)out; p.ldc = ld; p.c_split_stride = stride; p.symmetric = symmetric; p.dbg = 0;
     if (pl.splits == 1) { p.c_block_cols = c_block_cols; p.c_block_stride = c_block_stride; }   // partials stay row-major
+    // a B operand that is larger than L2 (dense basis / coefficient matrices against the small implicit design) is
+    // streamed once per wave of M tiles instead of once per few M tiles
+    p.raster_m_fast = (!symmetric && (int64_t)N * K * 4 > ((int64_t)64 << 20) && M >= 148 * 128 && N <= 65535 * 128) ? 1 : 0;
     const int slot = prof_begin(2.0 * M * (double)N * K * (symmetric ? 0.5 : 1.0), st);
     MVB_CUDA(mvb::tc_gemm_launch(p, pl.splits, N > 128 ? 256 : 128, st));
     prof_end(slot, st);

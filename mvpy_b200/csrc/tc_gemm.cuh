@@ -50,6 +50,8 @@ struct TcGemmParams {
   int64_t c_batch_stride;             // per-batch offset of C (elements), used when c_roff == nullptr
   const int64_t* c_roff;              // optional [batch][M] element offsets of the output rows
   const unsigned int* skip_flag;      // optional: the whole launch is a no-op when *skip_flag != 0
+  int raster_m_fast;                  // 1: consecutive CTAs walk the M tiles of one N tile (B tile stays hot in L2 while a
+                                      //    large dense B streams once); 0: consecutive CTAs walk the N tiles of one M tile
   // ---- output options ----
   int c_block_cols;                   // > 0: C is stored in column blocks, [N / c_block_cols][M][c_block_cols]
   int64_t c_block_stride;             //      elements between consecutive column blocks (>= M * c_block_cols)
@@ -295,8 +297,8 @@ template <int BN, int A_MODE, int B_MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams p) {
   using C_ = Cfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int m0 = blockIdx.y * BM;
-  const int n0 = blockIdx.x * BN;
+  const int m0 = (p.raster_m_fast ? blockIdx.x : blockIdx.y) * BM;
+  const int n0 = (p.raster_m_fast ? blockIdx.y : blockIdx.x) * BN;
   if (p.symmetric && n0 > m0 + BM - 1) return;  // strictly above the diagonal: mirrored by the lower tile
   if (p.skip_flag && *p.skip_flag) return;
   const int splits = gridDim.z / p.batch;
@@ -470,7 +472,8 @@ inline cudaError_t launch_variant(const TcGemmParams& p, int k_splits, cudaStrea
   cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, AM, BMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg<BN>::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, k_splits * (p.batch > 0 ? p.batch : 1));
+  const unsigned nt = (p.N + BN - 1) / BN, mt = (p.M + BM - 1) / BM;
+  dim3 grid(p.raster_m_fast ? mt : nt, p.raster_m_fast ? nt : mt, k_splits * (p.batch > 0 ? p.batch : 1));
   tc_gemm_kernel<BN, AM, BMODE><<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, st>>>(p);
   return cudaGetLastError();
 }
