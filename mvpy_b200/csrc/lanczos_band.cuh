@@ -167,17 +167,53 @@ __global__ void __launch_bounds__(1024) chol_orth_kernel(const float* __restrict
   }
   __syncthreads();
   const float floor_ = fmaxf(s_max * 1e-10f, 1e-36f);
-  for (int k = 0; k < NB; ++k) {
-    const float piv = Cm[k * CLD + k];
-    const float d = sqrtf(fmaxf(piv, floor_));
+  // left-looking Cholesky in 16-column panels: 3 block barriers per panel instead of 3 per column
+  constexpr int PB = 16;
+  for (int pb = 0; pb < NB; pb += PB) {
+    // (1) panel -= L[:, 0:pb] L[pb:pb+16, 0:pb]^T   (lower part only)
+    for (int e = threadIdx.x; e < (NB - pb) * PB; e += blockDim.x) {
+      const int i = pb + e / PB, c = pb + e % PB;
+      if (c <= i) {
+        float acc = 0.f;
+        for (int k = 0; k < pb; ++k) acc += Cm[i * CLD + k] * Cm[c * CLD + k];
+        Cm[i * CLD + c] -= acc;
+      }
+    }
     __syncthreads();
-    if (threadIdx.x == 0) { Cm[k * CLD + k] = d; s_min = fminf(s_min, piv); }
-    for (int i = k + 1 + threadIdx.x; i < NB; i += blockDim.x) Cm[i * CLD + k] /= d;
+    // (2) factor the 16 x 16 diagonal block: one warp, lane r owns row pb + r
+    if (threadIdx.x < 32) {
+      const int r = threadIdx.x;
+      float pmin = s_min;
+      for (int k = 0; k < PB; ++k) {
+        const float piv = Cm[(pb + k) * CLD + pb + k];
+        const float d = sqrtf(fmaxf(piv, floor_));
+        pmin = fminf(pmin, piv);
+        __syncwarp();
+        if (r == k) Cm[(pb + k) * CLD + pb + k] = d;
+        if (r > k && r < PB) Cm[(pb + r) * CLD + pb + k] /= d;
+        __syncwarp();
+        if (r > k && r < PB) {
+          const float lrk = Cm[(pb + r) * CLD + pb + k];
+          for (int c = k + 1; c <= r; ++c) Cm[(pb + r) * CLD + pb + c] -= lrk * Cm[(pb + c) * CLD + pb + k];
+        }
+        __syncwarp();
+      }
+      if (r == 0) s_min = pmin;
+    }
     __syncthreads();
-    const int m = NB - 1 - k;                       // trailing size
-    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
-      const int i = k + 1 + e / m, jj = k + 1 + e % m;
-      if (jj <= i) Cm[i * CLD + jj] -= Cm[i * CLD + k] * Cm[jj * CLD + k];
+    // (3) rows below the panel: L[i, panel] = A[i, panel] L_pp^-T, one thread per row
+    for (int i = pb + PB + threadIdx.x; i < NB; i += blockDim.x) {
+      float x[PB];
+#pragma unroll
+      for (int c = 0; c < PB; ++c) {
+        float v = Cm[i * CLD + pb + c];
+#pragma unroll
+        for (int k = 0; k < PB; ++k)
+          if (k < c) v -= x[k] * Cm[(pb + c) * CLD + pb + k];
+        x[c] = v / Cm[(pb + c) * CLD + pb + c];
+      }
+#pragma unroll
+      for (int c = 0; c < PB; ++c) Cm[i * CLD + pb + c] = x[c];
     }
     __syncthreads();
   }

@@ -953,8 +953,14 @@ int mvb_score(const void* y, const void* yhat, const void* y_b, int64_t R, int64
               void* pearson_out, void* stream) {
   if (!y || !yhat || R < 1 || K < 1 || (!r2_out && !pearson_out)) return fail(MVB_E_ARG, "score: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == MVB_F32) mvb::score_kernel<float><<<cdiv(K, 128), 128, 0, st>>>((const float*)y, (const float*)yhat, (const float*)y_b, R, K, (float*)r2_out, (float*)pearson_out);
-  else if (dtype == MVB_F64) mvb::score_kernel<double><<<cdiv(K, 128), 128, 0, st>>>((const double*)y, (const double*)yhat, (const double*)y_b, R, K, (double*)r2_out, (double*)pearson_out);
+  const int grid = cdiv(K, 128);
+  if (dtype == MVB_F32) {
+    if (R <= 32) mvb::score_kernel<float, 32><<<grid, 128, 0, st>>>((const float*)y, (const float*)yhat, (const float*)y_b, R, K, (float*)r2_out, (float*)pearson_out);
+    else mvb::score_kernel<float, 0><<<grid, 128, 0, st>>>((const float*)y, (const float*)yhat, (const float*)y_b, R, K, (float*)r2_out, (float*)pearson_out);
+  } else if (dtype == MVB_F64) {
+    if (R <= 32) mvb::score_kernel<double, 32><<<grid, 128, 0, st>>>((const double*)y, (const double*)yhat, (const double*)y_b, R, K, (double*)r2_out, (double*)pearson_out);
+    else mvb::score_kernel<double, 0><<<grid, 128, 0, st>>>((const double*)y, (const double*)yhat, (const double*)y_b, R, K, (double*)r2_out, (double*)pearson_out);
+  }
   else return fail(MVB_E_UNSUPPORTED, "score: dtype %d", dtype);
   MVB_LAUNCHED();
   return MVB_OK;

@@ -527,21 +527,47 @@ __global__ void predict_layout_kernel(const T* __restrict__ P, int64_t n_trials,
 //   r2      = 1 - sum (y - yhat)^2 / sum (y - y_b)^2, 0 where the denominator <= 0   (math/r2.py:92-100)
 //   pearson = sum dx dy / sqrt(sum dx^2 sum dy^2) with dx, dy centred                  (math/pearsonr.py:55-56)
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+// One thread per kept cell k; the reduced samples r are the slow axis, so every load is coalesced across the warp.
+// RC > 0: R <= RC samples are held in registers (all loads issued up front, each value read from memory once);
+// RC == 0: generic two-pass loop for long reduce dims.  fp64 accumulators, results rounded to T like the reference's
+// fp32 tensor ops.
+template <typename T, int RC>
 __global__ void score_kernel(const T* __restrict__ y, const T* __restrict__ yh, const T* __restrict__ yb, int64_t R,
                              int64_t K, T* r2, T* pr) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
-  double sy = 0, sh = 0;
-  for (int64_t r = 0; r < R; ++r) { sy += (double)y[r * K + k]; sh += (double)yh[r * K + k]; }
-  const T my = (T)(sy / R), mh = (T)(sh / R);
-  const T base = yb ? yb[k] : my;
-  double num = 0, den = 0, sxy = 0, sxx = 0, syy = 0;
-  for (int64_t r = 0; r < R; ++r) {
-    const T a = y[r * K + k], b = yh[r * K + k];
-    const T e = a - b, g = a - base, dx = a - my, dy = b - mh;
-    num += (double)(e * e); den += (double)(g * g);
-    sxy += (double)(dx * dy); sxx += (double)(dx * dx); syy += (double)(dy * dy);
+  double sy = 0, sh = 0, num = 0, den = 0, sxy = 0, sxx = 0, syy = 0;
+  if (RC > 0) {
+    T a[RC > 0 ? RC : 1], b[RC > 0 ? RC : 1];
+#pragma unroll
+    for (int r = 0; r < RC; ++r) {
+      a[r] = (r < R) ? __ldg(y + r * K + k) : (T)0;
+      b[r] = (r < R) ? __ldg(yh + r * K + k) : (T)0;
+    }
+    double sy2 = 0, sh2 = 0;
+#pragma unroll
+    for (int r = 0; r < RC; r += 2) { sy += (double)a[r]; sh += (double)b[r]; if (r + 1 < RC) { sy2 += (double)a[r + 1]; sh2 += (double)b[r + 1]; } }
+    sy += sy2; sh += sh2;
+    const T my = (T)(sy / R), mh = (T)(sh / R);
+    const T base = yb ? yb[k] : my;
+#pragma unroll
+    for (int r = 0; r < RC; ++r) {
+      if (r < R) {
+        const T e = a[r] - b[r], g = a[r] - base, dx = a[r] - my, dy = b[r] - mh;
+        num += (double)(e * e); den += (double)(g * g);
+        sxy += (double)(dx * dy); sxx += (double)(dx * dx); syy += (double)(dy * dy);
+      }
+    }
+  } else {
+    for (int64_t r = 0; r < R; ++r) { sy += (double)y[r * K + k]; sh += (double)yh[r * K + k]; }
+    const T my = (T)(sy / R), mh = (T)(sh / R);
+    const T base = yb ? yb[k] : my;
+    for (int64_t r = 0; r < R; ++r) {
+      const T av = y[r * K + k], bv = yh[r * K + k];
+      const T e = av - bv, g = av - base, dx = av - my, dy = bv - mh;
+      num += (double)(e * e); den += (double)(g * g);
+      sxy += (double)(dx * dy); sxx += (double)(dx * dx); syy += (double)(dy * dy);
+    }
   }
   if (r2) r2[k] = ((T)den > (T)0) ? (T)1 - (T)num / (T)den : (T)0;
   if (pr) pr[k] = (T)sxy / (T)sqrt((double)((T)sxx * (T)syy));
