@@ -321,6 +321,19 @@ def band_reduce(G: torch.Tensor, counters: bool = False):
     return Qt, Td, Ts
 
 
+def matmul_nt(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """A (M, K) @ B (N, K)^T on the library's contraction kernel (both operands row-major, k contiguous)."""
+    A, B = A.contiguous(), B.contiguous()
+    M, K = A.shape
+    N = B.shape[0]
+    dev = A.device
+    a_r = torch.arange(M, device=dev, dtype=torch.int64) * K
+    b_r = torch.arange(N, device=dev, dtype=torch.int64) * K
+    k_o = torch.arange(K, device=dev, dtype=torch.int64)
+    vec = 2 if (A.dtype == torch.float32 and K % 4 == 0 and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0) else 1
+    return contract(A, a_r, k_o, vec, B, b_r, k_o, vec, M, N, K)
+
+
 def contract(a_base, a_roff, a_koff, a_contig, b_base, b_roff, b_koff, b_contig, M, N, K, symmetric=False) -> torch.Tensor:
     """Generic separable-gather contraction C[M,N] = sum_k A(m,k) B(n,k) (tests, patterns)."""
     C = torch.empty((M, N), dtype=a_base.dtype, device=a_base.device)

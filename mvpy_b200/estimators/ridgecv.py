@@ -26,13 +26,13 @@ def _as_alphas(alphas) -> torch.Tensor:
 
 
 def solve_design(design: _lib.Design, y: torch.Tensor, alphas: torch.Tensor, fit_intercept: bool, alpha_per_target: bool,
-                 stats=None, want_loss: bool = False):
+                 stats=None, want_loss: bool = False, keep_gram: bool = True):
     """Shared fit core: y is (N, F, T) on the device of ``design``.  Returns dict with flat coef (F, p),
     intercept (F,), alpha (0-d or (F,)), best, loss, and the centred Gram (for patterns)."""
     if stats is None:
         stats = _lib.trf_stats(design, y, fit_intercept)
     G, XtY, mu, ybar = stats
-    Gkeep = G.clone()
+    Gkeep = G.clone() if keep_gram else None          # the solve may overwrite G; patterns need cov(X) = G / (n - 1)
     coef, icpt, alpha, best, loss = _lib.ridge_solve(design, y, G, XtY, mu, ybar, alphas, fit_intercept, alpha_per_target,
                                                      want_loss=want_loss)
     return dict(coef=coef, intercept=icpt, alpha=alpha if alpha_per_target else alpha.reshape(()), best=best, loss=loss,

@@ -54,9 +54,9 @@ class _RidgeDecoder_torch(sklearn.base.BaseEstimator):
         if y.shape[1] > 1:
             yd = _lib.to_device(y).to(Sx.dtype)
             Py = torch.linalg.pinv(torch.cov((yd - yd.mean(0, keepdim=True)).T))   # (f x f): tiny
-            self.pattern_ = Sx.mm(coef.T).mm(Py).to(out_dev)
+            self.pattern_ = _lib.matmul_nt(_lib.matmul_nt(Sx, coef), Py.T.contiguous()).to(out_dev)
         else:
-            self.pattern_ = (Sx.mm(coef.T) * (1.0 / float(n - 1))).to(out_dev)
+            self.pattern_ = (_lib.matmul_nt(Sx, coef) * (1.0 / float(n - 1))).to(out_dev)
         return self
 
     def predict(self, X: torch.Tensor) -> torch.Tensor:

@@ -80,9 +80,9 @@ class _TimeDelayed_torch(sklearn.base.BaseEstimator):
             yd[design.trial_idx.long()].permute(0, 2, 1).reshape(-1, yd.shape[1])
         if yt.shape[1] > 1:
             Py = torch.linalg.inv(torch.cov((yt - yt.mean(0, keepdim=True)).T))
-            pat = Sx.mm(coef.T).mm(Py)
+            pat = _lib.matmul_nt(_lib.matmul_nt(Sx, coef), Py.T.contiguous())
         else:
-            pat = Sx.mm(coef.T) * (1.0 / float(yt.shape[0] - 1))
+            pat = _lib.matmul_nt(Sx, coef) * (1.0 / float(yt.shape[0] - 1))
         return pat.reshape((self.f_, self.c_, self.w_)).flip(-1)
 
     def fit(self, X: torch.Tensor, y: torch.Tensor):
@@ -97,7 +97,8 @@ class _TimeDelayed_torch(sklearn.base.BaseEstimator):
         est = self.estimator
         est.alphas = est.alphas.to(X.dtype).to(X.device)              # ridgecv.py:125
         design = self._design(Xd)
-        fit = solve_design(design, yd, _lib.to_device(est.alphas).contiguous(), est.fit_intercept, est.alpha_per_target)
+        fit = solve_design(design, yd, _lib.to_device(est.alphas).contiguous(), est.fit_intercept, est.alpha_per_target,
+                           keep_gram=self.patterns)
         self._finish_fit(fit, design, yd, out_dev)
         return self
 
