@@ -334,6 +334,14 @@ def matmul_nt(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     return contract(A, a_r, k_o, vec, B, b_r, k_o, vec, M, N, K)
 
 
+def covariance(Y: torch.Tensor) -> torch.Tensor:
+    """Unbiased covariance of the columns of Y (n, f) -> (f, f), like ``torch.cov(Y.T)``: centred columns, then one
+    contraction over the samples on the library kernel."""
+    n = Y.shape[0]
+    Yt = transpose((Y - Y.mean(0, keepdim=True)).contiguous())          # (f, n), samples contiguous
+    return matmul_nt(Yt, Yt) / float(n - 1)
+
+
 def contract(a_base, a_roff, a_koff, a_contig, b_base, b_roff, b_koff, b_contig, M, N, K, symmetric=False) -> torch.Tensor:
     """Generic separable-gather contraction C[M,N] = sum_k A(m,k) B(n,k) (tests, patterns)."""
     C = torch.empty((M, N), dtype=a_base.dtype, device=a_base.device)

@@ -79,7 +79,7 @@ class _TimeDelayed_torch(sklearn.base.BaseEstimator):
         yt = yd.permute(0, 2, 1).reshape(-1, yd.shape[1]) if design.trial_idx is None else \
             yd[design.trial_idx.long()].permute(0, 2, 1).reshape(-1, yd.shape[1])
         if yt.shape[1] > 1:
-            Py = torch.linalg.inv(torch.cov((yt - yt.mean(0, keepdim=True)).T))
+            Py = torch.linalg.inv(_lib.covariance(yt.contiguous()))   # inverse of the (f x f) target covariance
             pat = _lib.matmul_nt(_lib.matmul_nt(Sx, coef), Py.T.contiguous())
         else:
             pat = _lib.matmul_nt(Sx, coef) * (1.0 / float(yt.shape[0] - 1))
