@@ -1,5 +1,7 @@
 from .kfold import KFold
+from .repeatedkfold import RepeatedKFold
+from .lgo import LeaveGroupsOut
 from .validator import Validator
 from .cross_val_score import cross_val_score
 
-__all__ = ['KFold', 'Validator', 'cross_val_score']
+__all__ = ['KFold', 'RepeatedKFold', 'LeaveGroupsOut', 'Validator', 'cross_val_score']

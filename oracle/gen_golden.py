@@ -11,6 +11,7 @@ Fixtures (all produced through the reference's public classes/functions):
   delay.npz        _delay_matrices known answer (arange(24).reshape(2,2,6), lags -3..2) + a random case.
   scaler.npz       _Scaler_torch statistics/transforms for several dims.
   kfold.npz        KFold index listings (plain + shuffled with seeds).
+  splitters.npz    RepeatedKFold and LeaveGroupsOut (single- and multi-label groups) index listings.
   metrics.npz      math.r2 / math.pearsonr incl. zero-variance rows and the y_b baseline.
   trf_small.npz    make_meeg_continuous(fs=50, n_trials=40, n_channels=8, n_features=4) seed 0:
                    cross_val_score / hierarchical_score / shapley_score through Scaler+TimeDelayed.
@@ -146,6 +147,28 @@ def gen_kfold():
 
 
 # ---------------------------------------------------------------------------------------- metrics
+def gen_splitters():
+    out = {}
+    X = torch.zeros(11, 2)
+    rkf = ref.crossvalidation.RepeatedKFold(n_splits=3, n_repeats=2, random_state=7)
+    for i, (tr, te) in enumerate(rkf.split(X)):
+        out[f'rkf_tr{i}'], out[f'rkf_te{i}'] = tr, te
+    obj = ref.crossvalidation.RepeatedKFold(n_splits=2, n_repeats=2, random_state=1).to_torch()
+    for rep in range(2):                          # a kept torch object continues its random stream across calls
+        for i, (tr, te) in enumerate(obj.split(torch.zeros(6))):
+            out[f'rkfobj{rep}_tr{i}'], out[f'rkfobj{rep}_te{i}'] = tr, te
+    g1 = torch.arange(4).repeat(3)
+    lgo = ref.crossvalidation.LeaveGroupsOut(n_splits=2, n_repeats=2, random_state=3)
+    for i, (tr, te) in enumerate(lgo.split(torch.zeros(12, 2), groups=g1)):
+        out[f'lgo1_tr{i}'], out[f'lgo1_te{i}'] = tr, te
+    g2 = torch.stack([torch.arange(12) % 4, (torch.arange(12) // 3) % 4], dim=1)
+    lgo2 = ref.crossvalidation.LeaveGroupsOut(n_splits=2, n_repeats=1, random_state=5)
+    for i, (tr, te) in enumerate(lgo2.split(torch.zeros(12, 2), groups=g2)):
+        out[f'lgo2_tr{i}'], out[f'lgo2_te{i}'] = tr, te
+    out['g1'], out['g2'] = g1, g2
+    save('splitters.npz', **out)
+
+
 def gen_metrics():
     g = torch.Generator().manual_seed(5)
     y = torch.randn(6, 9, 24, generator=g)
@@ -258,6 +281,6 @@ def gen_cfg1():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['ridgecv', 'delay', 'scaler', 'kfold', 'metrics', 'trf_small', 'decoder', 'encoder', 'cfg1']
+    which = sys.argv[1:] or ['ridgecv', 'delay', 'scaler', 'kfold', 'splitters', 'metrics', 'trf_small', 'decoder', 'encoder', 'cfg1']
     for w in which:
         globals()['gen_' + w]()

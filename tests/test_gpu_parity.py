@@ -437,3 +437,28 @@ def test_ill_conditioned_designs(kind):
     yh = td.predict(X.cuda()).cpu().double()
     yh_ref = orc.trf_predict(X.double(), win, ref['flat_coef'], ref['intercept'])
     assert ((yh - yh_ref).norm() / yh_ref.norm()).item() < 2e-4
+
+
+def test_validator_with_repeated_kfold_and_leave_groups_out(golden):
+    """§8(f) splitters through the CUDA path: every fold's score equals a hand-rolled fit / score on the same indices
+    (indices themselves are checked bit-exactly against the reference in tests/test_host_logic.py)."""
+    mv, orc = _mv(), _orc()
+    g = golden('trf_small.npz')
+    X, y, al = T(g['X']).cuda(), T(g['y']).cuda(), T(g['alphas'])
+    win = orc.lag_window(-0.4, 0.0, 50)
+    pipe = make_pipeline(mv.preprocessing.Scaler().to_torch(), mv.estimators.TimeDelayed(-0.4, 0.0, 50, alphas=al))
+    groups = (torch.arange(X.shape[0]) % 8).cuda()
+    for cv, kw in [(mv.crossvalidation.RepeatedKFold(n_splits=4, n_repeats=2, random_state=3), {}),
+                   (mv.crossvalidation.LeaveGroupsOut(n_splits=4, n_repeats=1, random_state=2), dict(groups=groups))]:
+        val, sc = mv.crossvalidation.cross_val_score(pipe, X, y, cv=cv, **kw)
+        folds = list(cv.split(X, y, **kw)) if kw else list(cv.split(X, y))
+        assert sc.shape[0] == len(folds) == val.cv_n_
+        k = len(folds) - 1                                  # check the last fold against the fp64 oracle on the same indices
+        tr, te = folds[k][0].cpu(), folds[k][1].cpu()
+        Xc, yc = X.cpu().double(), y.cpu().double()
+        st = orc.scaler_fit(Xc[tr], (0,))
+        fit = orc.trf_fit(orc.scaler_transform(Xc[tr], st), yc[tr], win, al.double(), solver=orc.ridge_loo_fit_primal)
+        yh = orc.trf_predict(orc.scaler_transform(Xc[te], st), win, fit['flat_coef'], fit['intercept'])
+        r2 = orc.r2_last(orc.move_reduce_last(yc[te], (0,)), orc.move_reduce_last(yh, (0,)),
+                         orc.move_reduce_last(yc[tr].mean(0, keepdim=True), (0,)))
+        np.testing.assert_allclose(sc[k].cpu().numpy(), r2.numpy(), atol=1e-5)

@@ -167,3 +167,37 @@ def test_dataset_matches_reference_checksum(golden):
     assert X.shape == (120, 3, 400) and y.shape == (120, 64, 400)
     assert abs(float(X.double().sum()) - float(g['x_checksum'])) < 1e-9
     assert abs(float(y.double().sum()) - float(g['y_checksum'])) < 1e-9
+
+
+def test_repeated_kfold_and_leave_groups_out_bit_exact(golden):
+    """Index listings of the reference's RepeatedKFold / LeaveGroupsOut (tests/golden/splitters.npz)."""
+    g = golden('splitters.npz')
+    rkf = mv.crossvalidation.RepeatedKFold(n_splits=3, n_repeats=2, random_state=7)
+    folds = list(rkf.split(torch.zeros(11, 2)))
+    assert len(folds) == 6
+    for i, (tr, te) in enumerate(folds):
+        assert tr.dtype == torch.long and np.array_equal(tr.numpy(), g[f'rkf_tr{i}']) and np.array_equal(te.numpy(), g[f'rkf_te{i}'])
+    obj = mv.crossvalidation.RepeatedKFold(n_splits=2, n_repeats=2, random_state=1).to_torch()
+    for rep in range(2):                       # a kept splitter continues its random stream across split() calls
+        for i, (tr, te) in enumerate(obj.split(torch.zeros(6))):
+            assert np.array_equal(tr.numpy(), g[f'rkfobj{rep}_tr{i}']) and np.array_equal(te.numpy(), g[f'rkfobj{rep}_te{i}'])
+    lgo = mv.crossvalidation.LeaveGroupsOut(n_splits=2, n_repeats=2, random_state=3)
+    for i, (tr, te) in enumerate(lgo.split(torch.zeros(12, 2), groups=T(g['g1']))):
+        assert np.array_equal(tr.numpy(), g[f'lgo1_tr{i}']) and np.array_equal(te.numpy(), g[f'lgo1_te{i}'])
+    lgo2 = mv.crossvalidation.LeaveGroupsOut(n_splits=2, n_repeats=1, random_state=5)
+    seen = 0
+    for i, (tr, te) in enumerate(lgo2.split(torch.zeros(12, 2), groups=T(g['g2']))):
+        assert np.array_equal(tr.numpy(), g[f'lgo2_tr{i}']) and np.array_equal(te.numpy(), g[f'lgo2_te{i}'])
+        assert len(tr) + len(te) < 12           # multi-label samples with labels on both sides are in neither
+        seen += 1
+    assert seen == 2
+    with pytest.raises(ValueError):
+        list(lgo.split(torch.zeros(12, 2)))
+    # Validator accepts them: n_splits * n_repeats folds
+    class M:
+        metric_ = None
+        def clone(self): return M()
+        def fit(self, X, y): return self
+        def score(self, X, y): return X.sum().reshape(1)
+    v = mv.crossvalidation.Validator(M(), cv=mv.crossvalidation.RepeatedKFold(n_splits=3, n_repeats=2, random_state=0))
+    assert v.cv_n_ == 6
