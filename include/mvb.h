@@ -145,6 +145,11 @@ int mvb_trf_predict(const mvb_design* d, const void* coef, const void* intercept
 int mvb_score(const void* y, const void* yhat, const void* y_b, int64_t R, int64_t K, int dtype,
               void* r2_out, void* pearson_out, void* stream);
 
+/* ---- ranks (widening, SURVEY 8f: spearmanr) --------------------------------------------------------------
+ * replaces math.rank (math/rank.py:62-112) for the metric layout: x viewed as [R][K], average ranks (ties get the
+ * mean of their positions, 1-based) along R for every one of the K cells.  spearmanr = mvb_score's pearson on ranks. */
+int mvb_rank(const void* x, int64_t R, int64_t K, int dtype, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

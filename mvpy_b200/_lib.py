@@ -66,6 +66,7 @@ _SIGNATURES = {
     'mvb_band_reduce_counters': (c_int, [c_void_p, c_int, c_void_p]),
     'mvb_trf_predict_workspace_bytes': (c_size_t, [POINTER(mvb_design), c_int]),
     'mvb_trf_predict': (c_int, [POINTER(mvb_design), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'mvb_rank': (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     'mvb_score': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
@@ -291,6 +292,14 @@ def score(y2: torch.Tensor, yh2: torch.Tensor, yb: Optional[torch.Tensor], want_
     pr = torch.empty(K, dtype=y2.dtype, device=y2.device) if want_pearson else None
     check(load().mvb_score(_ptr(y2), _ptr(yh2), _ptr(yb), R, K, dtype_code(y2), _ptr(r2), _ptr(pr), _stream(y2)), 'mvb_score')
     return r2, pr
+
+
+def rank_rows(x2: torch.Tensor) -> torch.Tensor:
+    """x2: (R, K) contiguous -> average ranks along R for every column, same shape / dtype."""
+    R, K = x2.shape
+    out = torch.empty_like(x2)
+    check(load().mvb_rank(_ptr(x2), R, K, dtype_code(x2), _ptr(out), _stream(x2)), 'mvb_rank')
+    return out
 
 
 def eigh(A: torch.Tensor):

@@ -949,6 +949,21 @@ int mvb_trf_predict(const mvb_design* d, const void* coef, const void* intercept
   return predict_impl<double>(d, (const double*)coef, (const double*)intercept, n_targets, (double*)yhat, ws, ws_bytes, st);
 }
 
+int mvb_rank(const void* x, int64_t R, int64_t K, int dtype, void* out, void* stream) {
+  if (!x || !out || R < 1 || K < 1) return fail(MVB_E_ARG, "rank: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = cdiv(K, 128);
+  if (dtype == MVB_F32) {
+    if (R <= 64) mvb::rank_kernel<float, 64><<<grid, 128, 0, st>>>((const float*)x, R, K, (float*)out);
+    else mvb::rank_kernel<float, 0><<<grid, 128, 0, st>>>((const float*)x, R, K, (float*)out);
+  } else if (dtype == MVB_F64) {
+    if (R <= 64) mvb::rank_kernel<double, 64><<<grid, 128, 0, st>>>((const double*)x, R, K, (double*)out);
+    else mvb::rank_kernel<double, 0><<<grid, 128, 0, st>>>((const double*)x, R, K, (double*)out);
+  } else return fail(MVB_E_UNSUPPORTED, "rank: dtype %d", dtype);
+  MVB_LAUNCHED();
+  return MVB_OK;
+}
+
 int mvb_score(const void* y, const void* yhat, const void* y_b, int64_t R, int64_t K, int dtype, void* r2_out,
               void* pearson_out, void* stream) {
   if (!y || !yhat || R < 1 || K < 1 || (!r2_out && !pearson_out)) return fail(MVB_E_ARG, "score: bad argument");

@@ -527,6 +527,40 @@ __global__ void predict_layout_kernel(const T* __restrict__ P, int64_t n_trials,
 //   r2      = 1 - sum (y - yhat)^2 / sum (y - y_b)^2, 0 where the denominator <= 0   (math/r2.py:92-100)
 //   pearson = sum dx dy / sqrt(sum dx^2 sum dy^2) with dx, dy centred                  (math/pearsonr.py:55-56)
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// average ranks along the reduced axis (math/rank.py:62-112): x viewed as [R][K], out[r][k] = 1 + #{x_j < x_r}
+// + (#{x_j == x_r} - 1) / 2 over column k.  One thread per cell, O(R^2) comparisons from a register cache when
+// R <= 64 (the trials-first reduce of the metrics), strided re-reads otherwise.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int RC>
+__global__ void rank_kernel(const T* __restrict__ x, int64_t R, int64_t K, T* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  if (RC > 0) {
+    T v[RC > 0 ? RC : 1];
+#pragma unroll
+    for (int r = 0; r < RC; ++r) v[r] = (r < R) ? __ldg(x + r * K + k) : (T)0;
+#pragma unroll
+    for (int r = 0; r < RC; ++r) {
+      if (r < R) {
+        int less = 0, equal = 0;
+#pragma unroll
+        for (int j = 0; j < RC; ++j) {
+          if (j < R) { less += v[j] < v[r]; equal += v[j] == v[r]; }
+        }
+        out[r * K + k] = (T)(1.0 + less + 0.5 * (equal - 1));
+      }
+    }
+  } else {
+    for (int64_t r = 0; r < R; ++r) {
+      const T xr = x[r * K + k];
+      int64_t less = 0, equal = 0;
+      for (int64_t j = 0; j < R; ++j) { const T xj = x[j * K + k]; less += xj < xr; equal += xj == xr; }
+      out[r * K + k] = (T)(1.0 + (double)less + 0.5 * (double)(equal - 1));
+    }
+  }
+}
+
 // One thread per kept cell k; the reduced samples r are the slow axis, so every load is coalesced across the warp.
 // RC > 0: R <= RC samples are held in registers (all loads issued up front, each value read from memory once);
 // RC == 0: generic two-pass loop for long reduce dims.  fp64 accumulators, results rounded to T like the reference's

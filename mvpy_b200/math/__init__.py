@@ -1,4 +1,6 @@
 from .r2 import r2
 from .pearsonr import pearsonr
+from .rank import rank
+from .spearmanr import spearmanr, spearmanr_d
 
-__all__ = ['r2', 'pearsonr']
+__all__ = ['r2', 'pearsonr', 'rank', 'spearmanr', 'spearmanr_d']

@@ -13,6 +13,7 @@ Fixtures (all produced through the reference's public classes/functions):
   kfold.npz        KFold index listings (plain + shuffled with seeds).
   splitters.npz    RepeatedKFold and LeaveGroupsOut (single- and multi-label groups) index listings.
   metrics.npz      math.r2 / math.pearsonr incl. zero-variance rows and the y_b baseline.
+  rank.npz         math.rank (ties, integer input, the docstring example) and math.spearmanr.
   trf_small.npz    make_meeg_continuous(fs=50, n_trials=40, n_channels=8, n_features=4) seed 0:
                    cross_val_score / hierarchical_score / shapley_score through Scaler+TimeDelayed.
   decoder.npz      per-slice RidgeCV(alpha_per_target) + Haufe pattern (RidgeDecoder maths), Sliding.
@@ -169,6 +170,18 @@ def gen_splitters():
     save('splitters.npz', **out)
 
 
+def gen_rank():
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(5, 7, 24, generator=g)
+    x[0, 0, 3] = x[0, 0, 9] = x[0, 0, 17]                         # a three-way tie and a pair
+    x[2, 4, 0] = x[2, 4, 23]
+    xi = torch.randint(0, 6, (4, 30), generator=g)                # integer input with many ties
+    y = 0.6 * x + 0.8 * torch.randn(5, 7, 24, generator=g)
+    save('rank.npz', x=x, xi=xi, y=y, rank_x=ref.math.rank(x), rank_xi=ref.math.rank(xi),
+         doc=ref.math.rank(torch.tensor([2, 0.5, 1, 1])), spearman=ref.math.spearmanr(x, y),
+         spearman_d=ref.math.spearmanr_d(x, y), x64=x.double(), rank_x64=ref.math.rank(x.double()))
+
+
 def gen_metrics():
     g = torch.Generator().manual_seed(5)
     y = torch.randn(6, 9, 24, generator=g)
@@ -281,6 +294,6 @@ def gen_cfg1():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['ridgecv', 'delay', 'scaler', 'kfold', 'splitters', 'metrics', 'trf_small', 'decoder', 'encoder', 'cfg1']
+    which = sys.argv[1:] or ['ridgecv', 'delay', 'scaler', 'kfold', 'splitters', 'metrics', 'rank', 'trf_small', 'decoder', 'encoder', 'cfg1']
     for w in which:
         globals()['gen_' + w]()

@@ -285,6 +285,21 @@ def pearsonr_last(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return (dx * dy).sum(-1) / torch.sqrt(dx.square().sum(-1) * dy.square().sum(-1))
 
 
+def rank_last(x: torch.Tensor) -> torch.Tensor:
+    """Average ranks (1-based, ties share the mean of their positions) along the last dim.
+    reference: math/rank.py:62-112 (sort, first / last position of each run of equal values, mean of the two)."""
+    if not torch.is_floating_point(x):
+        x = x.to(torch.float64)
+    less = (x.unsqueeze(-1) > x.unsqueeze(-2)).sum(-1)           # [..., r, j]: x_j < x_r
+    equal = (x.unsqueeze(-1) == x.unsqueeze(-2)).sum(-1)
+    return (1.0 + less + 0.5 * (equal - 1)).to(x.dtype)
+
+
+def spearmanr_last(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """Pearson correlation of the ranks.                   reference: math/spearmanr.py:35-50."""
+    return pearsonr_last(rank_last(x), rank_last(y))
+
+
 def score_fold(y_test: torch.Tensor, y_hat: torch.Tensor, y_train: torch.Tensor, metric: str = 'r2',
                reduce: Sequence[int] = (0,)) -> torch.Tensor:
     """What ``fit_model_`` + ``metrics.score`` compute for one fold: the R2 baseline is the mean of

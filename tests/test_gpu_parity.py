@@ -462,3 +462,29 @@ def test_validator_with_repeated_kfold_and_leave_groups_out(golden):
         r2 = orc.r2_last(orc.move_reduce_last(yc[te], (0,)), orc.move_reduce_last(yh, (0,)),
                          orc.move_reduce_last(yc[tr].mean(0, keepdim=True), (0,)))
         np.testing.assert_allclose(sc[k].cpu().numpy(), r2.numpy(), atol=1e-5)
+
+
+def test_rank_and_spearman_golden(golden):
+    """§8(f) widening: math.rank / math.spearmanr / metrics.spearmanr on the CUDA path vs the reference's outputs."""
+    mv = _mv()
+    g = golden('rank.npz')
+    for key, ref_key in [('x', 'rank_x'), ('x64', 'rank_x64'), ('xi', 'rank_xi')]:
+        r = mv.math.rank(T(g[key]).cuda())
+        assert r.is_cuda and np.array_equal(r.cpu().numpy(), g[ref_key])          # ranks are exact (halves of integers)
+    assert np.array_equal(mv.math.rank(torch.tensor([2, 0.5, 1, 1])).numpy(), g['doc'])
+    x, y = T(g['x']).cuda(), T(g['y']).cuda()
+    np.testing.assert_allclose(mv.math.spearmanr(x, y).cpu().numpy(), g['spearman'], atol=1e-6)
+    np.testing.assert_allclose(mv.math.spearmanr_d(x, y).cpu().numpy(), g['spearman_d'], atol=1e-6)
+    long = torch.randn(3, 200, generator=torch.Generator().manual_seed(1))            # R > 64: generic kernel path
+    ref = torch.empty_like(long)
+    ref.scatter_(1, long.argsort(1), torch.arange(1, 201, dtype=torch.float32).repeat(3, 1))
+    assert torch.equal(mv.math.rank(long.cuda()).cpu(), ref)
+    # as a metric inside the scoring protocol: reduce over trials (dim 0)
+    class M:
+        def predict(self, X):
+            return X * 2.0 + 1.0
+    sc = mv.metrics.score(M(), (mv.metrics.spearmanr, mv.metrics.pearsonr), y, y + x)
+    assert sc['spearmanr'].shape == (7, 24)
+    from oracle import mvpy_oracle as orc
+    ref_s = orc.spearmanr_last(orc.move_reduce_last((y + x).cpu().double(), (0,)), orc.move_reduce_last((y * 2 + 1).cpu().double(), (0,)))
+    np.testing.assert_allclose(sc['spearmanr'].cpu().numpy(), ref_s.numpy(), atol=1e-5)

@@ -168,3 +168,11 @@ def test_encoder(golden):
     f2 = orc.encoder_fit(X[..., 0], y[..., 0], al)
     assert torch.equal(f2['alpha'], T(g['alpha2']))
     np.testing.assert_allclose(orc.encoder_predict(X[..., 0], f2).numpy(), g['pred2'], atol=1e-4)
+
+
+def test_rank_and_spearman(golden):
+    g = golden('rank.npz')
+    assert np.array_equal(orc.rank_last(T(g['x'])).numpy(), g['rank_x'])
+    assert np.array_equal(orc.rank_last(T(g['xi'])).numpy(), g['rank_xi'])
+    assert np.array_equal(orc.rank_last(torch.tensor([2, 0.5, 1, 1])).numpy(), g['doc'])
+    np.testing.assert_allclose(orc.spearmanr_last(T(g['x']), T(g['y'])).numpy(), g['spearman'], atol=1e-6)
