@@ -41,6 +41,10 @@ WORKLOADS = {
                                                       'cross_val_score 5-fold x 20 alphas (BASELINE configs[1])'),
     'cfg1': dict(n_features=3, n_channels=64, label='make_meeg_continuous(fs=200) + Scaler + TimeDelayed(-1,0), '
                                                     '5-fold x 20 alphas (BASELINE configs[0])'),
+    # one Shapley permutation of BASELINE configs[3] per rank and step: 8 groups of 8 features -> 8 nested predictor sets
+    # (8 ... 64 features, p = 1608 ... 12864) x 5 folds x 20 alphas = 800 fits; permutations are the sharding unit
+    'cfg4': dict(n_features=64, n_channels=306, label='shapley_score unit: 1 permutation over 8 groups of 8 features (8 nested sets) '
+                                                      'x 5 folds x 20 alphas, cfg2 data (BASELINE configs[3], one permutation per GPU per step)'),
 }
 
 
@@ -112,6 +116,9 @@ def cpu_baseline(X, y, alphas, workload: str):
     scale = (C / n_s) ** 2
     per_fold_full = sec * scale
     value = N_ALPHAS / per_fold_full
+    if workload == 'cfg4':      # 8 nested sets of k/8 of the features each, same cost law per set
+        nested = sum((k / 8.0) ** 2 for k in range(1, 9))
+        value = 8 * N_ALPHAS / (per_fold_full * nested)
     sample = (f'1 of {N_FOLDS} folds, {n_s} of {C} stimulus features (p={n_s * W} of {C * W} columns, n={n_rows} rows, '
               f'{y.shape[1]} channels, {N_ALPHAS} alphas) took {sec:.2f} s on {threads} threads = {N_ALPHAS / sec:.3f} fits/s; '
               f'value extrapolates to the full column count with the n*p^2 cost law (x{scale:.0f})')
@@ -137,7 +144,7 @@ def main():
     config = dict(workload=cfg['label'], trials=120, features=cfg['n_features'], channels=cfg['n_channels'], timepoints=400,
                   lags=201, alphas=N_ALPHAS, folds=N_FOLDS, units_per_step_per_gpu=1, parallelism=f'units-sharded x{args.gpus}',
                   l2='inputs + per-fold operands (>=1.3 GB at cfg2) exceed the 126 MB L2; no explicit flush')
-    fits_per_unit = N_ALPHAS * N_FOLDS
+    fits_per_unit = N_ALPHAS * N_FOLDS * (8 if args.workload == 'cfg4' else 1)
 
     if args.impl == 'reference':
         if rank != 0:
@@ -182,11 +189,20 @@ def main():
 
     from mvpy_b200 import _dist
 
+    groups = torch.eye(8).repeat_interleave(8, 1)
+
+    def run_unit(Xu, yu):
+        """One sharding unit on this rank: a whole cross-validation (cfg1/cfg2) or a whole Shapley permutation (cfg4)."""
+        with _dist.sharded_region():        # nothing inside the unit is sharded further, exactly as inside shapley_score
+            if args.workload == 'cfg4':
+                torch.manual_seed(1 + rank)
+                sh = mv.model_selection.Shapley(mv.crossvalidation.Validator(pipe, cv=N_FOLDS), n_permutations=1,
+                                                keep_validators=False).fit(Xu, yu, groups=groups.to(Xu.device))
+                return sh, sh.score_
+            return mv.crossvalidation.cross_val_score(pipe, Xu, yu, cv=N_FOLDS)
+
     def step_device():
-        # each rank owns a whole cross-validation unit (the Shapley / hierarchical sharding unit): the folds inside it
-        # run locally, exactly as they do inside a sharded shapley_score
-        with _dist.sharded_region():
-            _, sc = mv.crossvalidation.cross_val_score(pipe, Xd, yd, cv=N_FOLDS)
+        _, sc = run_unit(Xd, yd)
         if world > 1:
             out = torch.empty((world,) + tuple(sc.shape), dtype=sc.dtype, device=dev)
             dist.all_gather_into_tensor(out, sc.contiguous())
@@ -194,8 +210,7 @@ def main():
         return sc
 
     def step_host():
-        with _dist.sharded_region():
-            val, sc = mv.crossvalidation.cross_val_score(pipe, Xh, yh, cv=N_FOLDS)  # h2d inside, results back on host
+        val, sc = run_unit(Xh, yh)                                                   # h2d inside, results back on host
         if world > 1:                                                                # the one collective: gather of score shards
             out = torch.empty((world,) + tuple(sc.shape), dtype=sc.dtype, device=dev)
             dist.all_gather_into_tensor(out, sc.to(dev).contiguous())
@@ -261,7 +276,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     d2h = sc_h.numel() * sc_h.element_size()
-    for m in val.model_:
+    for m in (val.model_ if hasattr(val, 'model_') else []):      # fitted pipelines come back to the host with the scores
         td = m[-1]
         d2h += td.estimator.coef_.numel() * 4 + td.estimator.intercept_.numel() * 4 + m[0].mean_.numel() * 8
     e2e = dict(value=world * fits_per_unit / e2e_s, unit='fits/s', h2d_bytes_per_step=int(Xh.numel() * 4 + yh.numel() * 4),

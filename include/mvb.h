@@ -40,7 +40,7 @@ int64_t mvb_launch_count(void);
 
 /* ---- measurement hook ----------------------------------------------------------------------------
  * Off by default.  After mvb_profile_reset() every tensor-core contraction launch is bracketed by CUDA
- * events on its own stream (at most 512 timed launches per kernel class; the rest are only counted).
+ * events on its own stream (at most 32768 timed launches per kernel class; the rest are only counted).
  * mvb_profile_read synchronises those events and reports, per class c < n_classes: timed milliseconds,
  * algorithmic flops (2*M*N*K) of the timed launches, flops of all launches, #timed and #all launches.
  * Used by bench.py for the roofline line; mvb_profile_disable() turns the hook off again.            */

@@ -35,7 +35,7 @@ static_assert(NB == bj::PR, "block size must match the shared-memory eigensolver
 struct Plan {
   int p, P, nblk;
   size_t bytes;
-  size_t off_Gp, off_Wt, off_Wt2, off_H, off_S, off_J, off_M, off_lam, off_rowP, off_row128, off_iota, off_part, off_ctl;
+  size_t off_Gp, off_Qc, off_Wt, off_Wt2, off_H, off_S, off_J, off_M, off_lam, off_rowP, off_row128, off_iota, off_part, off_ctl;
   size_t part_elems;
 };
 
@@ -49,6 +49,7 @@ inline Plan make_plan(int p) {
   size_t off = 0;
   auto take = [&](size_t bytes) { off = (off + 255) / 256 * 256; size_t o = off; off += bytes; return o; };
   pl.off_Gp = take(P * P * 4);
+  pl.off_Qc = take(P * P * 4);          // Q^T, kept in step with Qt so that products over Q's rows read k-contiguous operands
   pl.off_Wt = take(NB * P * 4);
   pl.off_Wt2 = take(NB * P * 4);
   pl.off_H = take(NB * P * 4);
@@ -310,6 +311,15 @@ __global__ void __launch_bounds__(1024) ns_matrix_kernel(const float* __restrict
   }
 }
 
+// Qc[c][j0 + r] = Qt_block[r][c]  for one 128-row block of Qt (both matrices P x P row-major)
+__global__ void transpose_block_kernel(const float* __restrict__ blk, int P, int j0, float* __restrict__ Qc) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) tile[i][threadIdx.x] = blk[(size_t)(r0 + i) * P + c0 + threadIdx.x];
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) Qc[(size_t)(c0 + i) * P + j0 + r0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+
 __global__ void latch_kernel(unsigned int* dst, const unsigned int* src) { if (threadIdx.x == 0) *dst = *src; }
 __global__ void copy_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n, const unsigned int* skip) {
   if (skip && *skip) return;
@@ -412,7 +422,7 @@ inline bool reorth(Ctx& cx, float* W, const float* Qt, int nq, const unsigned in
   float *H = cx.f(pl.off_H), *W2 = cx.f(pl.off_Wt2);
   GatherOperand w{W, rowP, iota, NB, 2}, q{Qt, rowP, iota, nq, 2};
   if (!gemm(cx, w, q, NB, nq, P, H, P, skip)) return false;
-  GatherOperand h{H, rowP, iota, NB, 2}, qc{Qt, iota, rowP, P, 0};
+  GatherOperand h{H, rowP, iota, NB, 2}, qc{cx.f(pl.off_Qc), rowP, iota, P, 2};      // rows c of Q^T, k over Q's first nq rows
   if (!gemm(cx, h, qc, NB, P, nq, W2, P, skip)) return false;
   sub_kernel<<<148 * 2, 256, 0, cx.st>>>(W, W2, (int64_t)NB * P, skip); ++cx.launches;
   return true;
@@ -453,6 +463,7 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
   LB_CK(cudaMemcpyAsync(Qt, Wt, (size_t)NB * P * 4, cudaMemcpyDeviceToDevice, st));
   for (int j = 0; j < nb; ++j) {
     const float* Qj = Qt + (size_t)j * NB * P;
+    transpose_block_kernel<<<dim3(P / 32, NB / 32), dim3(32, 8), 0, st>>>(Qj, P, j * NB, cx.f(pl.off_Qc)); ++cx.launches;   // block j is final
     // W = Q_j Gp ;  H = W Q_{0..j}^T  -> T_jj, T_{j,j-1}
     GatherOperand qj{Qj, rowP, iota, NB, 2}, g{Gp, rowP, iota, P, 2};
     LB_OK(gemm(cx, qj, g, NB, P, P, Wt, P));
@@ -469,7 +480,7 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
     if (j == nb - 1) break;
     {
       float* W2 = cx.f(pl.off_Wt2);
-      GatherOperand h{H + (size_t)b0 * NB, rowP, iota, NB, 2}, qc{Qt + (size_t)b0 * NB * P, iota, rowP, P, 0};
+      GatherOperand h{H + (size_t)b0 * NB, rowP, iota, NB, 2}, qc{cx.f(pl.off_Qc), rowP, iota + (size_t)b0 * NB, P, 2};
       LB_OK(gemm(cx, h, qc, NB, P, nq1, W2, P));
       sub_kernel<<<148 * 2, 256, 0, st>>>(Wt, W2, (int64_t)NB * P); ++cx.launches;
     }

@@ -45,10 +45,10 @@ int fail(int code, const char* fmt, ...) {
 // ---- measurement hook (include/mvb.h) ------------------------------------------------------------------
 enum ProfClass { PC_GRAM = 0, PC_XTY, PC_SMALL, PC_LEVERAGE_Z, PC_RESIDUAL, PC_PREDICT, PC_EIG_GRAM, PC_EIG_APPLY,
                  PC_EIG_REFRESH, PC_OTHER, PC_COUNT };
-const char* kProfNames[PC_COUNT] = {"gram X^T X (implicit Toeplitz)", "X^T y", "V^T b / beta (dense)", "Z = X V (leverages)",
+const char* kProfNames[PC_COUNT] = {"gram X^T X (implicit Toeplitz)", "X^T y", "Q b and beta = Q^T x (dense)", "Z = X Q^T (leverages)",
                                     "R = X beta (LOO residuals)", "predict X coef", "eig: pair Gram", "eig: rotate rows",
-                                    "eig refresh / band reduction (block Lanczos)", "other"};
-constexpr int kProfMaxTimed = 512;
+                                    "band reduction (block Lanczos) / eig refresh", "block substitution sweep (forward / backward)"};
+constexpr int kProfMaxTimed = 32768;   // per class: enough to time every contraction launch of a multi-step bench run
 struct ProfState {
   bool on = false;
   std::mutex mu;
@@ -624,7 +624,8 @@ int ridge_solve_band(const mvb_design* d, const float* y, int F, float* G, const
     }
     // beta_all[(a,f)][jj] = sum_k Xb[(a,f)][k] Qt[k][jj]
     mvb_operand opX{w.Xb, w.rowP, w.iota, (int)AF, 2};
-    mvb_operand opQc{w.Qt, w.iota, w.rowP, (int)p, 0};        // rows jj (contiguous), contraction k (stride P)
+    const float* Qc = (const float*)((const char*)w.lanczos_ws + mvb::lb::make_plan((int)p).off_Qc);   // Q^T from the reduction
+    mvb_operand opQc{Qc, w.rowP, w.iota, (int)p, 2};          // rows jj of Q^T, contraction k contiguous
     { ProfScope ps(PC_SMALL); rc = run_contract<float>(opX, opQc, (int)AF, (int)p, (int)P, w.beta, p, 0, w.contract_ws, w.contract_bytes, st); }
     if (rc) return rc;
   }
