@@ -488,3 +488,18 @@ def test_rank_and_spearman_golden(golden):
     from oracle import mvpy_oracle as orc
     ref_s = orc.spearmanr_last(orc.move_reduce_last((y + x).cpu().double(), (0,)), orc.move_reduce_last((y * 2 + 1).cpu().double(), (0,)))
     np.testing.assert_allclose(sc['spearmanr'].cpu().numpy(), ref_s.numpy(), atol=1e-5)
+
+
+@pytest.mark.parametrize('n_alphas', [1, 37])
+def test_alpha_grid_sizes(n_alphas):
+    """A single alpha (the constructor default) and a grid that is not a multiple of anything, band route."""
+    mv, orc = _mv(), _orc()
+    g = torch.Generator().manual_seed(9)
+    X = torch.randn(10, 3, 90, generator=g)
+    y = torch.einsum('fc,nct->nft', torch.randn(2, 3, generator=g), X) + torch.randn(10, 2, 90, generator=g)
+    alphas = torch.tensor([10.0]) if n_alphas == 1 else torch.logspace(-4, 6, n_alphas)
+    td = mv.estimators.TimeDelayed(-0.5, 0.0, 100, alphas=alphas).fit(X.cuda(), y.cuda())      # 51 lags -> p = 153
+    ref = orc.trf_fit(X.double(), y.double(), orc.lag_window(-0.5, 0.0, 100), alphas.double(), solver=orc.ridge_loo_fit_primal)
+    assert float(td.estimator.alpha_) == float(ref['alpha'])
+    rc = ref['flat_coef'].numpy()
+    np.testing.assert_allclose(td.estimator.coef_.cpu().numpy(), rc, rtol=1e-4, atol=1e-4 * np.abs(rc).max())
