@@ -114,15 +114,16 @@ __global__ void sub_kernel(float* __restrict__ W, const float* __restrict__ W2, 
 }
 
 // out[z-sum] : reduce split-K partials (fixed order)
+// subtract: out -= sum of partials (the Gram-Schmidt update W -= H Q without a temporary)
 __global__ void reduce_parts_kernel(const float* __restrict__ part, int splits, int64_t stride, int M, int N, float* out, int64_t ldo,
-                                    const unsigned int* skip = nullptr) {
+                                    const unsigned int* skip = nullptr, int subtract = 0) {
   if (skip && *skip) return;
   const int64_t total = (int64_t)M * N;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = e / N, n = e - m * N;
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += part[z * stride + e];
-    out[m * ldo + n] = s;
+    out[m * ldo + n] = subtract ? out[m * ldo + n] - s : s;
   }
 }
 
@@ -218,22 +219,51 @@ __global__ void __launch_bounds__(1024) chol_orth_kernel(const float* __restrict
     }
     __syncthreads();
   }
-  // Li = L^-1 (lower): column c solved by 8 cooperating lanes (forward substitution)
-  {
-    const int c = threadIdx.x >> 3, sub = threadIdx.x & 7;      // 128 columns x 8 lanes
-    for (int i = 0; i < NB; ++i) {
-      float acc = 0.f;
-      if (i >= c) {
-        for (int k = c + sub; k < i; k += 8) acc += Cm[i * CLD + k] * Li[k * CLD + c];
-      }
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-      if (sub == 0) Li[i * CLD + c] = (i < c) ? 0.f : (((i == c) ? 1.f : 0.f) - acc) / Cm[i * CLD + i];
-      __syncwarp();
+  // Li = L^-1 (lower) by 16 x 16 blocks:  M_ii = L_ii^-1 (all eight diagonal blocks at once, one thread per column),
+  // then block row by block row  M_ij = -M_ii sum_{j <= k < i} L_ik M_kj  (two barriers per block row).
+  constexpr int NBLK = NB / PB;
+  if (threadIdx.x < NB) {
+    const int blk = threadIdx.x / PB, c = threadIdx.x % PB, o = blk * PB;      // column c of diagonal block blk
+    float x[PB];
+#pragma unroll
+    for (int i = 0; i < PB; ++i) {
+      float v = (i == c) ? 1.f : 0.f;
+#pragma unroll
+      for (int k = 0; k < PB; ++k)
+        if (k < i && k >= c) v -= Cm[(o + i) * CLD + o + k] * x[k];
+      x[i] = (i < c) ? 0.f : v / Cm[(o + i) * CLD + o + i];
     }
+#pragma unroll
+    for (int i = 0; i < PB; ++i) Li[(o + i) * CLD + o + c] = x[i];
   }
   __syncthreads();
+  float* Tm = Cm;      // the strictly-lower blocks of Cm are read (L_ik) and, per block row, reused for T_ij after the reads
+  for (int bi = 1; bi < NBLK; ++bi) {
+    // T_ij = sum_{k=j}^{bi-1} L_{bi,k} M_{k,j}  for all j < bi: bi * 256 elements
+    float t_acc[2] = {0.f, 0.f};
+    int n_mine = 0;
+    for (int e = threadIdx.x; e < bi * PB * PB; e += blockDim.x, ++n_mine) {
+      const int j = e / (PB * PB), r = (e / PB) % PB, c = e % PB;
+      float acc = 0.f;
+      for (int k = j * PB; k < bi * PB; ++k) acc += Cm[(bi * PB + r) * CLD + k] * Li[k * CLD + j * PB + c];
+      t_acc[n_mine] = acc;
+    }
+    __syncthreads();
+    n_mine = 0;
+    for (int e = threadIdx.x; e < bi * PB * PB; e += blockDim.x, ++n_mine) {
+      const int j = e / (PB * PB), r = (e / PB) % PB, c = e % PB;
+      Tm[(bi * PB + r) * CLD + j * PB + c] = t_acc[n_mine];       // overwrite L_{bi,j} with T_{bi,j} (all reads are done)
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < bi * PB * PB; e += blockDim.x) {
+      const int j = e / (PB * PB), r = (e / PB) % PB, c = e % PB;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < PB; ++k) acc += Li[(bi * PB + r) * CLD + bi * PB + k] * Tm[(bi * PB + k) * CLD + j * PB + c];
+      Li[(bi * PB + r) * CLD + j * PB + c] = -acc;
+    }
+    __syncthreads();
+  }
   for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) Mmat[e] = Li[(e / NB) * CLD + (e % NB)];
   if (threadIdx.x == 0) {
     const bool ok = s_min > pivot_tol * s_max;     // NaN compares false -> robust path
@@ -349,7 +379,7 @@ struct Ctx {
 
 // C[M x N] (ld ldc) = A(M x K) * B(N x K)^T with automatic split-K for skinny outputs
 inline bool gemm(Ctx& cx, const GatherOperand& A, const GatherOperand& B, int M, int N, int K, float* C, int64_t ldc,
-                 const unsigned int* skip = nullptr) {
+                 const unsigned int* skip = nullptr, bool subtract = false) {
   const int bn = N > 128 ? 256 : 128;
   const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
   int max_splits = (int)std::min<size_t>(64, cx.pl.part_elems / ((size_t)M * N));
@@ -357,7 +387,8 @@ inline bool gemm(Ctx& cx, const GatherOperand& A, const GatherOperand& B, int M,
   const int splits = tc_choose_splits(tiles, (K + tc::BK - 1) / tc::BK, max_splits, (int64_t)M * N);
   TcGemmParams g = tc_gemm_defaults();
   g.A = A; g.B = B; g.M = M; g.N = N; g.K = K; g.skip_flag = skip;
-  if (splits > 1) { g.C = cx.f(cx.pl.off_part); g.ldc = N; g.c_split_stride = (int64_t)M * N; }
+  const bool via_parts = splits > 1 || subtract;      // C -= A B^T always goes through the partial-sum buffer
+  if (via_parts) { g.C = cx.f(cx.pl.off_part); g.ldc = N; g.c_split_stride = (int64_t)M * N; }
   else { g.C = C; g.ldc = ldc; }
   const bool timed = cx.hooks && !skip;       // conditional (clean-up round) launches are normally no-ops: not profiled
   const int slot = timed ? cx.hooks->begin(2, 2.0 * M * (double)N * K, cx.st) : -1;
@@ -365,8 +396,8 @@ inline bool gemm(Ctx& cx, const GatherOperand& A, const GatherOperand& B, int M,
   if (timed) cx.hooks->end(slot, cx.st);
   ++cx.launches;
   if (cx.err != cudaSuccess) return false;
-  if (splits > 1) {
-    reduce_parts_kernel<<<148 * 4, 256, 0, cx.st>>>(cx.f(cx.pl.off_part), splits, (int64_t)M * N, M, N, C, ldc, skip);
+  if (via_parts) {
+    reduce_parts_kernel<<<148 * 4, 256, 0, cx.st>>>(cx.f(cx.pl.off_part), splits, (int64_t)M * N, M, N, C, ldc, skip, subtract ? 1 : 0);
     ++cx.launches;
   }
   return true;
@@ -423,9 +454,7 @@ inline bool reorth(Ctx& cx, float* W, const float* Qt, int nq, const unsigned in
   GatherOperand w{W, rowP, iota, NB, 2}, q{Qt, rowP, iota, nq, 2};
   if (!gemm(cx, w, q, NB, nq, P, H, P, skip)) return false;
   GatherOperand h{H, rowP, iota, NB, 2}, qc{cx.f(pl.off_Qc), rowP, iota, P, 2};      // rows c of Q^T, k over Q's first nq rows
-  if (!gemm(cx, h, qc, NB, P, nq, W2, P, skip)) return false;
-  sub_kernel<<<148 * 2, 256, 0, cx.st>>>(W, W2, (int64_t)NB * P, skip); ++cx.launches;
-  return true;
+  return gemm(cx, h, qc, NB, P, nq, W, P, skip, true);                                // W -= H Q
 }
 
 // Enqueue the reduction.  G: p x p.  Outputs: Qt (P x P), Tdiag / Tsub ([nblk][128][128]; Tsub[j] = T_{j,j-1}).
@@ -479,10 +508,8 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
     }
     if (j == nb - 1) break;
     {
-      float* W2 = cx.f(pl.off_Wt2);
       GatherOperand h{H + (size_t)b0 * NB, rowP, iota, NB, 2}, qc{cx.f(pl.off_Qc), rowP, iota + (size_t)b0 * NB, P, 2};
-      LB_OK(gemm(cx, h, qc, NB, P, nq1, W2, P));
-      sub_kernel<<<148 * 2, 256, 0, st>>>(Wt, W2, (int64_t)NB * P); ++cx.launches;
+      LB_OK(gemm(cx, h, qc, NB, P, nq1, Wt, P, nullptr, true));                        // W -= T_j,j-1 Q_j-1 + T_jj Q_j
     }
     if (cx.reorth2) LB_OK(reorth(cx, Wt, Qt, nq));
     float* Qn = Qt + (size_t)(j + 1) * NB * P;
