@@ -108,11 +108,13 @@ def cpu_reference_sample(X, y, alphas, n_feat_sample: int, threads: int):
 def cpu_baseline(X, y, alphas, workload: str):
     threads = os.cpu_count() or 1
     C = X.shape[1]
-    n_s = C if workload == 'cfg1' else 8
+    n_s = C if workload == 'cfg1' else 16         # a quarter of the predictors: ~10-20 s of CPU work per sample
     sec = cpu_reference_sample(X, y, alphas, n_s, threads)
     W = 201
     n_rows = (X.shape[0] - X.shape[0] // N_FOLDS) * X.shape[2]
     # the reference's cost is dominated by the thin SVD of the (n x p) design and the (A x n x p x f) dual products: ~ n p^2
+    # (SURVEY 8d measured the unmodified reference at ~4.5 min per fold on 8 cores at the full size, which this law
+    # reproduces from the 16-feature sample to within ~20 %)
     scale = (C / n_s) ** 2
     per_fold_full = sec * scale
     value = N_ALPHAS / per_fold_full
