@@ -13,6 +13,7 @@
 #include "jacobi_block.cuh"
 #include "lanczos_band.cuh"
 #include "band_loo.cuh"
+#include "sweep_chain.cuh"
 
 namespace {
 
@@ -563,10 +564,20 @@ int ridge_solve_band(const mvb_design* d, const float* y, int F, float* G, const
   MVB_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
   MVB_CUDA(cudaEventDestroy(ev_fork));
   MVB_CUDA(cudaEventDestroy(ev_join));
-  // 4. forward substitution over the blocks for every (alpha, row) as ONE K = 256 contraction per block:
-  //    u_j = [Minv_j | -N_j] [z_j ; u_{j-1}],  h += |u_j|^2 in the epilogue (two column halves, added at the end)
-  MVB_CUDA(cudaMemsetAsync(w.h, 0, (size_t)mvb::TC_ROWSQ_PARTS * A * n * 4, st));
-  {
+  // 4. forward substitution over the blocks for every (alpha, row):  u_j = [Minv_j | -N_j] [z_j ; u_{j-1}],  h = sum_j |u_j|^2.
+  //    Default: one kernel in which every (row tile, alpha) CTA walks its whole chain with u resident on the SM
+  //    (sweep_chain.cuh).  MVB_SWEEP_CHAIN=0: one batched K = 256 contraction per block with |u|^2 in its epilogue.
+  const char* chain_env = getenv("MVB_SWEEP_CHAIN");
+  const bool use_chain = !(chain_env && atoi(chain_env) == 0);
+  if (use_chain) {
+    g_prof_class = PC_OTHER;
+    const int slot = prof_begin(2.0 * n * 128.0 * 256.0 * A * nb, st);
+    MVB_CUDA(mvb::sc::sweep_chain_launch(w.Z, w.MN, n, (int)nb, A, w.h, st));
+    prof_end(slot, st);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    leverage_to_d_kernel<<<grid_for(n * A), 256, 0, st>>>(w.h, n, A, fit_intercept ? 1.f / (float)n : 0.f, w.dd, 1);   MVB_LAUNCHED();
+  } else {
+    MVB_CUDA(cudaMemsetAsync(w.h, 0, (size_t)mvb::TC_ROWSQ_PARTS * A * n * 4, st));
     sweep_koff_kernel<<<grid_for(nb * A * 256), 256, 0, st>>>(w.kofs, (int)nb, A, n, w.U0 - w.Z, w.U1 - w.Z);   MVB_LAUNCHED();
     mvb::iota_offsets_kernel<<<grid_for((int64_t)A * nb * 128), 256, 0, st>>>(w.tab256, (int64_t)A * nb * 128, 256);   MVB_LAUNCHED();
     for (int j = 0; j < nb; ++j) {
@@ -584,8 +595,8 @@ int ridge_solve_band(const mvb_design* d, const float* y, int F, float* G, const
       prof_end(slot, st);
       g_launches.fetch_add(1, std::memory_order_relaxed);
     }
+    leverage_to_d_kernel<<<grid_for(n * A), 256, 0, st>>>(w.h, n, A, fit_intercept ? 1.f / (float)n : 0.f, w.dd, mvb::TC_ROWSQ_PARTS);   MVB_LAUNCHED();
   }
-  leverage_to_d_kernel<<<grid_for(n * A), 256, 0, st>>>(w.h, n, A, fit_intercept ? 1.f / (float)n : 0.f, w.dd, mvb::TC_ROWSQ_PARTS);   MVB_LAUNCHED();
   // 5. beta for every alpha:  Ct[f] = Qt b_f ;  L u = Ct ;  L^T x = u ;  beta = Qt^T x
   {
     mvb_operand opB{XtY, w.iota, w.iota_F, F, 0};            // rows f (contiguous), contraction j (stride F)
