@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(NTH, 1) sweep_chain_kernel(const float* __rest
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t smem0 = tc::smem_u32(smem);
+  const uint64_t dzero = tc::make_desc(0, LBO, 128);        // descriptor with a zero start address
 
   // staging map: thread -> (row = tid / 4, 16-byte k-chunk = tid % 4) of the 128 x 16 stage tile
   const int srow = threadIdx.x >> 2, skc = threadIdx.x & 3;
@@ -120,16 +121,16 @@ __global__ void __launch_bounds__(NTH, 1) sweep_chain_kernel(const float* __rest
       const bool chunk_last = ((s + 1) % (NSTAGE / 2)) == 0;
       if (threadIdx.x == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sbase = smem0 + buf * STAGE;
-        const uint32_t a_hi = from_z ? sbase : smem0 + OFF_U + (uint32_t)((s - NSTAGE / 2) * (SBK / 4) * LBO);
-        const uint32_t a_lo = from_z ? sbase + ST_PLANE : a_hi + U_PLANE;
-        const uint32_t b_hi = sbase + 2 * ST_PLANE, b_lo = sbase + 3 * ST_PLANE;
+        // descriptors differ only in their 14-bit start-address field (bytes >> 4; all of shared memory fits): one add each
+        const uint64_t dstage = dzero + (uint64_t)((smem0 + buf * STAGE) >> 4);
+        const uint64_t du = dzero + (uint64_t)((smem0 + OFF_U) >> 4) + (uint64_t)(from_z ? 0 : ((s - NSTAGE / 2) * (SBK / 4) * LBO) >> 4);
 #pragma unroll
         for (int ks = 0; ks < SBK / 8; ++ks) {
-          const uint64_t da_hi = tc::make_desc(a_hi + 2 * ks * LBO, LBO, 128);
-          const uint64_t da_lo = tc::make_desc(a_lo + 2 * ks * LBO, LBO, 128);
-          const uint64_t db_hi = tc::make_desc(b_hi + 2 * ks * LBO, LBO, 128);
-          const uint64_t db_lo = tc::make_desc(b_lo + 2 * ks * LBO, LBO, 128);
+          constexpr uint64_t KS = (2 * LBO) >> 4;
+          const uint64_t da_hi = (from_z ? dstage : du) + ks * KS;
+          const uint64_t da_lo = (from_z ? dstage + (ST_PLANE >> 4) : du + (U_PLANE >> 4)) + ks * KS;
+          const uint64_t db_hi = dstage + ((2 * ST_PLANE) >> 4) + ks * KS;
+          const uint64_t db_lo = dstage + ((3 * ST_PLANE) >> 4) + ks * KS;
           tc::mma_tf32(tmem_base, da_lo, db_hi, IDESC, (!chunk_first || ks > 0) ? 1u : 0u);
           tc::mma_tf32(tmem_base, da_hi, db_lo, IDESC, 1u);
           tc::mma_tf32(tmem_base, da_hi, db_hi, IDESC, 1u);
