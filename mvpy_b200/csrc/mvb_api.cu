@@ -566,13 +566,16 @@ int ridge_solve_band(const mvb_design* d, const float* y, int F, float* G, const
   MVB_CUDA(cudaEventDestroy(ev_join));
   // 4. forward substitution over the blocks for every (alpha, row):  u_j = [Minv_j | -N_j] [z_j ; u_{j-1}],  h = sum_j |u_j|^2.
   //    Default: one kernel in which every (row tile, alpha) CTA walks its whole chain with u resident on the SM
-  //    (sweep_chain.cuh).  MVB_SWEEP_CHAIN=0: one batched K = 256 contraction per block with |u|^2 in its epilogue.
+  //    (sweep_chain.cuh): in tensor memory as the MMA's A operand (MVB_SWEEP_CHAIN=2, default) or in shared memory (=1).
+  //    MVB_SWEEP_CHAIN=0: one batched K = 256 contraction per block with |u|^2 in its epilogue.
   const char* chain_env = getenv("MVB_SWEEP_CHAIN");
-  const bool use_chain = !(chain_env && atoi(chain_env) == 0);
+  const int chain_mode = chain_env ? atoi(chain_env) : 2;
+  const bool use_chain = chain_mode != 0;
   if (use_chain) {
     g_prof_class = PC_OTHER;
     const int slot = prof_begin(2.0 * n * 128.0 * 256.0 * A * nb, st);
-    MVB_CUDA(mvb::sc::sweep_chain_launch(w.Z, w.MN, n, (int)nb, A, w.h, st));
+    if (chain_mode == 2) MVB_CUDA(mvb::sc::sweep_chain_tmem_launch(w.Z, w.MN, n, (int)nb, A, w.h, st));
+    else MVB_CUDA(mvb::sc::sweep_chain_launch(w.Z, w.MN, n, (int)nb, A, w.h, st));
     prof_end(slot, st);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     leverage_to_d_kernel<<<grid_for(n * A), 256, 0, st>>>(w.h, n, A, fit_intercept ? 1.f / (float)n : 0.f, w.dd, 1);   MVB_LAUNCHED();
