@@ -34,13 +34,16 @@ constexpr int SMEM_BYTES = OFF_RED + 4 * NB * 4;
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 // Zblk: [nb][n][128] centred Z = X Q^T in column blocks; MN: [A][nb][128][256] rows [L_j^-1 | -L_j^-1 W_j];
-// h: [A][n] = sum_j |u_j|^2.   grid = (ceil(n / 128), A), 512 threads.
+// h: [A][n] = sum_j |u_j|^2.   grid = (A, ceil(n / 128)), 512 threads.
 __global__ void __launch_bounds__(NTH, 1) sweep_chain_kernel(const float* __restrict__ Zblk, const float* __restrict__ MN, int64_t n,
                                                              int nb, float* __restrict__ h) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row0 = (int64_t)blockIdx.x * NB;
-  const int a = blockIdx.y;
+  // alpha is the fast grid index: the ~148 CTAs running at a time cover all alphas of a few row tiles, so a z tile is
+  // fetched from HBM once and served to the other alphas by L2 (row tiles fastest re-read Z from DRAM once per alpha:
+  // ncu measured 40.8 GB of DRAM reads for 2 GB of Z), while the factor blocks of all alphas stay L2 resident
+  const int64_t row0 = (int64_t)blockIdx.y * NB;
+  const int a = blockIdx.x;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);     // [0],[1]: stage buffer free; [2]: chunk complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 32);
   float* red = reinterpret_cast<float*>(smem + OFF_RED);
@@ -196,7 +199,7 @@ inline cudaError_t sweep_chain_launch(const float* Zblk, const float* MN, int64_
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid((unsigned)((n + NB - 1) / NB), (unsigned)A);
+  dim3 grid((unsigned)A, (unsigned)((n + NB - 1) / NB));
   sweep_chain_kernel<<<grid, NTH, SMEM_BYTES, st>>>(Zblk, MN, n, nb, h);
   return cudaGetLastError();
 }
@@ -244,8 +247,11 @@ __global__ void __launch_bounds__(NTH, 1) sweep_chain_tmem_kernel(const float* _
                                                                   int nb, float* __restrict__ h) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row0 = (int64_t)blockIdx.x * NB;
-  const int a = blockIdx.y;
+  // alpha is the fast grid index: the ~148 CTAs running at a time cover all alphas of a few row tiles, so a z tile is
+  // fetched from HBM once and served to the other alphas by L2 (row tiles fastest re-read Z from DRAM once per alpha:
+  // ncu measured 40.8 GB of DRAM reads for 2 GB of Z), while the factor blocks of all alphas stay L2 resident
+  const int64_t row0 = (int64_t)blockIdx.y * NB;
+  const int a = blockIdx.x;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T_OFF_BAR);   // [0],[1]: stage buffer free; [2]: chunk complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T_OFF_BAR + 32);
   float* red = reinterpret_cast<float*>(smem + T_OFF_RED);
@@ -406,7 +412,7 @@ inline cudaError_t sweep_chain_tmem_launch(const float* Zblk, const float* MN, i
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid((unsigned)((n + NB - 1) / NB), (unsigned)A);
+  dim3 grid((unsigned)A, (unsigned)((n + NB - 1) / NB));
   tm::sweep_chain_tmem_kernel<<<grid, NTH, tm::T_SMEM_BYTES, st>>>(Zblk, MN, n, nb, h);
   return cudaGetLastError();
 }
