@@ -12,6 +12,8 @@ Fixtures (all produced through the reference's public classes/functions):
   scaler.npz       _Scaler_torch statistics/transforms for several dims.
   kfold.npz        KFold index listings (plain + shuffled with seeds).
   splitters.npz    RepeatedKFold and LeaveGroupsOut (single- and multi-label groups) index listings.
+  stratified.npz   StratifiedKFold / RepeatedStratifiedKFold index listings (multi-feature labels, 3-D labels, shuffled with
+                   the global generator seeded as stored in the script).
   metrics.npz      math.r2 / math.pearsonr incl. zero-variance rows and the y_b baseline.
   rank.npz         math.rank (ties, integer input, the docstring example) and math.spearmanr.
   trf_small.npz    make_meeg_continuous(fs=50, n_trials=40, n_channels=8, n_features=4) seed 0:
@@ -170,6 +172,28 @@ def gen_splitters():
     save('splitters.npz', **out)
 
 
+def gen_stratified():
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    y1 = torch.tensor([2, 0, 1, 1, 0, 2, 2, 1, 0, 0, 1, 2, 0, 1, 2, 2, 0])            # one feature, three classes, uneven
+    y2 = torch.stack([torch.randint(0, 2, (40,), generator=g), 10 + torch.randint(0, 3, (40,), generator=g)], dim=1)
+    y3 = y2[:, :, None].expand(-1, -1, 5).float()                                        # (n, features, time): time 0 is used
+    out['y1'], out['y2'], out['y3'] = y1, y2, y3
+    for name, y, k in (('s1', y1, 3), ('s2', y2, 4), ('s3', y3, 4)):
+        skf = ref.crossvalidation.StratifiedKFold(n_splits=k)
+        for i, (tr, te) in enumerate(skf.split(torch.zeros(y.shape[0], 2), y)):
+            out[f'{name}_tr{i}'], out[f'{name}_te{i}'] = tr, te
+    torch.manual_seed(21)                            # the reference's shuffle draws from torch's global generator
+    skf = ref.crossvalidation.StratifiedKFold(n_splits=4, shuffle=True, random_state=3)
+    for i, (tr, te) in enumerate(skf.split(torch.zeros(40, 2), y2)):
+        out[f'sh_tr{i}'], out[f'sh_te{i}'] = tr, te
+    torch.manual_seed(22)
+    rsk = ref.crossvalidation.RepeatedStratifiedKFold(n_splits=3, n_repeats=2, random_state=5)
+    for i, (tr, te) in enumerate(rsk.split(torch.zeros(17, 2), y1)):
+        out[f'rsk_tr{i}'], out[f'rsk_te{i}'] = tr, te
+    save('stratified.npz', **out)
+
+
 def gen_rank():
     g = torch.Generator().manual_seed(4)
     x = torch.randn(5, 7, 24, generator=g)
@@ -294,6 +318,6 @@ def gen_cfg1():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['ridgecv', 'delay', 'scaler', 'kfold', 'splitters', 'metrics', 'rank', 'trf_small', 'decoder', 'encoder', 'cfg1']
+    which = sys.argv[1:] or ['ridgecv', 'delay', 'scaler', 'kfold', 'splitters', 'stratified', 'metrics', 'rank', 'trf_small', 'decoder', 'encoder', 'cfg1']
     for w in which:
         globals()['gen_' + w]()

@@ -201,3 +201,33 @@ def test_repeated_kfold_and_leave_groups_out_bit_exact(golden):
         def score(self, X, y): return X.sum().reshape(1)
     v = mv.crossvalidation.Validator(M(), cv=mv.crossvalidation.RepeatedKFold(n_splits=3, n_repeats=2, random_state=0))
     assert v.cv_n_ == 6
+
+
+def test_stratified_kfold_bit_exact(golden):
+    """Index listings of the reference's StratifiedKFold / RepeatedStratifiedKFold (tests/golden/stratified.npz):
+    single-feature, multi-feature and 3-D labels; shuffled folds draw from torch's global generator like the reference."""
+    g = golden('stratified.npz')
+    for name, k in (('s1', 3), ('s2', 4), ('s3', 4)):
+        y = T(g['y' + name[1]])
+        folds = list(mv.crossvalidation.StratifiedKFold(n_splits=k).split(torch.zeros(y.shape[0], 2), y))
+        assert len(folds) == k
+        for i, (tr, te) in enumerate(folds):
+            assert tr.dtype == torch.long and np.array_equal(tr.numpy(), g[f'{name}_tr{i}']) and np.array_equal(te.numpy(), g[f'{name}_te{i}'])
+    y2, y1 = T(g['y2']), T(g['y1'])
+    torch.manual_seed(21)
+    for i, (tr, te) in enumerate(mv.crossvalidation.StratifiedKFold(n_splits=4, shuffle=True, random_state=3).split(torch.zeros(40, 2), y2)):
+        assert np.array_equal(tr.numpy(), g[f'sh_tr{i}']) and np.array_equal(te.numpy(), g[f'sh_te{i}'])
+        # stratification: every joint label keeps its share in the held-out fold (within one sample)
+        joint = y2[:, 0] * 100 + y2[:, 1]
+        for v in joint.unique():
+            assert abs(int((joint[te] == v).sum()) - int((joint == v).sum()) / 4) < 1.0
+    torch.manual_seed(22)
+    rsk = mv.crossvalidation.RepeatedStratifiedKFold(n_splits=3, n_repeats=2, random_state=5)
+    folds = list(rsk.split(torch.zeros(17, 2), y1))
+    assert len(folds) == 6 and rsk.n_splits * rsk.n_repeats == 6
+    for i, (tr, te) in enumerate(folds):
+        assert np.array_equal(tr.numpy(), g[f'rsk_tr{i}']) and np.array_equal(te.numpy(), g[f'rsk_te{i}'])
+    with pytest.raises(ValueError):
+        list(mv.crossvalidation.StratifiedKFold(n_splits=5).split(torch.zeros(3, 2), torch.zeros(3)))
+    with pytest.raises(ValueError):          # every class smaller than n_splits
+        list(mv.crossvalidation.StratifiedKFold(n_splits=4).split(torch.zeros(6, 2), torch.tensor([0, 0, 0, 1, 1, 1])))
