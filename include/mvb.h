@@ -150,6 +150,25 @@ int mvb_score(const void* y, const void* yhat, const void* y_b, int64_t R, int64
  * mean of their positions, 1-based) along R for every one of the K cells.  spearmanr = mvb_score's pearson on ranks. */
 int mvb_rank(const void* x, int64_t R, int64_t K, int dtype, void* out, void* stream);
 
+/* ---- ReceptiveField pieces (widening) ----------------------------------------------------------
+ * The per-epoch lagged Gram / cross-moment of _ReceptiveField_torch._compute_corrs (estimators/receptivefield.py:976-1118)
+ * is mvb_trf_stats on a ZERO-padded stimulus with one trial selected (fit_intercept = 0): its rows are exactly the
+ * epoch's samples, which is what the reference's edge correction (:779-807) removes from the FFT correlations.
+ *
+ * mvb_rf_assemble: G [n_trials][p][p] (kernel lag order) + the centred epochs Xc [n_trials][n_feat][n_time] -> cov
+ *   [n_trials][p][p] as the reference lays cov_ out (feature-major, lag s_min.. ascending), reproducing its un-transposed
+ *   lower blocks (:1097-1103) and its head correction for negative lags (:801-807).  With edge_correction = 0 pass the
+ *   Gram of the extended rows (all rows any lagged sample reaches) instead.
+ * mvb_sum_slabs: out = sum_i A[idx[i]] over slabs of slab_elems values -- X_XT[train].sum(0) (:1204-1206).
+ * mvb_penalised_solve: for every alpha, (G + alpha * reg) x = rhs by LU with partial pivoting (torch.linalg.solve,
+ *   :1224-1229; the matrix is not symmetric).  mats [n_alphas][p][p] is scratch, sol [n_alphas][p][n_rhs] the solutions,
+ *   info[s] = 0 or (column + 1) without a non-zero pivot.                                                             */
+int mvb_rf_assemble(const void* G, const void* Xc, int n_trials, int n_feat, int n_lag, int n_time, int s_min, int s_max,
+                    int edge_correction, int dtype, void* cov, void* stream);
+int mvb_sum_slabs(const void* A, int64_t slab_elems, const int32_t* idx, int n_idx, int dtype, void* out, void* stream);
+int mvb_penalised_solve(const void* G, const void* reg, const void* alphas, int n_alphas, const void* rhs, int p, int n_rhs,
+                        int dtype, void* mats, void* sol, int* info, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,9 @@ _SIGNATURES = {
     'mvb_trf_predict_workspace_bytes': (c_size_t, [POINTER(mvb_design), c_int]),
     'mvb_trf_predict': (c_int, [POINTER(mvb_design), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'mvb_rank': (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    'mvb_rf_assemble': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'mvb_sum_slabs': (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    'mvb_penalised_solve': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'mvb_score': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
@@ -300,6 +303,34 @@ def rank_rows(x2: torch.Tensor) -> torch.Tensor:
     out = torch.empty_like(x2)
     check(load().mvb_rank(_ptr(x2), R, K, dtype_code(x2), _ptr(out), _stream(x2)), 'mvb_rank')
     return out
+
+
+def rf_assemble(G: torch.Tensor, Xc: torch.Tensor, s_min: int, s_max: int, edge_correction: bool) -> torch.Tensor:
+    """G (N, p, p) in kernel lag order + centred epochs Xc (N, C, T) -> cov_ (N, p, p) in the reference's layout."""
+    N, C, Tn = Xc.shape
+    cov = torch.empty_like(G)
+    check(load().mvb_rf_assemble(_ptr(G), _ptr(Xc), N, C, s_max - s_min, Tn, s_min, s_max, int(edge_correction), dtype_code(G),
+                                 _ptr(cov), _stream(G)), 'mvb_rf_assemble')
+    return cov
+
+
+def sum_slabs(A: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """A (N, ...) contiguous -> sum over the slabs listed in idx."""
+    idx = idx.to(device=A.device, dtype=torch.int32).contiguous()
+    out = torch.empty(A.shape[1:], dtype=A.dtype, device=A.device)
+    check(load().mvb_sum_slabs(_ptr(A), out.numel(), _ptr(idx), idx.numel(), dtype_code(A), _ptr(out), _stream(A)), 'mvb_sum_slabs')
+    return out
+
+
+def penalised_solve(G: torch.Tensor, reg: torch.Tensor, alphas: torch.Tensor, rhs: torch.Tensor):
+    """(G + alpha reg) x = rhs for every alpha: solutions (S, p, F) and info (S,) int32 (0 = ok)."""
+    p, F, S = G.shape[0], rhs.shape[1], int(alphas.numel())
+    mats = torch.empty((S, p, p), dtype=G.dtype, device=G.device)
+    sol = torch.empty((S, p, F), dtype=G.dtype, device=G.device)
+    info = torch.zeros(S, dtype=torch.int32, device=G.device)
+    check(load().mvb_penalised_solve(_ptr(G), _ptr(reg), _ptr(alphas), S, _ptr(rhs), p, F, dtype_code(G), _ptr(mats), _ptr(sol),
+                                     _ptr(info), _stream(G)), 'mvb_penalised_solve')
+    return sol, info
 
 
 def eigh(A: torch.Tensor):

@@ -14,6 +14,7 @@
 #include "lanczos_band.cuh"
 #include "band_loo.cuh"
 #include "sweep_chain.cuh"
+#include "rf_kernels.cuh"
 
 namespace {
 
@@ -993,6 +994,61 @@ int mvb_score(const void* y, const void* yhat, const void* y_b, int64_t R, int64
   }
   else return fail(MVB_E_UNSUPPORTED, "score: dtype %d", dtype);
   MVB_LAUNCHED();
+  return MVB_OK;
+}
+
+// ---- ReceptiveField pieces ------------------------------------------------------------------------
+int mvb_rf_assemble(const void* G, const void* Xc, int n_trials, int n_feat, int n_lag, int n_time, int s_min, int s_max,
+                    int edge_correction, int dtype, void* cov, void* stream) {
+  if (!G || !Xc || !cov || n_trials < 1 || n_feat < 1 || n_lag < 1 || n_time < 1 || s_max - s_min != n_lag)
+    return fail(MVB_E_ARG, "rf_assemble: bad argument");
+  const int L = (edge_correction && s_min < 0) ? -s_min : 0;
+  if (L > n_time) return fail(MVB_E_ARG, "rf_assemble: %d negative lags need at least as many samples (%d)", L, n_time);
+  const int Lh = L < n_lag ? L : n_lag;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = (int64_t)n_trials * n_feat * n_lag * n_feat * n_lag;
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  if (dtype == MVB_F32) mvb::rf::assemble_kernel<float><<<grid, 256, 0, st>>>((const float*)G, (const float*)Xc, n_trials, n_feat, n_lag, n_time, L, Lh, (float*)cov);
+  else if (dtype == MVB_F64) mvb::rf::assemble_kernel<double><<<grid, 256, 0, st>>>((const double*)G, (const double*)Xc, n_trials, n_feat, n_lag, n_time, L, Lh, (double*)cov);
+  else return fail(MVB_E_UNSUPPORTED, "rf_assemble: dtype %d", dtype);
+  MVB_LAUNCHED();
+  return MVB_OK;
+}
+
+int mvb_sum_slabs(const void* A, int64_t slab_elems, const int32_t* idx, int n_idx, int dtype, void* out, void* stream) {
+  if (!A || !idx || !out || slab_elems < 1 || n_idx < 0) return fail(MVB_E_ARG, "sum_slabs: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (int)std::min<int64_t>((slab_elems + 255) / 256, 148 * 16);
+  if (dtype == MVB_F32) mvb::rf::sum_slabs_kernel<float><<<grid, 256, 0, st>>>((const float*)A, slab_elems, idx, n_idx, (float*)out);
+  else if (dtype == MVB_F64) mvb::rf::sum_slabs_kernel<double><<<grid, 256, 0, st>>>((const double*)A, slab_elems, idx, n_idx, (double*)out);
+  else return fail(MVB_E_UNSUPPORTED, "sum_slabs: dtype %d", dtype);
+  MVB_LAUNCHED();
+  return MVB_OK;
+}
+
+int mvb_penalised_solve(const void* G, const void* reg, const void* alphas, int n_alphas, const void* rhs, int p, int n_rhs,
+                        int dtype, void* mats, void* sol, int* info, void* stream) {
+  if (!G || !reg || !alphas || !rhs || !mats || !sol || !info || n_alphas < 1 || p < 1 || n_rhs < 1)
+    return fail(MVB_E_ARG, "penalised_solve: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t pp = (int64_t)p * p;
+  const size_t es = dtype == MVB_F32 ? 4 : 8;
+  const int grid = (int)std::min<int64_t>((pp * n_alphas + 255) / 256, 148 * 16);
+  for (int s = 0; s < n_alphas; ++s) {      // every system starts from the same right-hand sides
+    cudaError_t e = cudaMemcpyAsync((char*)sol + (size_t)s * p * n_rhs * es, rhs, (size_t)p * n_rhs * es, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return fail(MVB_E_CUDA, "penalised_solve: %s", cudaGetErrorString(e));
+  }
+  if (dtype == MVB_F32) {
+    mvb::rf::penalised_kernel<float><<<grid, 256, 0, st>>>((const float*)G, (const float*)reg, (const float*)alphas, n_alphas, pp, (float*)mats);
+    mvb::rf::lu_solve_kernel<float><<<n_alphas, mvb::rf::LU_THREADS, 0, st>>>((float*)mats, (float*)sol, p, n_rhs, info);
+  } else if (dtype == MVB_F64) {
+    mvb::rf::penalised_kernel<double><<<grid, 256, 0, st>>>((const double*)G, (const double*)reg, (const double*)alphas, n_alphas, pp, (double*)mats);
+    mvb::rf::lu_solve_kernel<double><<<n_alphas, mvb::rf::LU_THREADS, 0, st>>>((double*)mats, (double*)sol, p, n_rhs, info);
+  } else return fail(MVB_E_UNSUPPORTED, "penalised_solve: dtype %d", dtype);
+  MVB_LAUNCHED();
+  MVB_LAUNCHED();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MVB_E_CUDA, "penalised_solve: %s", cudaGetErrorString(e));
   return MVB_OK;
 }
 

@@ -3,5 +3,7 @@ from .timedelayed import TimeDelayed
 from .ridgeencoder import RidgeEncoder
 from .ridgedecoder import RidgeDecoder
 from .sliding import Sliding
+from .b2b import B2B
+from .receptivefield import ReceptiveField
 
-__all__ = ['RidgeCV', 'TimeDelayed', 'RidgeEncoder', 'RidgeDecoder', 'Sliding']
+__all__ = ['RidgeCV', 'TimeDelayed', 'RidgeEncoder', 'RidgeDecoder', 'Sliding', 'B2B', 'ReceptiveField']

@@ -19,6 +19,9 @@ Fixtures (all produced through the reference's public classes/functions):
   trf_small.npz    make_meeg_continuous(fs=50, n_trials=40, n_channels=8, n_features=4) seed 0:
                    cross_val_score / hierarchical_score / shapley_score through Scaler+TimeDelayed.
   decoder.npz      per-slice RidgeCV(alpha_per_target) + Haufe pattern (RidgeDecoder maths), Sliding.
+  b2b.npz          back-to-back regression composed from _RidgeCV_torch + _Scaler_torch as b2b.py:267-306 does.
+  rf.npz           ReceptiveField (needs MVPY_COMPILE_TORCH=0): single alpha, k-fold and LOO alpha selection, laplacian
+                   penalties, patterns, no edge correction / intercept, causal-only and anticausal-only lag ranges.
   encoder.npz      RidgeEncoder 2-D and 3-D (expanded design).
   cfg1_summary.npz config 1 (README flow, fs=200): per-fold alphas, mean scores, strided score samples.
 """
@@ -288,6 +291,89 @@ def gen_decoder():
     save('decoder.npz', **out)
 
 
+def gen_b2b():
+    """B2B composed from the reference's working parts exactly as b2b.py:267-306 spells it out (the class itself
+    cannot be constructed at this commit: it forwards `normalise` to RidgeCV)."""
+    from mvpy.preprocessing.scaler import _Scaler_torch
+    g = torch.Generator().manual_seed(31)
+    N, C, F = 160, 14, 4
+    E = torch.randn(N, F, generator=g)
+    E[:, 1] = 0.7 * E[:, 0] + 0.3 * E[:, 1]                        # correlated targets; target 3 has no effect on X
+    Fm = torch.randn(F, C, generator=g); Fm[3] = 0.0
+    X = E @ Fm + torch.randn(N, C, generator=g)
+    alphas = torch.logspace(-3, 3, 13)
+    out = dict(X=X, y=E, alphas=alphas)
+    for tag, per_target, norm in (('a', False, True), ('b', True, False)):
+        half = N // 2
+        dec = _RidgeCV_torch(alphas=alphas, fit_intercept=True, alpha_per_target=per_target).fit(X[:half], E[:half])
+        sc = _Scaler_torch(with_mean=norm, with_std=norm).fit(dec.predict(X[half:]))
+        enc = _RidgeCV_torch(alphas=alphas, fit_intercept=True, alpha_per_target=per_target).fit(sc.transform(dec.predict(X[half:])), E[half:])
+        Xc, yc = X[:half] - X[:half].mean(0, keepdim=True), E[:half] - E[:half].mean(0, keepdim=True)
+        out[f'{tag}_pattern'] = torch.cov(Xc.T).mm(dec.coef_.T).mm(torch.linalg.pinv(torch.cov(yc.T)))
+        out[f'{tag}_causal'] = enc.coef_.diagonal()
+        out[f'{tag}_dec_alpha'], out[f'{tag}_enc_alpha'] = dec.alpha_, enc.alpha_
+        out[f'{tag}_pred'] = enc.predict(sc.transform(dec.predict(X)))
+    save('b2b.npz', **out)
+
+
+def rf_problem(seed, N, C, F, T, s_lo, s_hi, noise=1.0):
+    g = torch.Generator().manual_seed(seed)
+    X = torch.randn(N, C, T, generator=g, dtype=torch.float64)
+    X = X + 0.6 * torch.roll(X, 1, -1) + 0.5                       # coloured, non-zero mean
+    w = torch.randn(F, C, s_hi - s_lo, generator=g, dtype=torch.float64)
+    y = torch.zeros(N, F, T, dtype=torch.float64)
+    for k in range(s_hi - s_lo):
+        lag = s_lo + k
+        Z = torch.zeros_like(X)
+        if lag >= 0:
+            Z[..., lag:] = X[..., :T - lag]
+        else:
+            Z[..., :T + lag] = X[..., -lag:]
+        y += torch.einsum('fc,nct->nft', w[:, :, k], Z)
+    y = y + noise * y.std() * torch.randn(N, F, T, generator=g, dtype=torch.float64) + 1.5
+    return X, y
+
+
+RF_CASES = {
+    # name: (problem args, (t_min, t_max, fs), constructor kwargs)
+    'single': ((41, 10, 3, 2, 120, -4, 7), (-0.04, 0.06, 100), dict(alpha=1.0)),
+    'kfold': ((41, 10, 3, 2, 120, -4, 7), (-0.04, 0.06, 100), dict(alpha=torch.logspace(-1, 5, 7), reg_cv=5)),
+    'loo': ((41, 10, 3, 2, 120, -4, 7), (-0.04, 0.06, 100), dict(alpha=torch.logspace(-1, 5, 7), reg_cv='LOO')),
+    'laplacian': ((42, 9, 3, 2, 100, -3, 5), (-0.03, 0.04, 100), dict(alpha=[0.1, 10.0, 1000.0], reg_type='laplacian', reg_cv=3, patterns=True)),
+    'noedge': ((43, 6, 2, 3, 90, -5, 4), (-0.05, 0.03, 100), dict(alpha=2.0, edge_correction=False, fit_intercept=False, reg_type=['laplacian', 'ridge'])),
+    'causal': ((44, 8, 1, 1, 150, 2, 9), (0.02, 0.08, 100), dict(alpha=0.5, patterns=True)),
+    'anticausal': ((45, 8, 2, 2, 150, -8, -1), (-0.08, -0.02, 100), dict(alpha=3.0, reg_type=('ridge', 'laplacian'))),
+}
+
+
+RF_REG_CASES = [(3, 4, 'laplacian'), (3, 4, ('ridge', 'laplacian')), (3, 4, ('laplacian', 'ridge')), (1, 5, 'laplacian'),
+                (4, 1, 'laplacian'), (2, 2, 'laplacian'), (3, 4, 'ridge'), (5, 3, ['laplacian', 'laplacian'])]
+
+
+def gen_rf():
+    """ReceptiveField through the reference's public class (torch.compile switched off by MVPY_COMPILE_TORCH=0: the
+    decorated helper is plain Python then), fp64 inputs."""
+    assert os.environ.get('MVPY_COMPILE_TORCH') == '0', 'run with MVPY_COMPILE_TORCH=0 (no C++ toolchain for inductor here)'
+    out = {}
+    for name, (prob, (t0, t1, fs), kw) in RF_CASES.items():
+        X, y = rf_problem(*prob)
+        if name == 'causal':
+            X, y = X[:, 0], y[:, 0]                                # 2-D inputs: one feature, one channel
+        m = ref.estimators.ReceptiveField(t0, t1, fs, **kw).fit(X, y)
+        out[f'{name}_X'], out[f'{name}_y'] = X, y
+        out[f'{name}_cov'], out[f'{name}_coef'], out[f'{name}_alpha'] = m.cov_, m.coef_, m.alpha_
+        out[f'{name}_intercept'] = m.intercept_
+        if m.pattern_ is not None:
+            out[f'{name}_pattern'] = m.pattern_
+        out[f'{name}_pred'] = m.predict(X)
+        print(name, 's', m.s_min, m.s_max, 'alpha_', m.alpha_, 'cov asym', float((m.cov_ - m.cov_.transpose(1, 2)).abs().max()))
+    from mvpy.estimators.receptivefield import _ReceptiveField_torch
+    probe = _ReceptiveField_torch(-0.01, 0.01, 100)
+    for i, (C, W, rt) in enumerate(RF_REG_CASES):
+        out[f'reg{i}'] = probe._compute_reg_neighbours(C, W, rt)
+    save('rf.npz', **out)
+
+
 # ---------------------------------------------------------------------------------------- encoder
 def gen_encoder():
     g = torch.Generator().manual_seed(31)
@@ -318,6 +404,6 @@ def gen_cfg1():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['ridgecv', 'delay', 'scaler', 'kfold', 'splitters', 'stratified', 'metrics', 'rank', 'trf_small', 'decoder', 'encoder', 'cfg1']
+    which = sys.argv[1:] or ['ridgecv', 'delay', 'scaler', 'kfold', 'splitters', 'stratified', 'metrics', 'rank', 'trf_small', 'decoder', 'b2b', 'rf', 'encoder', 'cfg1']
     for w in which:
         globals()['gen_' + w]()

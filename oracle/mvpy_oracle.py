@@ -494,3 +494,193 @@ def encoder_predict(X: torch.Tensor, fit: Dict[str, torch.Tensor]) -> torch.Tens
         yh = ridge_predict(encoder_expand(X), fit['flat_coef'], fit['intercept'])
         return yh.reshape(N, T, -1).swapaxes(1, 2)
     return ridge_predict(X, fit['flat_coef'], fit['intercept'])
+
+
+# --------------------------------------------------------------------------------------------
+# ReceptiveField                  (mvpy/estimators/receptivefield.py:779-1556)
+# --------------------------------------------------------------------------------------------
+# Lag k of the filter stands for sample lag s_k = s_min + k, k = 0..W-1, W = s_max - s_min; the model is
+#   y[n, f, t] = sum_c sum_k coef[f, c, k] * X[n, c, t - s_k]   (X is zero outside 0..T-1)   (:1434-1488).
+# The reference builds the normal equations per epoch from FFT correlations; the same numbers are written
+# here as direct lag sums in the dtype of the inputs (use fp64).
+
+
+def rf_lags(t_min: float, t_max: float, fs: float) -> Tuple[int, int]:
+    """(s_min, s_max) with s_max exclusive (receptivefield.py:955-957)."""
+    return int(t_min * fs), int(t_max * fs) + 1
+
+
+def _lagged(x: torch.Tensor, lag: int) -> torch.Tensor:
+    """x (..., T) -> z with z[t] = x[t - lag], zero outside."""
+    T = x.shape[-1]
+    z = torch.zeros_like(x)
+    if lag >= 0:
+        if lag < T:
+            z[..., lag:] = x[..., :T - lag]
+    elif -lag < T:
+        z[..., :T + lag] = x[..., -lag:]
+    return z
+
+
+def _full_xcorr(a: torch.Tensor, b: torch.Tensor, tau: int) -> torch.Tensor:
+    """sum_t a[t + tau] b[t] over every t where both samples exist (the zero-padded FFT correlation, :1040-1055)."""
+    T = a.shape[-1]
+    if tau >= 0:
+        return (a[tau:] * b[:T - tau]).sum() if tau < T else a.new_zeros(())
+    return (a[:T + tau] * b[-tau:]).sum() if -tau < T else a.new_zeros(())
+
+
+def _diag_cumulative(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """out[m, n] = sum_{d=0..min(m,n)} a[m-d] b[n-d]: the outer product accumulated down its diagonals (:810-830)."""
+    L = a.shape[0]
+    out = a.new_zeros((L, L))
+    for m in range(L):
+        for n in range(L):
+            d = torch.arange(min(m, n) + 1)
+            out[m, n] = (a[m - d] * b[n - d]).sum()
+    return out
+
+
+def rf_corrs(X: torch.Tensor, y: torch.Tensor, s_min: int, s_max: int, fit_intercept: bool = True,
+             edge_correction: bool = True):
+    """Per-epoch auto- and cross-correlation blocks (receptivefield.py:976-1118).
+
+    Returns cov (N, C*W, C*W), xty (N, C*W, F) [row c*W+k], X_offset (C,) / y_offset (F,) (zeros without intercept).
+    Reproduced as the reference computes them, including two things a textbook version would do differently:
+      * the block below the diagonal, (j, i) with j > i, receives the SAME W x W lag block as (i, j), not its
+        transpose (:1097-1103), so cov is not symmetric for C > 1;
+      * the correction for rows before the epoch start (negative lags) accumulates the first |s_min| samples in
+        reversed order without flipping the result back (:801-807 with the flipped epoch passed at :1083).
+    """
+    N, C, T = X.shape
+    F = y.shape[1]
+    W = s_max - s_min
+    if fit_intercept:
+        x_off, y_off = X.mean((0, 2)), y.mean((0, 2))
+        X, y = X - x_off[None, :, None], y - y_off[None, :, None]
+    else:
+        x_off, y_off = X.new_zeros(C), y.new_zeros(F)
+    cov = X.new_zeros((N, C * W, C * W))
+    xty = X.new_zeros((N, C * W, F))
+    for n in range(N):
+        flipped = X[n].flip(-1)
+        for i in range(C):
+            for j in range(i, C):
+                blk = X.new_zeros((W, W))
+                for a in range(W):
+                    for b in range(W):
+                        blk[a, b] = _full_xcorr(X[n, i], X[n, j], b - a)
+                if edge_correction:
+                    if s_max > 0:                       # rows past the epoch end (positive lags)
+                        tail = _diag_cumulative(flipped[i, :s_max - 1], flipped[j, :s_max - 1])
+                        if s_min > 0:
+                            tail = tail[s_min - 1:, s_min - 1:]
+                        o = max(-s_min + 1, 0)
+                        blk[o:, o:] -= tail
+                    if s_min < 0:                       # rows before the epoch start (negative lags)
+                        head = _diag_cumulative(flipped[i, s_min:], flipped[j, s_min:])
+                        if s_max < 0:
+                            head = head[:s_max, :s_max]
+                        blk[:-s_min, :-s_min] -= head
+                cov[n, i * W:(i + 1) * W, j * W:(j + 1) * W] += blk
+                if i != j:
+                    cov[n, j * W:(j + 1) * W, i * W:(i + 1) * W] += blk
+            for k in range(W):
+                xty[n, i * W + k] = (y[n] * _lagged(X[n, i], s_min + k)[None, :]).sum(-1)
+    return cov, xty, x_off, y_off
+
+
+def rf_regulariser(C: int, W: int, reg_type='ridge') -> torch.Tensor:
+    """Penalty matrix (receptivefield.py:1120-1183): identity for ridge/ridge; otherwise the sum of a second-
+    difference (free-end) operator along lags within each feature and / or along features within each lag --
+    without the identity when only the feature direction is 'laplacian'."""
+    if isinstance(reg_type, str):
+        reg_type = (reg_type,) * 2
+    if len(reg_type) != 2:
+        raise ValueError(f'reg_type must be of length two, but got {len(reg_type)}.')
+    for r in reg_type:
+        if r not in ('ridge', 'laplacian'):
+            raise ValueError(f'Unknown reg_type. Expected ridge or laplacian, but got {r}.')
+
+    def second_difference(m: int) -> torch.Tensor:
+        L = torch.zeros((m, m))
+        for r in range(m - 1):
+            L[r, r] += 1; L[r + 1, r + 1] += 1; L[r, r + 1] -= 1; L[r + 1, r] -= 1
+        return L
+
+    over_time = reg_type[0] == 'laplacian' and W > 1
+    over_feat = reg_type[1] == 'laplacian' and C > 1
+    if not over_time and not over_feat:
+        return torch.eye(C * W)
+    reg = torch.zeros((C * W, C * W))
+    if over_time:
+        reg += torch.kron(torch.eye(C), second_difference(W))
+    if over_feat:
+        reg += torch.kron(second_difference(C), torch.eye(W))
+    return reg
+
+
+def rf_solve(cov: torch.Tensor, xty: torch.Tensor, alpha, reg: torch.Tensor, C: int, W: int) -> torch.Tensor:
+    """Sum the epochs, add alpha * reg, solve; (F, C, W) coefficients (receptivefield.py:1185-1244)."""
+    G, b = cov.sum(0), xty.sum(0)
+    w = torch.linalg.solve(G + float(alpha) * reg.to(G.dtype), b)
+    return w.T.reshape(b.shape[1], C, W)
+
+
+def rf_predict(X: torch.Tensor, coef: torch.Tensor, intercept, s_min: int) -> torch.Tensor:
+    """(N, F, T) predictions of the lagged model above, plus intercept (receptivefield.py:1434-1488)."""
+    Fn, C, W = coef.shape
+    out = X.new_zeros((X.shape[0], Fn, X.shape[-1]))
+    for k in range(W):
+        out += torch.einsum('fc,nct->nft', coef[:, :, k], _lagged(X, s_min + k))
+    if isinstance(intercept, torch.Tensor):
+        out = out + intercept.reshape(1, -1, 1)
+    return out
+
+
+def rf_fit(X: torch.Tensor, y: torch.Tensor, t_min: float, t_max: float, fs: float, alpha, reg_type='ridge', reg_cv=5,
+           fit_intercept: bool = True, edge_correction: bool = True, patterns: bool = False) -> Dict[str, object]:
+    """ReceptiveField.fit (receptivefield.py:1322-1432): one solve for a float alpha; a tensor of alphas is scored
+    by k-fold cross-validation over epochs (mean Pearson correlation across the held-out epochs, averaged over
+    time, channels and folds; first maximum wins) or, for reg_cv='LOO', handed to the LOO ridge solver with the
+    summed correlation matrix as its "data" (:1213-1221)."""
+    s_min, s_max = rf_lags(t_min, t_max, fs)
+    W = s_max - s_min
+    N, C, T = X.shape
+    F = y.shape[1]
+    cov, xty, x_off, y_off = rf_corrs(X, y, s_min, s_max, fit_intercept, edge_correction)
+    out: Dict[str, object] = dict(cov=cov, s_min=s_min, s_max=s_max)
+
+    def intercept_of(coef):
+        return (y_off - x_off @ coef.sum(-1).T) if fit_intercept else 0.0
+
+    if reg_cv == 'LOO':
+        fit = ridge_loo_fit(cov.sum(0), xty.sum(0), alpha.to(X.dtype), fit_intercept=True, alpha_per_target=False)
+        coef, best_alpha = fit['coef'].reshape(F, C, W), fit['alpha']
+    else:
+        reg = rf_regulariser(C, W, reg_type)
+        if isinstance(alpha, float):
+            best_alpha = alpha
+        else:
+            folds = kfold_indices(N, reg_cv) if isinstance(reg_cv, int) else list(reg_cv)
+            means = []
+            for a in alpha:
+                per_fold = []
+                for train, test in folds:
+                    c = rf_solve(cov[train], xty[train], a, reg, C, W)
+                    y_h = rf_predict(X[test], c, intercept_of(c), s_min).float()
+                    per_fold.append(pearsonr_last(y_h.permute(2, 1, 0), y[test].permute(2, 1, 0)).mean().item())
+                means.append(torch.mean(torch.tensor(per_fold)).item())
+            out['cv_scores'] = torch.tensor(means)
+            best_alpha = alpha[torch.argmax(out['cv_scores'])]
+        coef = rf_solve(cov, xty, best_alpha, reg, C, W)
+    out.update(coef=coef, alpha=best_alpha, intercept=intercept_of(coef))
+    if patterns:
+        S_X = cov.sum(0) / float(T * N - 1)
+        if F > 1:
+            z = y.swapaxes(1, 2).reshape(-1, F)
+            z = z - z.mean(0, keepdim=True)
+            out['pattern'] = (S_X @ (coef.reshape(C * W, F) @ torch.linalg.pinv(torch.cov(z.T)))).reshape(coef.shape)
+        else:
+            out['pattern'] = (S_X @ (coef.reshape(C * W, F) / float(T * N - 1))).reshape(coef.shape)
+    return out

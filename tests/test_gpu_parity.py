@@ -503,3 +503,92 @@ def test_alpha_grid_sizes(n_alphas):
     assert float(td.estimator.alpha_) == float(ref['alpha'])
     rc = ref['flat_coef'].numpy()
     np.testing.assert_allclose(td.estimator.coef_.cpu().numpy(), rc, rtol=1e-4, atol=1e-4 * np.abs(rc).max())
+
+
+def test_b2b_golden(golden):
+    """§8(f3) back-to-back regression: decoder on the first half, scaler + second ridge on the second half
+    (tests/golden/b2b.npz, composed from the reference's RidgeCV and Scaler as b2b.py:267-306 does)."""
+    mv = _mv()
+    g = golden('b2b.npz')
+    X, y, al = T(g['X']).cuda(), T(g['y']).cuda(), T(g['alphas'])
+    for tag, per_target, norm in (('a', False, True), ('b', True, False)):
+        m = mv.estimators.B2B(alphas=al, alpha_per_target=per_target, normalise_decoder=norm)
+        with pytest.raises(ValueError):
+            m.predict(X)
+        m.fit(X, y)
+        assert torch.equal(m.decoder_.alpha_.cpu(), T(g[f'{tag}_dec_alpha'])) and torch.equal(m.encoder_.alpha_.cpu(), T(g[f'{tag}_enc_alpha']))
+        np.testing.assert_allclose(m.causal_.cpu().numpy(), g[f'{tag}_causal'], rtol=1e-3, atol=1e-5)
+        np.testing.assert_allclose(m.pattern_.cpu().numpy(), g[f'{tag}_pattern'], rtol=2e-3, atol=1e-4)
+        np.testing.assert_allclose(m.predict(X).cpu().numpy(), g[f'{tag}_pred'], rtol=1e-4, atol=3e-4)
+        assert m.causal_.shape == (4,) and m.pattern_.shape == (14, 4)
+        c = m.clone()
+        assert c.causal_ is None and c.alpha_per_target == per_target and c.normalise_decoder == norm
+    assert abs(float(m.causal_[3])) < 0.05 < float(m.causal_[:3].min())        # the target without an effect is found
+
+
+def test_penalised_solve_and_sum_slabs():
+    """mvb_penalised_solve (batched LU with partial pivoting on non-symmetric systems) and mvb_sum_slabs vs fp64 torch."""
+    from mvpy_b200 import _lib
+    g = torch.Generator().manual_seed(3)
+    for dt, tol in ((torch.float64, 1e-10), (torch.float32, 2e-4)):
+        for p, F in ((1, 1), (7, 3), (33, 2), (150, 5), (300, 64)):
+            G = torch.randn(p, p, generator=g, dtype=torch.float64)
+            G = G @ G.T + 0.3 * p * torch.randn(p, p, generator=g, dtype=torch.float64)          # not symmetric, needs pivoting
+            if p > 1:
+                G[0, 0] = 0.0
+            reg = torch.eye(p, dtype=torch.float64) + 0.1 * torch.randn(p, p, generator=g, dtype=torch.float64)
+            al = torch.tensor([0.0, 0.5, 30.0], dtype=torch.float64)
+            b = torch.randn(p, F, generator=g, dtype=torch.float64)
+            sol, info = _lib.penalised_solve(G.to(dt).cuda(), reg.to(dt).cuda(), al.to(dt).cuda(), b.to(dt).cuda())
+            assert info.tolist() == [0, 0, 0]
+            for s in range(3):
+                M = G + al[s] * reg
+                want = torch.linalg.solve(M, b)
+                resid = (M @ sol[s].cpu().double() - b).norm() / b.norm()
+                assert resid < tol * max(1.0, float(torch.linalg.cond(M)) * 1e-3), (dt, p, s, float(resid))
+                if dt == torch.float64:
+                    np.testing.assert_allclose(sol[s].cpu().numpy(), want.numpy(), rtol=1e-7, atol=1e-9)
+        sing = torch.ones(4, 4, dtype=dt).cuda()
+        _, info = _lib.penalised_solve(sing, torch.zeros(4, 4, dtype=dt).cuda(), torch.ones(1, dtype=dt).cuda(), torch.ones(4, 1, dtype=dt).cuda())
+        assert int(info[0]) == 2                                    # second column has no pivot left
+        A = torch.randn(9, 5, 11, generator=g, dtype=torch.float64).to(dt).cuda()
+        idx = torch.tensor([8, 0, 3, 3])
+        np.testing.assert_allclose(_lib.sum_slabs(A, idx).cpu().numpy(), A[idx.cuda()].sum(0).cpu().numpy(), rtol=1e-6, atol=1e-6)
+
+
+def test_receptive_field_golden(golden):
+    """§8(f1) ReceptiveField against the unmodified reference (tests/golden/rf.npz: fp64 inputs) -- per-epoch cov_ with the
+    reference's layout quirks, k-fold / LOO alpha choice (exact), coef_ / intercept_ / pattern_ / predictions; run in
+    fp64 (CUDA-core route, tight) and fp32 (tensor-core route, coef 1e-4 relative to the largest coefficient)."""
+    from tests.rf_cases import RF_CASES
+    mv, orc = _mv(), _orc()
+    g = golden('rf.npz')
+    for dt, rel in ((torch.float64, 1e-8), (torch.float32, 1e-4)):
+        for name, ((t0, t1, fs), kw) in RF_CASES.items():
+            X, y = T(g[f'{name}_X']).to(dt).cuda(), T(g[f'{name}_y']).to(dt).cuda()
+            m = mv.estimators.ReceptiveField(t0, t1, fs, **kw).fit(X, y)
+            tag = f'{name}/{dt}'
+            scale = float(np.abs(g[f'{name}_cov']).max())
+            np.testing.assert_allclose(m.cov_.cpu().numpy(), g[f'{name}_cov'], rtol=0, atol=rel * scale, err_msg=tag)
+            assert float(m.alpha_) == float(g[f'{name}_alpha']), tag
+            cmax = float(np.abs(g[f'{name}_coef']).max())
+            np.testing.assert_allclose(m.coef_.cpu().numpy(), g[f'{name}_coef'], rtol=0, atol=(20 * rel if name == 'loo' else rel) * cmax, err_msg=tag)
+            assert m.coef_.shape == g[f'{name}_coef'].shape and m.coef_.dtype == dt
+            if kw.get('fit_intercept', True):
+                np.testing.assert_allclose(m.intercept_.cpu().numpy(), g[f'{name}_intercept'], rtol=0, atol=100 * rel, err_msg=tag)
+            else:
+                assert m.intercept_ == 0.0
+            if kw.get('patterns'):
+                pmax = float(np.abs(g[f'{name}_pattern']).max())
+                np.testing.assert_allclose(m.pattern_.cpu().numpy(), g[f'{name}_pattern'], rtol=0, atol=10 * rel * pmax, err_msg=tag)
+            else:
+                assert m.pattern_ is None
+            pred = m.predict(X)
+            assert pred.dtype == torch.float32 and pred.shape == g[f'{name}_pred'].shape[:1] + (m.n_channels_,) + g[f'{name}_pred'].shape[-1:]
+            np.testing.assert_allclose(pred.cpu().numpy().reshape(g[f'{name}_pred'].shape), g[f'{name}_pred'], rtol=1e-4, atol=2e-4 * max(1.0, cmax), err_msg=tag)
+            r2 = m.score(X, y.reshape(pred.shape))
+            assert r2.shape == pred.shape[1:] and torch.isfinite(r2).all()
+    # under cross_val_score like any other estimator
+    X, y = T(g['kfold_X']).float().cuda(), T(g['kfold_y']).float().cuda()
+    _, sc = mv.crossvalidation.cross_val_score(mv.estimators.ReceptiveField(-0.04, 0.06, 100, alpha=10.0), X, y, cv=5)
+    assert sc.shape == (5, 2, 120) and torch.isfinite(sc).all()

@@ -231,3 +231,30 @@ def test_stratified_kfold_bit_exact(golden):
         list(mv.crossvalidation.StratifiedKFold(n_splits=5).split(torch.zeros(3, 2), torch.zeros(3)))
     with pytest.raises(ValueError):          # every class smaller than n_splits
         list(mv.crossvalidation.StratifiedKFold(n_splits=4).split(torch.zeros(6, 2), torch.tensor([0, 0, 0, 1, 1, 1])))
+
+
+def test_receptive_field_host_side(golden):
+    """ReceptiveField pieces that need no device: lag range, argument checks, dispatch, penalty matrices
+    (bit-equal to the reference's, tests/golden/rf.npz)."""
+    from tests.rf_cases import RF_REG_CASES
+    g = golden('rf.npz')
+    rf = mv.estimators.ReceptiveField(-0.04, 0.06, 100, alpha=[1.0])
+    assert (rf.s_min, rf.s_max) == (-4, 7) and rf.alpha == 1.0 and rf.window.tolist() == list(range(-4, 7))
+    assert rf.metric_ is mv.metrics.r2 and rf.coef_ is None
+    for i, (C, W, rt) in enumerate(RF_REG_CASES):
+        assert np.array_equal(rf._compute_reg_neighbours(C, W, rt).numpy(), g[f'reg{i}']), (C, W, rt)
+    for bad in (dict(t_min=0.1, t_max=0.0), dict(reg_type='laplacian', reg_cv='LOO'), dict(reg_cv=2.5), dict(alpha=None)):
+        kw = dict(t_min=-0.1, t_max=0.1, fs=100); kw.update(bad)
+        with pytest.raises(ValueError):
+            mv.estimators.ReceptiveField(**kw)
+    with pytest.raises(ValueError):
+        rf._compute_reg_neighbours(2, 3, 'lasso')
+    with pytest.raises(ValueError):
+        rf._compute_reg_neighbours(2, 3, ('ridge',))
+    with pytest.raises(ValueError):
+        rf.predict(torch.zeros(2, 3, 10))
+    c = mv.estimators.ReceptiveField(0.0, 0.1, 50, alpha=torch.logspace(-1, 1, 3), reg_cv=4, patterns=True).clone()
+    assert c.reg_cv == 4 and c.patterns and torch.equal(c.alpha, torch.logspace(-1, 1, 3))
+    x = torch.arange(5.0)[None]
+    sh = type(rf)._shift
+    assert sh(x, 2, 8).tolist() == [[0, 0, 0, 1, 2, 3, 4, 0]] and sh(x, -2, 4).tolist() == [[2, 3, 4, 0]] and sh(x, 9, 3).tolist() == [[0, 0, 0]]

@@ -176,3 +176,35 @@ def test_rank_and_spearman(golden):
     assert np.array_equal(orc.rank_last(T(g['xi'])).numpy(), g['rank_xi'])
     assert np.array_equal(orc.rank_last(torch.tensor([2, 0.5, 1, 1])).numpy(), g['doc'])
     np.testing.assert_allclose(orc.spearmanr_last(T(g['x']), T(g['y'])).numpy(), g['spearman'], atol=1e-6)
+
+
+def test_receptive_field_reference_cases(golden):
+    """the ReceptiveField restatement (direct lag sums) against the reference's FFT route -- per-epoch
+    correlation blocks (with the reference's asymmetric lower blocks and head correction), penalties, alpha
+    selection by k-fold / LOO, coefficients, intercepts, patterns, predictions."""
+    from tests.rf_cases import RF_CASES
+    g = golden('rf.npz')
+    for name, ((t0, t1, fs), kw) in RF_CASES.items():
+        X, y = T(g[f'{name}_X']), T(g[f'{name}_y'])
+        X3, y3 = (X[:, None], y[:, None]) if X.ndim == 2 else (X, y)
+        kw = dict(kw)
+        alpha = kw.pop('alpha')
+        if isinstance(alpha, list):
+            alpha = torch.tensor(alpha)
+        fit = orc.rf_fit(X3, y3, t0, t1, fs, alpha, **kw)
+        np.testing.assert_allclose(fit['cov'].numpy(), g[f'{name}_cov'], rtol=1e-9, atol=1e-8, err_msg=name)
+        assert float(fit['alpha']) == float(g[f'{name}_alpha']), name
+        np.testing.assert_allclose(fit['coef'].numpy(), g[f'{name}_coef'], rtol=1e-7, atol=1e-9, err_msg=name)
+        if kw.get('fit_intercept', True):
+            np.testing.assert_allclose(fit['intercept'].numpy(), g[f'{name}_intercept'], rtol=1e-7, atol=1e-9, err_msg=name)
+        else:
+            assert float(g[f'{name}_intercept']) == 0.0
+        if kw.get('patterns'):
+            np.testing.assert_allclose(fit['pattern'].numpy(), g[f'{name}_pattern'], rtol=1e-7, atol=1e-9, err_msg=name)
+        pred = orc.rf_predict(X3, fit['coef'], fit['intercept'], fit['s_min'])
+        np.testing.assert_allclose(pred.numpy(), g[f'{name}_pred'], rtol=1e-4, atol=1e-4, err_msg=name)   # reference returns fp32
+    from tests.rf_cases import RF_REG_CASES
+    for i, (C, W, rt) in enumerate(RF_REG_CASES):
+        assert np.array_equal(orc.rf_regulariser(C, W, rt).numpy(), g[f'reg{i}']), (C, W, rt)
+    with pytest.raises(ValueError):
+        orc.rf_regulariser(2, 3, 'lasso')
