@@ -215,11 +215,10 @@ class _ReceptiveField_torch(sklearn.base.BaseEstimator):
         G_all, b_all = _lib.sum_slabs(cov, everything), _lib.sum_slabs(xty, everything)
         if self.reg_cv == 'LOO':
             # The summed correlation matrix is handed to the LOO ridge solver as its data matrix (:1213-1221).  That
-            # "design" is square, so with an intercept every row is (nearly) interpolated and 1 - leverage is of order
-            # alpha / eigenvalue; the Gram-route kernels form 1 - h explicitly, which needs fp64 here (p x p, small).
-            est = _RidgeCV_torch(alphas=self.alpha, fit_intercept=True).fit(G_all.double(), b_all.double())
-            coef = est.coef_.to(Xd.dtype).reshape((self.n_channels_, self.n_features_, self.n_trf_))
-            return finish(coef, est.alpha_.to(Xd.dtype).to(out_dev))
+            # "design" is square: the ridge core switches to its fp64 kernels for it (estimators/ridgecv.py, solve_design).
+            est = _RidgeCV_torch(alphas=self.alpha, fit_intercept=True).fit(G_all, b_all)
+            coef = est.coef_.reshape((self.n_channels_, self.n_features_, self.n_trf_))
+            return finish(coef, est.alpha_.to(out_dev))
         reg = self._compute_reg_neighbours(self.n_features_, self.n_trf_, self.reg_type).to(device=Xd.device, dtype=Xd.dtype)
         if not isinstance(self.alpha, float):
             if self.alpha.device != X.device:

@@ -29,6 +29,14 @@ def solve_design(design: _lib.Design, y: torch.Tensor, alphas: torch.Tensor, fit
                  stats=None, want_loss: bool = False, keep_gram: bool = True):
     """Shared fit core: y is (N, F, T) on the device of ``design``.  Returns dict with flat coef (F, p),
     intercept (F,), alpha (0-d or (F,)), best, loss, and the centred Gram (for patterns)."""
+    if (stats is None and design.xp.dtype == torch.float32 and design.n_rows <= design.n_cols + int(fit_intercept)
+            and design.n_cols <= 2048):
+        # No more rows than unknowns: every training row is (nearly) interpolated, 1 - leverage is of order
+        # alpha / eigenvalue and fp32 cannot form it (the reference's dual route for n <= p, ridgecv.py:135-190, never
+        # does).  This regime is small by construction (the Gram is p x p with p >= n), so it runs on the fp64 kernels.
+        wide = _lib.Design(design.xp.double(), design.n_time, design.n_lag, design.trial_idx, design.feat_idx)
+        out = solve_design(wide, y.double(), alphas.double(), fit_intercept, alpha_per_target, None, want_loss, keep_gram)
+        return {k: (v.float() if isinstance(v, torch.Tensor) and v.dtype == torch.float64 else v) for k, v in out.items()}
     if stats is None:
         stats = _lib.trf_stats(design, y, fit_intercept)
     G, XtY, mu, ybar = stats

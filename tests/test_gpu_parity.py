@@ -74,6 +74,26 @@ def test_ridgecv_fp32_tall(golden):
         np.testing.assert_allclose(m.loss_.cpu().numpy(), f64['losses'].numpy(), rtol=1e-4)
 
 
+def test_ridgecv_fp32_wide(golden):
+    """fp32 inputs with no more rows than columns (the reference's dual-Gram regime, 10 x 20 in its own tests): every row
+    is nearly interpolated, so the ridge core runs its fp64 kernels; alphas exact, predictions within fp32 rounding."""
+    mv = _mv()
+    g = golden('ridgecv.npz')
+    alphas = T(g['alphas']).float()
+    seen = 0
+    for c in range(int(g['n_cases'])):
+        n, p, f, icpt, per_target = g[f'c{c}_cfg']
+        if n > p:
+            continue
+        X, y = T(g[f'c{c}_X']).float().cuda(), T(g[f'c{c}_y']).float().cuda()
+        m = mv.estimators.RidgeCV(alphas=alphas, fit_intercept=bool(icpt), alpha_per_target=bool(per_target)).fit(X, y)
+        assert m.coef_.dtype == torch.float32 and m.alpha_.dtype == torch.float32
+        np.testing.assert_array_equal(m.alpha_.cpu().numpy().reshape(-1), g[f'c{c}_alpha'].reshape(-1).astype(np.float32), err_msg=f'case {c}')
+        np.testing.assert_allclose(m.predict(X).cpu().numpy(), g[f'c{c}_pred'], rtol=1e-4, atol=1e-4, err_msg=f'case {c}')
+        seen += 1
+    assert seen >= 2
+
+
 def test_ridgecv_errors():
     mv = _mv()
     X, y = torch.randn(10, 3, device='cuda'), torch.randn(9, 2, device='cuda')
