@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- TRF ridge fits/s (folds x alphas x sets) of the cross-validated ridge hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg1] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg1|cfg3|cfg4|cfg5] [--impl ours|reference]
 
 One step = one ``cross_val_score(make_pipeline(Scaler, TimeDelayed), X, y, cv=5)`` with 20 alphas
 (= 100 fits) on make_meeg_continuous-style synthetic data.  Default workload: BASELINE.json configs[1]
@@ -43,6 +43,13 @@ WORKLOADS = {
                                                     '5-fold x 20 alphas (BASELINE configs[0])'),
     # one Shapley permutation of BASELINE configs[3] per rank and step: 8 groups of 8 features -> 8 nested predictor sets
     # (8 ... 64 features, p = 1608 ... 12864) x 5 folds x 20 alphas = 800 fits; permutations are the sharding unit
+    # BASELINE configs[2]: hierarchical_score over the 8 unique predictor sets of 4 feature groups (16 ... 64 features,
+    # p = 3216 ... 12864) x 5 folds x 20 alphas = 800 fits per step
+    'cfg3': dict(n_features=64, n_channels=306, label='hierarchical_score over 8 predictor sets (16..64 of 64 features) x 5 folds x 20 alphas, '
+                                                      'cfg2 data (BASELINE configs[2])'),
+    # BASELINE configs[4]: per-timepoint decoding, one independent RidgeDecoder per time slice
+    'cfg5': dict(n_features=306, n_channels=3, label='Sliding RidgeDecoder per-timepoint decoding: 2000 trials x 306 channels x 500 timepoints -> 3 targets, '
+                                                     '20 alphas (per target) x 5 folds (BASELINE configs[4]; linear-Gaussian stand-in data, SURVEY 8d)'),
     'cfg4': dict(n_features=64, n_channels=306, label='shapley_score unit: 1 permutation over 8 groups of 8 features (8 nested sets) '
                                                       'x 5 folds x 20 alphas, cfg2 data (BASELINE configs[3], one permutation per GPU per step)'),
 }
@@ -52,6 +59,12 @@ def make_data(workload: str):
     from mvpy_b200.dataset import make_meeg_continuous
     cfg = WORKLOADS[workload]
     torch.manual_seed(0)
+    if workload == 'cfg5':      # make_meeg_continuous at this size stacks ~91 GB of intermediates: documented stand-in
+        N, C, T, F = 2000, 306, 500, 3
+        X = torch.randn(N, C, T)
+        B = torch.randn(C, F) * 0.05
+        y = torch.einsum('nct,cf->nft', X, B) * torch.hann_window(T) + torch.randn(N, F, T)
+        return X.contiguous(), y.contiguous()
     X, y = make_meeg_continuous(fs=200, n_features=cfg['n_features'], n_channels=cfg['n_channels'])
     return X.contiguous(), y.contiguous()
 
@@ -105,7 +118,29 @@ def cpu_reference_sample(X, y, alphas, n_feat_sample: int, threads: int):
     return time.perf_counter() - t0
 
 
+def cpu_baseline_decoding(X, y, alphas):
+    """cfg5: the oracle's per-slice RidgeDecoder (reference route: SVD LOO ridge + pattern) on one training fold of a
+    sample of the 500 time slices."""
+    from oracle import mvpy_oracle as orc
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n_tr = X.shape[0] - X.shape[0] // N_FOLDS
+    n_slices = 25
+    idx = torch.linspace(0, X.shape[2] - 1, n_slices).long()
+    Xs, ys = X[:n_tr][..., idx].contiguous(), y[:n_tr][..., idx].contiguous()
+    t0 = time.perf_counter()
+    orc.sliding_decoder_fit(Xs, ys, alphas)
+    sec = time.perf_counter() - t0
+    value = n_slices * N_ALPHAS / sec
+    sample = (f'{n_slices} of {X.shape[2]} time slices, 1 of {N_FOLDS} training folds (n={n_tr} trials x p={X.shape[1]} channels, '
+              f'{y.shape[1]} targets, {N_ALPHAS} alphas) took {sec:.2f} s on {threads} threads; fits/s = slices x alphas / s '
+              f'(every slice-fold costs the same, no extrapolation law needed)')
+    return dict(value=value, unit='fits/s', cores=threads, kind='port', sample=sample), sec
+
+
 def cpu_baseline(X, y, alphas, workload: str):
+    if workload == 'cfg5':
+        return cpu_baseline_decoding(X, y, alphas)
     threads = os.cpu_count() or 1
     C = X.shape[1]
     n_s = C if workload == 'cfg1' else 16         # a quarter of the predictors: ~10-20 s of CPU work per sample
@@ -120,6 +155,9 @@ def cpu_baseline(X, y, alphas, workload: str):
     value = N_ALPHAS / per_fold_full
     if workload == 'cfg4':      # 8 nested sets of k/8 of the features each, same cost law per set
         nested = sum((k / 8.0) ** 2 for k in range(1, 9))
+        value = 8 * N_ALPHAS / (per_fold_full * nested)
+    if workload == 'cfg3':      # 8 predictor sets of 16, 32 x3, 48 x3 and 64 of the 64 features, same cost law per set
+        nested = sum((k / 4.0) ** 2 for k in (1, 2, 2, 2, 3, 3, 3, 4))
         value = 8 * N_ALPHAS / (per_fold_full * nested)
     sample = (f'1 of {N_FOLDS} folds, {n_s} of {C} stimulus features (p={n_s * W} of {C * W} columns, n={n_rows} rows, '
               f'{y.shape[1]} channels, {N_ALPHAS} alphas) took {sec:.2f} s on {threads} threads = {N_ALPHAS / sec:.3f} fits/s; '
@@ -146,7 +184,9 @@ def main():
     config = dict(workload=cfg['label'], trials=120, features=cfg['n_features'], channels=cfg['n_channels'], timepoints=400,
                   lags=201, alphas=N_ALPHAS, folds=N_FOLDS, units_per_step_per_gpu=1, parallelism=f'units-sharded x{args.gpus}',
                   l2='inputs + per-fold operands (>=1.3 GB at cfg2) exceed the 126 MB L2; no explicit flush')
-    fits_per_unit = N_ALPHAS * N_FOLDS * (8 if args.workload == 'cfg4' else 1)
+    if args.workload == 'cfg5':
+        config.update(trials=2000, timepoints=500, lags=1, l2='inputs (1.2 GB) exceed the 126 MB L2; no explicit flush')
+    fits_per_unit = N_ALPHAS * N_FOLDS * {'cfg4': 8, 'cfg3': 8, 'cfg5': 500}.get(args.workload, 1)
 
     if args.impl == 'reference':
         if rank != 0:
@@ -192,6 +232,10 @@ def main():
     from mvpy_b200 import _dist
 
     groups = torch.eye(8).repeat_interleave(8, 1)
+    groups3 = torch.zeros(4, 64)
+    groups3[:, :16] = 1                     # the baseline block is in every row; rows 1..3 add one block each
+    for r in range(1, 4):
+        groups3[r, 16 * r:16 * (r + 1)] = 1
 
     def run_unit(Xu, yu):
         """One sharding unit on this rank: a whole cross-validation (cfg1/cfg2) or a whole Shapley permutation (cfg4)."""
@@ -201,10 +245,17 @@ def main():
                 sh = mv.model_selection.Shapley(mv.crossvalidation.Validator(pipe, cv=N_FOLDS), n_permutations=1,
                                                 keep_validators=False).fit(Xu, yu, groups=groups.to(Xu.device))
                 return sh, sh.score_
+            if args.workload == 'cfg3':
+                return mv.model_selection.hierarchical_score(pipe, Xu, yu, groups=groups3.to(Xu.device), cv=N_FOLDS)
+            if args.workload == 'cfg5':
+                dec = mv.estimators.Sliding(mv.estimators.RidgeDecoder(alphas=alphas), dims=-1)
+                return mv.crossvalidation.cross_val_score(dec, Xu, yu, cv=N_FOLDS, metric=(mv.metrics.r2, mv.metrics.pearsonr))
             return mv.crossvalidation.cross_val_score(pipe, Xu, yu, cv=N_FOLDS)
 
     def step_device():
         _, sc = run_unit(Xd, yd)
+        if isinstance(sc, dict):
+            sc = torch.stack([sc[k] for k in sorted(sc)])
         if world > 1:
             out = torch.empty((world,) + tuple(sc.shape), dtype=sc.dtype, device=dev)
             dist.all_gather_into_tensor(out, sc.contiguous())
@@ -213,6 +264,8 @@ def main():
 
     def step_host():
         val, sc = run_unit(Xh, yh)                                                   # h2d inside, results back on host
+        if isinstance(sc, dict):
+            sc = torch.stack([sc[k] for k in sorted(sc)])
         if world > 1:                                                                # the one collective: gather of score shards
             out = torch.empty((world,) + tuple(sc.shape), dtype=sc.dtype, device=dev)
             dist.all_gather_into_tensor(out, sc.to(dev).contiguous())
@@ -278,7 +331,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     d2h = sc_h.numel() * sc_h.element_size()
-    for m in (val.model_ if hasattr(val, 'model_') else []):      # fitted pipelines come back to the host with the scores
+    for m in (val.model_ if hasattr(val, 'model_') and args.workload in ('cfg1', 'cfg2') else []):      # fitted pipelines come back with the scores
         td = m[-1]
         d2h += td.estimator.coef_.numel() * 4 + td.estimator.intercept_.numel() * 4 + m[0].mean_.numel() * 8
     e2e = dict(value=world * fits_per_unit / e2e_s, unit='fits/s', h2d_bytes_per_step=int(Xh.numel() * 4 + yh.numel() * 4),

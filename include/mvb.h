@@ -46,6 +46,10 @@ int64_t mvb_launch_count(void);
  * Used by bench.py for the roofline line; mvb_profile_disable() turns the hook off again.            */
 void mvb_profile_reset(void);
 void mvb_profile_disable(void);
+/* CUDA-graph support (mvpy_b200/_graphs.py): the hook must be off while a call sequence is being stream-captured
+ * (returns the previous state), and replays of a captured sequence report their kernel launches here.       */
+int mvb_profile_set(int on);
+void mvb_launch_count_add(int64_t n);
 int mvb_profile_read(double* ms_timed, double* flops_timed, double* flops_all, int64_t* n_timed, int64_t* n_all,
                      int max_classes);
 const char* mvb_profile_name(int cls);

@@ -41,6 +41,8 @@ _SIGNATURES = {
     'mvb_launch_count': (c_int64, []),
     'mvb_profile_reset': (None, []),
     'mvb_profile_disable': (None, []),
+    'mvb_profile_set': (c_int, [c_int]),
+    'mvb_launch_count_add': (None, [c_int64]),
     'mvb_profile_read': (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double),
                                  POINTER(c_int64), POINTER(c_int64), c_int]),
     'mvb_profile_name': (c_char_p, [c_int]),
@@ -331,6 +333,18 @@ def penalised_solve(G: torch.Tensor, reg: torch.Tensor, alphas: torch.Tensor, rh
     check(load().mvb_penalised_solve(_ptr(G), _ptr(reg), _ptr(alphas), S, _ptr(rhs), p, F, dtype_code(G), _ptr(mats), _ptr(sol),
                                      _ptr(info), _stream(G)), 'mvb_penalised_solve')
     return sol, info
+
+
+def pinv_symmetric(S: torch.Tensor) -> torch.Tensor:
+    """Pseudo-inverse of a small symmetric positive semi-definite matrix (the (f x f) target covariance of the Haufe
+    patterns) from the library's Jacobi eigensolver; eigenvalues below f * eps * max are dropped like
+    ``torch.linalg.pinv`` does with singular values.  Stream-ordered (no host synchronisation), so it can be captured."""
+    f = S.shape[0]
+    Vt, lam = eigh(S.clone()[None].contiguous())
+    Vt, lam = Vt[0], lam[0]
+    keep = lam > lam.max() * (f * torch.finfo(S.dtype).eps)
+    inv = torch.where(keep, 1.0 / torch.where(keep, lam, torch.ones_like(lam)), torch.zeros_like(lam))
+    return (Vt * inv[:, None]).T @ Vt
 
 
 def eigh(A: torch.Tensor):

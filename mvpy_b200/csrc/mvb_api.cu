@@ -545,8 +545,14 @@ int ridge_solve_band(const mvb_design* d, const float* y, int F, float* G, const
       attr_set = true;
     }
     cudaStream_t side = side_stream();
-    MVB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    MVB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    // one pair of events per host thread, reused: a wait binds to the record that precedes it in host order, so reuse
+    // across calls and streams is safe, and nothing is created or destroyed while a caller is stream-capturing
+    static thread_local cudaEvent_t tl_fork = nullptr, tl_join = nullptr;
+    if (!tl_fork) {
+      MVB_CUDA(cudaEventCreateWithFlags(&tl_fork, cudaEventDisableTiming));
+      MVB_CUDA(cudaEventCreateWithFlags(&tl_join, cudaEventDisableTiming));
+    }
+    ev_fork = tl_fork; ev_join = tl_join;
     MVB_CUDA(cudaEventRecord(ev_fork, st));
     MVB_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
     mvb::bl::block_chol_kernel<<<A, 1024, mvb::bl::CHOL_SMEM, side>>>(w.Tdiag, w.Tsub, (int)nb, alphas, w.Minv, w.Nmat, w.Pb, w.MN);
@@ -563,8 +569,6 @@ int ridge_solve_band(const mvb_design* d, const float* y, int F, float* G, const
   mvb::matvec_rows_kernel<float><<<cdiv(P * 32, 256), 256, 0, st>>>(w.Qt, P, P, w.mu64, w.cz);    MVB_LAUNCHED();
   sub_cols_blocked_kernel<<<grid_for(n * P), 256, 0, st>>>(w.Z, n, nb, w.cz);                        MVB_LAUNCHED();
   MVB_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
-  MVB_CUDA(cudaEventDestroy(ev_fork));
-  MVB_CUDA(cudaEventDestroy(ev_join));
   // 4. forward substitution over the blocks for every (alpha, row):  u_j = [Minv_j | -N_j] [z_j ; u_{j-1}],  h = sum_j |u_j|^2.
   //    Default: one kernel in which every (row tile, alpha) CTA walks its whole chain with u resident on the SM
   //    (sweep_chain.cuh): in tensor memory as the MMA's A operand (MVB_SWEEP_CHAIN=2, default) or in shared memory (=1).
@@ -796,6 +800,8 @@ void mvb_profile_reset(void) {
   g_prof.on = true;
 }
 void mvb_profile_disable(void) { g_prof.on = false; }
+int mvb_profile_set(int on) { const int was = g_prof.on ? 1 : 0; g_prof.on = on != 0; return was; }
+void mvb_launch_count_add(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int mvb_profile_read(double* ms_timed, double* flops_timed, double* flops_all, int64_t* n_timed, int64_t* n_all, int max_classes) {
   std::lock_guard<std::mutex> lk(g_prof.mu);
   const int nc = max_classes < PC_COUNT ? max_classes : PC_COUNT;

@@ -53,7 +53,7 @@ class _RidgeDecoder_torch(sklearn.base.BaseEstimator):
         coef = _lib.to_device(self.coef_).to(Sx.dtype)
         if y.shape[1] > 1:
             yd = _lib.to_device(y).to(Sx.dtype)
-            Py = torch.linalg.pinv(_lib.covariance(yd))        # pseudo-inverse of the tiny (f x f) target covariance
+            Py = _lib.pinv_symmetric(_lib.covariance(yd))      # pseudo-inverse of the tiny (f x f) target covariance
             self.pattern_ = _lib.matmul_nt(_lib.matmul_nt(Sx, coef), Py.T.contiguous()).to(out_dev)
         else:
             self.pattern_ = (_lib.matmul_nt(Sx, coef) * (1.0 / float(n - 1))).to(out_dev)

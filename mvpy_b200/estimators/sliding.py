@@ -12,7 +12,7 @@ import numpy as np
 import sklearn.base
 import torch
 
-from .. import metrics
+from .. import _graphs, metrics
 
 
 class _Sliding_torch(sklearn.base.BaseEstimator):
@@ -51,7 +51,10 @@ class _Sliding_torch(sklearn.base.BaseEstimator):
             Xm, ym, eff = self._moved(X, y)
             proto = _Sliding_torch(estimator=self.estimator, dims=eff[1:], n_jobs=None, top=False) if len(self.dims) > 1 \
                 else self.estimator.clone()
-            self.estimators_ = [proto.clone().fit(Xm[..., i], ym[..., j], *args) for i, j in self._pairs(Xm, ym)]
+            pairs = self._pairs(Xm, ym)
+            # many small identical fits: captured once as a CUDA graph and replayed per slice on concurrent streams
+            fitted = _graphs.fit_slices(proto, Xm, ym, pairs) if (len(self.dims) == 1 and not args) else None
+            self.estimators_ = fitted if fitted is not None else [proto.clone().fit(Xm[..., i], ym[..., j], *args) for i, j in pairs]
         else:
             self.estimators_ = []
         return self

@@ -612,3 +612,37 @@ def test_receptive_field_golden(golden):
     X, y = T(g['kfold_X']).float().cuda(), T(g['kfold_y']).float().cuda()
     _, sc = mv.crossvalidation.cross_val_score(mv.estimators.ReceptiveField(-0.04, 0.06, 100, alpha=10.0), X, y, cv=5)
     assert sc.shape == (5, 2, 120) and torch.isfinite(sc).all()
+
+
+@pytest.mark.parametrize('shape', [(200, 40, 3, 24), (700, 306, 2, 16)])
+def test_sliding_graph_executor_matches_eager(shape, monkeypatch):
+    """Sliding over a ridge estimator replays one captured CUDA graph per slice on concurrent streams
+    (mvpy_b200/_graphs.py); same kernels in the same order, so every fitted attribute must equal the eager loop's
+    (small p: Jacobi route; p = 306: band route with its forked side-stream work inside the capture)."""
+    from mvpy_b200 import _graphs, _lib
+    mv = _mv()
+    n, p, f, t = shape
+    g = torch.Generator().manual_seed(p)
+    X = torch.randn(n, p, t, generator=g).cuda()
+    y = (torch.einsum('npt,pf->nft', X.cpu(), torch.randn(p, f, generator=g) * 0.1) + torch.randn(n, f, t, generator=g)).cuda()
+    al = torch.logspace(-3, 3, 9)
+    for make in (lambda: mv.estimators.RidgeDecoder(alphas=al), lambda: mv.estimators.RidgeCV(alphas=al, alpha_per_target=False)):
+        monkeypatch.setenv('MVB_SLIDING_GRAPHS', '0')
+        eager = mv.estimators.Sliding(make(), dims=-1).fit(X, y)
+        monkeypatch.setenv('MVB_SLIDING_GRAPHS', '1')
+        monkeypatch.setenv('MVB_SLIDING_LANES', '4')
+        _graphs.clear_cache()
+        n0 = _lib.launch_count()
+        graphed = mv.estimators.Sliding(make(), dims=-1).fit(X, y)
+        assert not _graphs._broken and len(_graphs._CACHE) == 1                      # the graph path really ran
+        assert _lib.launch_count() - n0 > 20 * t                                     # replays are counted
+        again = mv.estimators.Sliding(make(), dims=-1).fit(X.flip(0), y.flip(0))     # cached lanes, new data
+        assert len(_graphs._CACHE) == 1
+        for attr in ('coef_', 'alpha_', 'intercept_') + (('pattern_',) if hasattr(eager.estimators_[0], 'pattern_') else ()):
+            a, b = eager.collect(attr), graphed.collect(attr)
+            assert a.shape == b.shape
+            np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=1e-6, atol=1e-7, err_msg=attr)
+        np.testing.assert_allclose(graphed.predict(X).cpu().numpy(), eager.predict(X).cpu().numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(again.collect('coef_').cpu().numpy(), eager.collect('coef_').cpu().numpy(), rtol=2e-3, atol=2e-5)
+        assert torch.equal(again.collect('alpha_'), eager.collect('alpha_'))
+    _graphs.clear_cache()
