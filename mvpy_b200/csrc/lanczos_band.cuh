@@ -397,7 +397,8 @@ inline bool gemm(Ctx& cx, const GatherOperand& A, const GatherOperand& B, int M,
   ++cx.launches;
   if (cx.err != cudaSuccess) return false;
   if (via_parts) {
-    reduce_parts_kernel<<<148 * 4, 256, 0, cx.st>>>(cx.f(cx.pl.off_part), splits, (int64_t)M * N, M, N, C, ldc, skip, subtract ? 1 : 0);
+    const int rgrid = (int)std::min<int64_t>(148 * 4, ((int64_t)M * N + 255) / 256);      // small outputs: a few CTAs, leave the SMs to concurrent work
+    reduce_parts_kernel<<<rgrid, 256, 0, cx.st>>>(cx.f(cx.pl.off_part), splits, (int64_t)M * N, M, N, C, ldc, skip, subtract ? 1 : 0);
     ++cx.launches;
   }
   return true;
@@ -484,9 +485,9 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
   LB_CK(cudaMemsetAsync(ctl, 0, sizeof(bj::Ctl), st));
   tables_kernel<<<64, 256, 0, st>>>(P, rowP, row128, iota); ++cx.launches;
   diag_mean_kernel<<<1, 256, 0, st>>>(G, p, cx.f(pl.off_lam)); ++cx.launches;
-  pad_gram_kernel<<<148 * 8, 256, 0, st>>>(G, p, P, Gp, cx.f(pl.off_lam)); ++cx.launches;
+  pad_gram_kernel<<<(int)std::min<int64_t>(148 * 8, ((int64_t)P * P + 255) / 256), 256, 0, st>>>(G, p, P, Gp, cx.f(pl.off_lam)); ++cx.launches;
   // Q_0: orthonormalised pseudo-random block
-  random_block_kernel<<<148 * 2, 256, 0, st>>>(Wt, (int64_t)NB * P, 0x9e3779b9u); ++cx.launches;
+  random_block_kernel<<<(int)std::min<int64_t>(148 * 2, ((int64_t)NB * P + 255) / 256), 256, 0, st>>>(Wt, (int64_t)NB * P, 0x9e3779b9u); ++cx.launches;
   LB_OK(svqb(cx, Wt, Qt));
   LB_OK(ns_polish(cx, Qt, Wt));
   LB_CK(cudaMemcpyAsync(Qt, Wt, (size_t)NB * P * 4, cudaMemcpyDeviceToDevice, st));
@@ -525,7 +526,7 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
       latch_kernel<<<1, 32, 0, st>>>(rs, &ctl->sweeps); ++cx.launches;
       LB_OK(reorth(cx, Qn, Qt, nq, rs));
       LB_OK(ns_polish(cx, Qn, Wt, rs));          // its ns_matrix_kernel rewrites ctl->sweeps for the next round
-      copy_kernel<<<148 * 2, 256, 0, st>>>(Qn, Wt, (int64_t)NB * P, rs); ++cx.launches;
+      copy_kernel<<<(int)std::min<int64_t>(148 * 2, ((int64_t)NB * P / 4 + 255) / 256), 256, 0, st>>>(Qn, Wt, (int64_t)NB * P, rs); ++cx.launches;
     }
   }
   LB_CK(cudaGetLastError());
