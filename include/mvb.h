@@ -173,6 +173,13 @@ int mvb_sum_slabs(const void* A, int64_t slab_elems, const int32_t* idx, int n_i
 int mvb_penalised_solve(const void* G, const void* reg, const void* alphas, int n_alphas, const void* rhs, int p, int n_rhs,
                         int dtype, void* mats, void* sol, int* info, void* stream);
 
+/* ---- classification metrics (widening): same [R][K] layout as mvb_score -------------------------------
+ * mvb_accuracy replaces math.accuracy (math/accuracy.py:13-33): fraction of equal entries along R per cell.
+ * mvb_roc_auc replaces the rank formula of math.roc_auc (math/roc_auc.py:139-152): positive != 0 marks the positive class,
+ * ties in score count one half, NaN where a cell has only one class.                                                   */
+int mvb_accuracy(const void* y, const void* yhat, int64_t R, int64_t K, int dtype, void* out, void* stream);
+int mvb_roc_auc(const void* positive, const void* score, int64_t R, int64_t K, int dtype, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,8 @@ _SIGNATURES = {
     'mvb_trf_predict_workspace_bytes': (c_size_t, [POINTER(mvb_design), c_int]),
     'mvb_trf_predict': (c_int, [POINTER(mvb_design), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'mvb_rank': (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    'mvb_accuracy': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    'mvb_roc_auc': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     'mvb_rf_assemble': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'mvb_sum_slabs': (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'mvb_penalised_solve': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -297,6 +299,22 @@ def score(y2: torch.Tensor, yh2: torch.Tensor, yb: Optional[torch.Tensor], want_
     pr = torch.empty(K, dtype=y2.dtype, device=y2.device) if want_pearson else None
     check(load().mvb_score(_ptr(y2), _ptr(yh2), _ptr(yb), R, K, dtype_code(y2), _ptr(r2), _ptr(pr), _stream(y2)), 'mvb_score')
     return r2, pr
+
+
+def accuracy_rows(y2: torch.Tensor, yh2: torch.Tensor) -> torch.Tensor:
+    """y2, yh2: (R, K) contiguous, same dtype -> fraction of equal entries along R, (K,)."""
+    R, K = y2.shape
+    out = torch.empty(K, dtype=y2.dtype, device=y2.device)
+    check(load().mvb_accuracy(_ptr(y2), _ptr(yh2), R, K, dtype_code(y2), _ptr(out), _stream(y2)), 'mvb_accuracy')
+    return out
+
+
+def roc_auc_rows(pos2: torch.Tensor, score2: torch.Tensor) -> torch.Tensor:
+    """pos2 (0/1), score2: (R, K) contiguous, same dtype -> area under the ROC curve along R, (K,)."""
+    R, K = pos2.shape
+    out = torch.empty(K, dtype=pos2.dtype, device=pos2.device)
+    check(load().mvb_roc_auc(_ptr(pos2), _ptr(score2), R, K, dtype_code(pos2), _ptr(out), _stream(pos2)), 'mvb_roc_auc')
+    return out
 
 
 def rank_rows(x2: torch.Tensor) -> torch.Tensor:

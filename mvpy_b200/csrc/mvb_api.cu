@@ -1058,4 +1058,25 @@ int mvb_penalised_solve(const void* G, const void* reg, const void* alphas, int 
   return MVB_OK;
 }
 
+// ---- classification metrics ------------------------------------------------------------------------
+int mvb_accuracy(const void* y, const void* yhat, int64_t R, int64_t K, int dtype, void* out, void* stream) {
+  if (!y || !yhat || !out || R < 1 || K < 1) return fail(MVB_E_ARG, "accuracy: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MVB_F32) mvb::accuracy_kernel<float><<<cdiv(K, 128), 128, 0, st>>>((const float*)y, (const float*)yhat, R, K, (float*)out);
+  else if (dtype == MVB_F64) mvb::accuracy_kernel<double><<<cdiv(K, 128), 128, 0, st>>>((const double*)y, (const double*)yhat, R, K, (double*)out);
+  else return fail(MVB_E_UNSUPPORTED, "accuracy: dtype %d", dtype);
+  MVB_LAUNCHED();
+  return MVB_OK;
+}
+
+int mvb_roc_auc(const void* positive, const void* score, int64_t R, int64_t K, int dtype, void* out, void* stream) {
+  if (!positive || !score || !out || R < 1 || K < 1) return fail(MVB_E_ARG, "roc_auc: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MVB_F32) mvb::auc_kernel<float><<<cdiv(K, 128), 128, 0, st>>>((const float*)positive, (const float*)score, R, K, (float*)out);
+  else if (dtype == MVB_F64) mvb::auc_kernel<double><<<cdiv(K, 128), 128, 0, st>>>((const double*)positive, (const double*)score, R, K, (double*)out);
+  else return fail(MVB_E_UNSUPPORTED, "roc_auc: dtype %d", dtype);
+  MVB_LAUNCHED();
+  return MVB_OK;
+}
+
 }  // extern "C"

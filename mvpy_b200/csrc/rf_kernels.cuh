@@ -127,4 +127,40 @@ __global__ void __launch_bounds__(LU_THREADS) lu_solve_kernel(T* __restrict__ A_
 }
 
 }  // namespace rf
+
+// ---- classification metrics, same [R][K] layout as score_kernel: reduced samples r are the slow axis ----
+// acc[k] = mean_r [ y[r][k] == yh[r][k] ]                                   (math/accuracy.py:13-33)
+template <typename T>
+__global__ void accuracy_kernel(const T* __restrict__ y, const T* __restrict__ yh, int64_t R, int64_t K, T* __restrict__ acc) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  int64_t hit = 0;
+  for (int64_t r = 0; r < R; ++r) hit += y[r * K + k] == yh[r * K + k];
+  acc[k] = (T)((double)hit / (double)R);
+}
+
+// auc[k] = (sum of the average ranks of the positives - P (P + 1) / 2) / (P N)   (math/roc_auc.py:139-152), written as the
+// pair count  sum_{i pos} sum_{j neg} [s_i > s_j] + [s_i == s_j] / 2,  which is the same number; NaN without both classes.
+template <typename T>
+__global__ void auc_kernel(const T* __restrict__ pos, const T* __restrict__ score, int64_t R, int64_t K, T* __restrict__ auc) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  double wins = 0.0;
+  int64_t P = 0;
+  for (int64_t i = 0; i < R; ++i) {
+    if (pos[i * K + k] == (T)0) continue;
+    ++P;
+    const T si = score[i * K + k];
+    int64_t gt = 0, eq = 0;
+    for (int64_t j = 0; j < R; ++j) {
+      if (pos[j * K + k] != (T)0) continue;
+      const T sj = score[j * K + k];
+      gt += si > sj; eq += si == sj;
+    }
+    wins += (double)gt + 0.5 * (double)eq;
+  }
+  const int64_t N = R - P;
+  auc[k] = (P == 0 || N == 0) ? (T)NAN : (T)(wins / ((double)P * (double)N));
+}
+
 }  // namespace mvb

@@ -1,3 +1,4 @@
 from .scaler import Scaler
+from .labelbinariser import LabelBinariser
 
-__all__ = ['Scaler']
+__all__ = ['Scaler', 'LabelBinariser']

@@ -22,6 +22,8 @@ Fixtures (all produced through the reference's public classes/functions):
   b2b.npz          back-to-back regression composed from _RidgeCV_torch + _Scaler_torch as b2b.py:267-306 does.
   rf.npz           ReceptiveField (needs MVPY_COMPILE_TORCH=0): single alpha, k-fold and LOO alpha selection, laplacian
                    penalties, patterns, no edge correction / intercept, causal-only and anticausal-only lag ranges.
+  clf.npz          LabelBinariser, math.accuracy / roc_auc, the Roc_auc metric (reference), RidgeClassifier OvR / OvO composed
+                   from the reference's binariser and _RidgeCV_torch.
   encoder.npz      RidgeEncoder 2-D and 3-D (expanded design).
   cfg1_summary.npz config 1 (README flow, fs=200): per-fold alphas, mean scores, strided score samples.
 """
@@ -316,6 +318,77 @@ def gen_b2b():
     save('b2b.npz', **out)
 
 
+def gen_clf():
+    """Classification pieces.  LabelBinariser, math.accuracy, math.roc_auc and the Roc_auc metric run through the
+    reference; RidgeClassifier (cannot be constructed at this commit: `normalise` keyword) is composed from the
+    reference's binariser + _RidgeCV_torch exactly as ridgeclassifier.py:356-470 and classifier.py:731-870 do."""
+    from mvpy.preprocessing.labelbinariser import _LabelBinariser_torch
+    g = torch.Generator().manual_seed(51)
+    N, C = 150, 10
+    X = torch.randn(N, C, generator=g)
+    W = torch.randn(C, 3, generator=g)
+    y0 = torch.argmax(X @ W + 0.8 * torch.randn(N, 3, generator=g), dim=1).float()              # three classes 0, 1, 2
+    y1 = torch.where(X[:, 0] + 0.7 * torch.randn(N, generator=g) > 0, 9.0, 5.0)                  # two classes 5, 9
+    y = torch.stack([y0, y1], dim=1)
+    alphas = torch.logspace(-2, 3, 6)
+    out = dict(X=X, y=y, alphas=alphas)
+    lb = _LabelBinariser_torch(neg_label=-1.0, pos_label=1.0)
+    L = lb.fit_transform(y)
+    out['L'], out['L01'] = L, ref.preprocessing.LabelBinariser().fit_transform(y)
+    out['L_inv'] = lb.inverse_transform(L)
+    m = _RidgeCV_torch(alphas=alphas, fit_intercept=True, alpha_per_target=False).fit(X, L)
+    df = m.predict(X)
+    onehot = torch.zeros_like(df)
+    for s, e in ((0, 3), (3, 5)):
+        onehot[torch.arange(N), s + torch.argmax(df[:, s:e], dim=1)] = 1.0
+    pred = lb.inverse_transform(onehot)
+    proba = 1 / (1 + torch.exp(-df))
+    for s, e in ((0, 3), (3, 5)):
+        proba[:, s:e] = proba[:, s:e] / proba[:, s:e].sum(-1, keepdim=True)
+    Xc, Lc = X - X.mean(0, keepdim=True), L - L.mean(0, keepdim=True)
+    out.update(ovr_alpha=m.alpha_, ovr_coef=m.coef_, ovr_intercept=m.intercept_, ovr_df=df, ovr_pred=pred, ovr_proba=proba,
+               ovr_pattern=torch.cov(Xc.T).mm(m.coef_.T).mm(torch.linalg.pinv(torch.cov(Lc.T))))
+    out['ovr_accuracy'] = ref.math.accuracy(y.T, pred.T)
+    out['ovr_roc_auc'] = ref.metrics.roc_auc(y.T, df.T)
+    # one-versus-one on both label features: pairwise fits on the two classes' samples, majority vote
+    votes_all, ovo_coef = [], []
+    cols = []
+    for i, labels in enumerate((torch.tensor([0.0, 1.0, 2.0]), torch.tensor([5.0, 9.0]))):
+        votes = []
+        for j in range(len(labels)):
+            for k in range(len(labels)):
+                if j <= k:
+                    continue
+                sel = (y[:, i] == labels[j]) | (y[:, i] == labels[k])
+                lb2 = _LabelBinariser_torch(neg_label=-1.0, pos_label=1.0)
+                L2 = lb2.fit_transform(y[sel, i][:, None])
+                m2 = _RidgeCV_torch(alphas=alphas, fit_intercept=True, alpha_per_target=False).fit(X[sel], L2)
+                d2 = m2.predict(X)
+                oh = torch.zeros_like(d2)
+                oh[torch.arange(N), torch.argmax(d2, dim=1)] = 1.0
+                votes.append(lb2.inverse_transform(oh).squeeze())
+                ovo_coef.append(m2.coef_)
+        votes = torch.stack(votes)
+        counts = torch.stack([(votes == l).float().sum(0) for l in labels], dim=1)
+        cols.append(labels[torch.argmax(counts, dim=1)])
+    out['ovo_pred'], out['ovo_coef'] = torch.stack(cols).T, torch.stack(ovo_coef)
+    # metric functions on their own: ties, multi-class one-versus-rest, a time axis, undefined cells
+    s = torch.randn(4, 3, 60, generator=g)
+    s[0, 0, :10] = s[0, 0, 10:20]                                                 # tied scores
+    t2 = (torch.randn(4, 3, 60, generator=g) + 0.8 * s > 0).float() * 2 - 1
+    t2[1, 1] = 1.0                                                                # one class only -> nan (kept by unique over the whole tensor)
+    out.update(auc_s=s, auc_t2=t2, auc_bin=ref.math.roc_auc(t2, s))
+    t3 = torch.randint(0, 3, (5, 80), generator=g).float()
+    s3 = torch.randn(5, 3, 80, generator=g) + torch.nn.functional.one_hot(t3.long(), 3).float().swapaxes(-1, -2)
+    out.update(auc_t3=t3, auc_s3=s3, auc_multi=ref.math.roc_auc(t3, s3))
+    a, b = torch.randint(0, 3, (6, 7, 40), generator=g).float(), torch.randint(0, 3, (6, 7, 40), generator=g).float()
+    out.update(acc_a=a, acc_b=b, acc=ref.math.accuracy(a, b))
+    yt = torch.stack([y0, y1], dim=0)[:, None, :].expand(-1, 4, -1).contiguous()                 # (features, time, samples)
+    dft = df.T[:, None, :] + 0.3 * torch.randn(5, 4, N, generator=g)
+    out.update(auc_metric_y=yt, auc_metric_df=dft, auc_metric=ref.metrics.roc_auc(yt, dft))
+    save('clf.npz', **out)
+
+
 def rf_problem(seed, N, C, F, T, s_lo, s_hi, noise=1.0):
     g = torch.Generator().manual_seed(seed)
     X = torch.randn(N, C, T, generator=g, dtype=torch.float64)
@@ -404,6 +477,6 @@ def gen_cfg1():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['ridgecv', 'delay', 'scaler', 'kfold', 'splitters', 'stratified', 'metrics', 'rank', 'trf_small', 'decoder', 'b2b', 'rf', 'encoder', 'cfg1']
+    which = sys.argv[1:] or ['ridgecv', 'delay', 'scaler', 'kfold', 'splitters', 'stratified', 'metrics', 'rank', 'trf_small', 'decoder', 'b2b', 'rf', 'clf', 'encoder', 'cfg1']
     for w in which:
         globals()['gen_' + w]()

@@ -646,3 +646,61 @@ def test_sliding_graph_executor_matches_eager(shape, monkeypatch):
         np.testing.assert_allclose(again.collect('coef_').cpu().numpy(), eager.collect('coef_').cpu().numpy(), rtol=2e-3, atol=2e-5)
         assert torch.equal(again.collect('alpha_'), eager.collect('alpha_'))
     _graphs.clear_cache()
+
+
+def test_classification_metrics_golden(golden):
+    """§8(f2) math.accuracy / math.roc_auc / the Roc_auc metric on the mvb_accuracy / mvb_roc_auc kernels against the
+    reference (tests/golden/clf.npz): tied scores, undefined (single-class) cells -> nan, multi-class macro average,
+    a time axis, integer labels."""
+    mv = _mv()
+    g = golden('clf.npz')
+    acc = mv.math.accuracy(T(g['acc_a']).cuda(), T(g['acc_b']).cuda())
+    assert acc.shape == (6, 7) and np.array_equal(acc.cpu().numpy(), g['acc'])
+    np.testing.assert_allclose(mv.math.accuracy(torch.tensor([[1, 0]]).cuda(), torch.tensor([[-1, 0]]).cuda()).cpu().numpy(), [0.5])
+    auc = mv.math.roc_auc(T(g['auc_t2']).cuda(), T(g['auc_s']).cuda())
+    np.testing.assert_allclose(auc.cpu().numpy(), g['auc_bin'], rtol=1e-6, atol=1e-7, equal_nan=True)
+    assert bool(torch.isnan(auc[1, 1]))
+    auc3 = mv.math.roc_auc(T(g['auc_t3']).cuda(), T(g['auc_s3']).cuda())
+    np.testing.assert_allclose(auc3.cpu().numpy(), g['auc_multi'], rtol=1e-6, atol=1e-7)
+    m = mv.metrics.roc_auc(T(g['auc_metric_y']).cuda(), T(g['auc_metric_df']).cuda())
+    np.testing.assert_allclose(m.cpu().numpy(), g['auc_metric'], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(mv.math.roc_auc(T(g['auc_t3']).double().cuda(), T(g['auc_s3']).double().cuda()).cpu().numpy(), g['auc_multi'], rtol=1e-6)
+    with pytest.raises(ValueError):
+        mv.math.roc_auc(torch.ones(4).cuda(), torch.randn(4).cuda())
+    with pytest.raises(ValueError):
+        mv.math.accuracy(torch.ones(4).cuda(), torch.ones(5).cuda())
+
+
+def test_ridge_classifier_golden(golden):
+    """§8(f2) RidgeClassifier (OvR and OvO through the Classifier wrapper) against fixtures composed from the reference's
+    LabelBinariser + _RidgeCV_torch as ridgeclassifier.py / classifier.py spell it out; accuracy / roc_auc through score()
+    and cross_val_score, Sliding decoding over a time axis."""
+    mv = _mv()
+    g = golden('clf.npz')
+    X, y, al = T(g['X']).cuda(), T(g['y']).cuda(), T(g['alphas'])
+    clf = mv.estimators.RidgeClassifier(alphas=al).fit(X, y)
+    assert float(clf.estimators_.estimator.alpha_) == float(g['ovr_alpha'])
+    np.testing.assert_allclose(clf.coef_.cpu().numpy(), g['ovr_coef'], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(clf.intercept_.cpu().numpy().reshape(-1), g['ovr_intercept'].reshape(-1), rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(clf.pattern_.cpu().numpy(), g['ovr_pattern'], rtol=2e-3, atol=1e-4)
+    np.testing.assert_allclose(clf.decision_function(X).cpu().numpy(), g['ovr_df'], rtol=1e-4, atol=1e-4)
+    assert np.array_equal(clf.predict(X).cpu().numpy(), g['ovr_pred'])
+    np.testing.assert_allclose(clf.predict_proba(X).cpu().numpy(), g['ovr_proba'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(clf.score(X, y).cpu().numpy(), g['ovr_accuracy'], rtol=1e-6)
+    np.testing.assert_allclose(clf.score(X, y, metric=mv.metrics.roc_auc).cpu().numpy(), g['ovr_roc_auc'], rtol=1e-5)
+    both = clf.score(X, y, metric=(mv.metrics.accuracy, mv.metrics.roc_auc))
+    assert set(both) == {'accuracy', 'roc_auc'}
+    ovo = mv.estimators.RidgeClassifier(alphas=al, method='OvO').fit(X, y)
+    assert len(ovo.estimators_) == 4 and ovo.coef_.shape == (4, 2, 10) and np.array_equal(ovo.predict(X).cpu().numpy(), g['ovo_pred'])
+    np.testing.assert_allclose(ovo.coef_.cpu().numpy(), g['ovo_coef'], rtol=1e-3, atol=1e-5)
+    assert ovo.decision_function(X).shape == (4, 150, 2)
+    with pytest.raises(NotImplementedError):
+        ovo.predict_proba(X)
+    _, sc = mv.crossvalidation.cross_val_score(mv.estimators.RidgeClassifier(alphas=al), X, y, cv=mv.crossvalidation.StratifiedKFold(n_splits=3))
+    assert sc.shape == (3, 2) and float(sc.min()) > 0.6
+    # decoding over time: one classifier per time slice
+    Xt = X[:, :, None] + 0.5 * torch.randn(150, 10, 6, device='cuda')
+    yt = y[:, :, None].expand(-1, -1, 6).contiguous()
+    sl = mv.estimators.Sliding(mv.estimators.RidgeClassifier(alphas=al), dims=-1).fit(Xt, yt)
+    pred = sl.predict(Xt)
+    assert pred.shape == (150, 2, 6) and float((pred == yt).float().mean()) > 0.75

@@ -258,3 +258,32 @@ def test_receptive_field_host_side(golden):
     x = torch.arange(5.0)[None]
     sh = type(rf)._shift
     assert sh(x, 2, 8).tolist() == [[0, 0, 0, 1, 2, 3, 4, 0]] and sh(x, -2, 4).tolist() == [[2, 3, 4, 0]] and sh(x, 9, 3).tolist() == [[0, 0, 0]]
+
+
+def test_label_binariser_golden(golden):
+    """LabelBinariser against the reference (tests/golden/clf.npz): two label features (3 and 2 classes), -1/+1 and 0/1
+    codes, inverse transform, dtype following neg_label, error cases."""
+    g = golden('clf.npz')
+    y = T(g['y'])
+    lb = mv.preprocessing.LabelBinariser(neg_label=-1.0, pos_label=1.0).to_torch()
+    L = lb.fit_transform(y)
+    assert L.dtype == torch.float32 and np.array_equal(L.numpy(), g['L'])
+    assert np.array_equal(lb.inverse_transform(L).numpy(), g['L_inv']) and np.array_equal(g['L_inv'], g['y'])
+    L01 = mv.preprocessing.LabelBinariser().fit_transform(y)
+    assert L01.dtype == torch.int64 and np.array_equal(L01.numpy(), g['L01'])
+    assert lb.n_features_ == 2 and lb.n_classes_ == [3, 2] and lb.C_.tolist() == [0.0, 3.0] and float(lb.N_) == 5.0
+    assert [l.tolist() for l in lb.labels_] == [[0.0, 1.0, 2.0], [5.0, 9.0]]
+    with pytest.raises(ValueError):
+        lb.transform(torch.tensor([[0.0, 7.0]]))                  # unknown label
+    with pytest.raises(ValueError):
+        lb.transform(torch.zeros(3, 3))                           # wrong number of label features
+    with pytest.raises(ValueError):
+        mv.preprocessing.LabelBinariser(1, 0).to_torch()
+    with pytest.raises(ValueError):
+        lb.clone().transform(y)                                   # not fitted
+    c = mv.estimators.RidgeClassifier(alphas=[1.0, 10.0], method='OvO', alpha_per_target=True)
+    assert c.method == 'OvO' and c.kwarguments['alpha_per_target'] and c.metric_ is mv.metrics.accuracy
+    with pytest.raises(ValueError):
+        mv.estimators.Classifier(mv.estimators.RidgeClassifier, method='OvA')
+    with pytest.raises(ValueError):
+        c.predict(torch.zeros(2, 3))
