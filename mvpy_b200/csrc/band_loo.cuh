@@ -72,7 +72,6 @@ __global__ void __launch_bounds__(1024) block_chol_kernel(const float* __restric
   // raised to it: the deficient directions get a finite, tiny weight instead of NaN -- what the reference's SVD does
   // with its noise-level singular values (ridgecv.py:223-233) -- and well-conditioned designs never reach the floor.
   __shared__ float s_tmax;
-  __shared__ int s_cmax;
   {
     __shared__ float red[32];
     float m = 0.f;
@@ -157,42 +156,104 @@ __global__ void __launch_bounds__(1024) block_chol_kernel(const float* __restric
     }
     __syncthreads();
     // in-place modified Cholesky (lower) of Cm: pivot_k = max(C_kk, floor, max_i C_ik^2 / tmax) -- the third term
-    // (Gill-Murray) bounds |L_ik| by sqrt(tmax) when rounding made the matrix indefinite, so the factor cannot blow up
-    for (int k = 0; k < NB; ++k) {
-      if (threadIdx.x == 0) s_cmax = 0;
-      __syncthreads();
-      if (threadIdx.x > k && threadIdx.x < NB) atomicMax(&s_cmax, __float_as_int(fabsf(Cm[threadIdx.x * LD + k])));
-      __syncthreads();
-      const float cm = __int_as_float(s_cmax);
-      const float d = sqrtf(fmaxf(fmaxf(Cm[k * LD + k], pivot_floor), cm * cm / fmaxf(s_tmax, 1e-30f)));
-      __syncthreads();
-      if (threadIdx.x == 0) Cm[k * LD + k] = d;
-      for (int i = k + 1 + threadIdx.x; i < NB; i += blockDim.x) Cm[i * LD + k] /= d;
-      __syncthreads();
-      const int m = NB - 1 - k;                       // trailing size
-      for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
-        const int i = k + 1 + e / m, jj = k + 1 + e % m;
-        if (jj <= i) Cm[i * LD + jj] -= Cm[i * LD + k] * Cm[jj * LD + k];
-      }
-      __syncthreads();
-    }
-    __syncthreads();
-    // Li = L^-1 (lower): column c solved by 8 cooperating lanes (forward substitution)
+    // (Gill-Murray) bounds |L_ik| by sqrt(tmax) when rounding made the matrix indefinite, so the factor cannot blow up.
+    // 16-column panels: (1) all threads bring the panel up to date with the columns already factored (left-looking),
+    // (2) threads 0..127 (one matrix row each, its 16 panel entries in registers) factor the panel column by column
+    // with two 128-thread named barriers per column instead of five block barriers.
     {
-      const int c = threadIdx.x >> 3, sub = threadIdx.x & 7;      // 128 columns x 8 lanes
-      for (int i = 0; i < NB; ++i) {
-        float s = 0.f;
-        if (i >= c) {
-          for (int k = c + sub; k < i; k += 8) s += Cm[i * LD + k] * Li[k * LD + c];
+      constexpr int PB = 16;
+      __shared__ float s_red[4], s_diag, s_lcol[PB];
+      const float inv_tmax = 1.f / fmaxf(s_tmax, 1e-30f);
+      for (int pb = 0; pb < NB; pb += PB) {
+        for (int e = threadIdx.x; e < (NB - pb) * PB; e += blockDim.x) {
+          const int i = pb + e / PB, c = pb + e % PB;
+          if (c <= i) {
+            float acc = 0.f;
+            for (int k = 0; k < pb; ++k) acc += Cm[i * LD + k] * Cm[c * LD + k];
+            Cm[i * LD + c] -= acc;
+          }
         }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        if (sub == 0) Li[i * LD + c] = (i < c) ? 0.f : (((i == c) ? 1.f : 0.f) - s) / Cm[i * LD + i];
-        __syncwarp();
+        __syncthreads();
+        if (threadIdx.x < NB) {
+          const int r = threadIdx.x;
+          float x[PB];
+#pragma unroll
+          for (int c = 0; c < PB; ++c) x[c] = (r >= pb + c) ? Cm[r * LD + pb + c] : 0.f;
+#pragma unroll
+          for (int k = 0; k < PB; ++k) {
+            const int col = pb + k;
+            float v = (r > col) ? fabsf(x[k]) : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if ((r & 31) == 0) s_red[r >> 5] = v;
+            if (r == col) s_diag = x[k];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const float cm = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+            const float d = sqrtf(fmaxf(fmaxf(s_diag, pivot_floor), cm * cm * inv_tmax));
+            if (r == col) x[k] = d;
+            else if (r > col) x[k] /= d;
+            if (r > col && r < pb + PB) s_lcol[r - pb] = x[k];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (r > col) {
+#pragma unroll
+              for (int c = 0; c < PB; ++c)
+                if (c > k && pb + c <= r) x[c] -= x[k] * s_lcol[c];
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < PB; ++c)
+            if (r >= pb + c) Cm[r * LD + pb + c] = x[c];
+        }
+        __syncthreads();
       }
     }
-    __syncthreads();
+    // Li = L^-1 (lower) by 16 x 16 blocks:  M_ii = L_ii^-1 (all eight diagonal blocks at once, one thread per column),
+    // then block row by block row  M_ij = -M_ii sum_{j <= k < i} L_ik M_kj  (the strictly-lower blocks of Cm become scratch).
+    {
+      constexpr int PB = 16, NBLK = NB / PB;
+      for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) Li[(e / NB) * LD + (e % NB)] = 0.f;
+      __syncthreads();
+      if (threadIdx.x < NB) {
+        const int blk = threadIdx.x / PB, c = threadIdx.x % PB, o = blk * PB;
+        float x[PB];
+#pragma unroll
+        for (int i = 0; i < PB; ++i) {
+          float v = (i == c) ? 1.f : 0.f;
+#pragma unroll
+          for (int k = 0; k < PB; ++k)
+            if (k < i && k >= c) v -= Cm[(o + i) * LD + o + k] * x[k];
+          x[i] = (i < c) ? 0.f : v / Cm[(o + i) * LD + o + i];
+        }
+#pragma unroll
+        for (int i = 0; i < PB; ++i) Li[(o + i) * LD + o + c] = x[i];
+      }
+      __syncthreads();
+      for (int bi = 1; bi < NBLK; ++bi) {
+        float t_acc[2] = {0.f, 0.f};
+        int n_mine = 0;
+        for (int e = threadIdx.x; e < bi * PB * PB; e += blockDim.x, ++n_mine) {
+          const int jb = e / (PB * PB), r = (e / PB) % PB, c = e % PB;
+          float acc = 0.f;
+          for (int k = jb * PB; k < bi * PB; ++k) acc += Cm[(bi * PB + r) * LD + k] * Li[k * LD + jb * PB + c];
+          t_acc[n_mine] = acc;
+        }
+        __syncthreads();
+        n_mine = 0;
+        for (int e = threadIdx.x; e < bi * PB * PB; e += blockDim.x, ++n_mine) {
+          const int jb = e / (PB * PB), r = (e / PB) % PB, c = e % PB;
+          Cm[(bi * PB + r) * LD + jb * PB + c] = t_acc[n_mine];
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < bi * PB * PB; e += blockDim.x) {
+          const int jb = e / (PB * PB), r = (e / PB) % PB, c = e % PB;
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < PB; ++k) acc += Li[(bi * PB + r) * LD + bi * PB + k] * Cm[(bi * PB + k) * LD + jb * PB + c];
+          Li[(bi * PB + r) * LD + jb * PB + c] = -acc;
+        }
+        __syncthreads();
+      }
+    }
     // outputs: Minv_j = Li ; N_j = Li W (Li lower-triangular)
     float* MN_aj = MN + ((int64_t)a * nblk + j) * NB * 2 * NB;
     for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
