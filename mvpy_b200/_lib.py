@@ -8,6 +8,7 @@ but any compute call raises if the library or a CUDA device is missing.
 from __future__ import annotations
 
 import ctypes
+import threading
 import os
 from ctypes import POINTER, c_char_p, c_int, c_int32, c_int64, c_size_t, c_void_p
 from typing import Optional, Tuple
@@ -127,6 +128,21 @@ def profile_read(disable: bool = True) -> dict:
     if disable:
         lib.mvb_profile_disable()
     return out
+
+
+# ------------------------------------------------------------------------------ shared-design context
+class _FoldContext(threading.local):
+    """What the predictor-set drivers (Hierarchical / Shapley) and the Validator know and the estimator at the end of
+    the chain does not: that the data it is about to be fitted on is a feature subset (``idx`` along ``dim``) of a larger
+    array ``parent`` restricted to the training trials ``train``, after the preprocessing steps of ``model``.  With that,
+    ``TimeDelayed.fit`` computes the fold's full Gram / cross-moment once and slices it for every predictor set
+    (``shared`` is the per-driver cache)."""
+    parent = None       # dict(X=..., dim=..., idx=..., shared={...}) set by fit_validator_
+    train = None        # training indices of the current fold, set by fit_model_
+    model = None        # the model clone being fitted in the current fold, set by fit_model_
+
+
+fold_ctx = _FoldContext()
 
 
 # ------------------------------------------------------------------------------------------- helpers

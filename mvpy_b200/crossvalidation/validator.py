@@ -76,7 +76,11 @@ def fit_model_(model, train: torch.Tensor, test: torch.Tensor, X: torch.Tensor, 
     if y is not None and metric is not None:
         for m in (metric if many else (metric,)):
             m.grant({'y_b': y[train].mean(m.reduce, keepdim=True)})
-    model.fit(*((X[train], y[train]) if y is not None else (X[train],)))
+    _lib.fold_ctx.train, _lib.fold_ctx.model = train, model        # lets TimeDelayed share per-fold statistics across predictor sets
+    try:
+        model.fit(*((X[train], y[train]) if y is not None else (X[train],)))
+    finally:
+        _lib.fold_ctx.train = _lib.fold_ctx.model = None
     args = (X[test], y[test]) if y is not None else (X[test],)
     score_i = score(model, metric, *args) if metric is not None else model.score(*args)
     if many and len(metric) > 1:

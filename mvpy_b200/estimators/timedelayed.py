@@ -6,6 +6,7 @@ Here the stimulus is only edge-padded (``mvb_trf_pad``); all contractions (X^T X
 prediction) read the padded series through offset tables, so the lag expansion never exists in HBM."""
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Tuple, Union
 
 import numpy as np
@@ -85,6 +86,53 @@ class _TimeDelayed_torch(sklearn.base.BaseEstimator):
             pat = _lib.matmul_nt(Sx, coef) * (1.0 / float(yt.shape[0] - 1))
         return pat.reshape((self.f_, self.c_, self.w_)).flip(-1)
 
+    def _shared_stats(self, Xd: torch.Tensor, yd: torch.Tensor):
+        """Inside ``Hierarchical`` / ``Shapley`` every predictor set is a feature subset of one array, and its Gram and
+        cross-moment for a fold are sub-matrices of that fold's full-predictor statistics (the preceding ``Scaler``
+        works per feature, so scaling commutes with the selection).  Those are computed once per fold, kept in the
+        driver's ``shared`` dict, and sliced here; returns (design on the full padded array with ``feat_idx``, stats)
+        or None when the situation is anything else."""
+        from sklearn.pipeline import Pipeline
+        from ..preprocessing.scaler import _Scaler_torch
+        ctx = _lib.fold_ctx
+        par, train, model = ctx.parent, ctx.train, ctx.model
+        if par is None or train is None or model is None or os.environ.get('MVB_SHARE_STATS', '1') == '0':
+            return None
+        X_all, idx = par['X'], par['idx']
+        if X_all.ndim != 3 or par['dim'] not in (-2, 1) or not X_all.is_cuda or X_all.dtype != Xd.dtype:
+            return None
+        if isinstance(model, Pipeline):
+            if model[-1] is not self:
+                return None
+            pre = [step for _, step in model.steps[:-1]]
+        elif model is self:
+            pre = []
+        else:
+            return None
+        for step in pre:              # only per-feature preprocessing commutes with the feature selection
+            if not isinstance(step, _Scaler_torch):
+                return None
+            dims = step.dims if step.dims is not None else (0,)
+            dims = (dims,) if isinstance(dims, int) else tuple(int(d) for d in dims)
+            if any(d % 3 == 1 for d in dims):
+                return None
+        n_tr, W = int(train.numel()), self.window.shape[0]
+        if Xd.shape != (n_tr, int(idx.numel()), X_all.shape[2]) or n_tr * X_all.shape[2] <= X_all.shape[1] * W + 1:
+            return None
+        key = (tuple(train.tolist()), W, self._lag_min, bool(self.estimator.fit_intercept))
+        entry = par['shared'].get(key)
+        if entry is None:
+            X_tr = X_all[train.to(X_all.device)]
+            for step in pre:
+                X_tr = step.clone().fit_transform(X_tr)
+            full = self._design(X_tr.contiguous())
+            entry = (full, _lib.trf_stats(full, yd, self.estimator.fit_intercept))
+            par['shared'][key] = entry
+        full, (G, XtY, mu, ybar) = entry
+        cols = (idx.to(G.device)[:, None] * W + torch.arange(W, device=G.device)[None, :]).reshape(-1)
+        stats = (G[cols][:, cols].contiguous(), XtY[cols].contiguous(), mu[cols].contiguous(), ybar)
+        return full.subset(feat_idx=idx), stats
+
     def fit(self, X: torch.Tensor, y: torch.Tensor):
         if (len(X.shape) != 3) | (len(y.shape) != 3):
             raise ValueError(f'X and y must have 3 dimensions (trials, channels, time), but got {X.shape} and {y.shape}.')
@@ -96,9 +144,10 @@ class _TimeDelayed_torch(sklearn.base.BaseEstimator):
         yd = _lib.to_device(y).to(Xd.dtype).contiguous()
         est = self.estimator
         est.alphas = est.alphas.to(X.dtype).to(X.device)              # ridgecv.py:125
-        design = self._design(Xd)
+        shared = self._shared_stats(Xd, yd)
+        design, stats = shared if shared is not None else (self._design(Xd), None)
         fit = solve_design(design, yd, _lib.to_device(est.alphas).contiguous(), est.fit_intercept, est.alpha_per_target,
-                           keep_gram=self.patterns)
+                           stats=stats, keep_gram=self.patterns)
         self._finish_fit(fit, design, yd, out_dev)
         return self
 

@@ -61,11 +61,19 @@ def check_dims_and_groups_(X: torch.Tensor, y: torch.Tensor, groups=None, dim: O
     return dim, group_ids, sets, masks, groups
 
 
-def fit_validator_(validator: Validator, X: torch.Tensor, y: torch.Tensor, mask: torch.Tensor, dim: int) -> Validator:
-    """One cross-validation on the predictors selected by ``mask`` (hierarchical.py:150-207)."""
-    X_i = torch.index_select(X, dim=dim, index=torch.nonzero(mask.to(X.device), as_tuple=False).squeeze(-1))
+def fit_validator_(validator: Validator, X: torch.Tensor, y: torch.Tensor, mask: torch.Tensor, dim: int,
+                   shared: Optional[dict] = None) -> Validator:
+    """One cross-validation on the predictors selected by ``mask`` (hierarchical.py:150-207).  ``shared``: a dict owned
+    by the caller and handed to every predictor set of the same (X, y): estimators that can (``TimeDelayed``) keep each
+    fold's full-predictor Gram / cross-moment in it and slice them per set instead of recomputing (``_lib.fold_ctx``)."""
+    idx = torch.nonzero(mask.to(X.device), as_tuple=False).squeeze(-1)
+    X_i = torch.index_select(X, dim=dim, index=idx)
     v = validator.clone()
-    v.fit(X_i, y)
+    _lib.fold_ctx.parent = None if shared is None else dict(X=X, dim=dim, idx=idx, shared=shared)
+    try:
+        v.fit(X_i, y)
+    finally:
+        _lib.fold_ctx.parent = None
     return v
 
 
@@ -103,12 +111,13 @@ class Hierarchical:
         mine = set(_dist.my_units(len(masks))) if shard else set(range(len(masks)))
         Xd, yd = _lib.stage(X), _lib.stage(y)          # one host->device copy for all sets
         self.validator_, local = [], {}
+        shared: dict = {}                              # per-fold statistics of the full predictor set, shared by all sets
         with _dist.sharded_region():
             for i, mask in enumerate(masks):
                 if i not in mine:
                     self.validator_.append(None)
                     continue
-                v = fit_validator_(self.validator, Xd, yd, mask, dim)
+                v = fit_validator_(self.validator, Xd, yd, mask, dim, shared)
                 local[i] = v.score_
                 self.validator_.append(_move_tensors(v, out_dev) if Xd.device != out_dev else v)
         if multi is not None:

@@ -34,14 +34,15 @@ def fit_permutation_(validator: Validator, X: torch.Tensor, y: torch.Tensor, gro
     perm, sort, data = draw['perm'], draw['sort'], draw['data'].to(X.device)
     Xs, ys = X[data], y[data]
     mask = groups[0, :].clone()
-    v = fit_validator_(validator, Xs, ys, mask, dim)
+    shared: dict = {}                 # per-fold full-predictor statistics, shared by the nested sets of this permutation
+    v = fit_validator_(validator, Xs, ys, mask, dim, shared)
     prev = v.score_
     is_dict = isinstance(prev, dict)
     phi = {name: [prev[name]] for name in prev} if is_dict else [prev]
     validators = [v]
     for p_i in perm.tolist():
         mask = mask | groups[p_i]
-        v = fit_validator_(validator, Xs, ys, mask, dim)
+        v = fit_validator_(validator, Xs, ys, mask, dim, shared)
         validators.append(v)
         cur = v.score_
         if is_dict:

@@ -32,7 +32,7 @@ class _StubValidator:
         self.score_ = score
 
 
-def _stub_fit_validator(validator, X, y, mask, dim):
+def _stub_fit_validator(validator, X, y, mask, dim, shared=None):
     m = mask.to(torch.float32)
     w = torch.arange(1, m.numel() + 1, dtype=torch.float32)
     trial_sig = (X[:, 0, 0] * torch.arange(1, X.shape[0] + 1, dtype=torch.float32)).sum()     # order of the trials matters

@@ -704,3 +704,40 @@ def test_ridge_classifier_golden(golden):
     sl = mv.estimators.Sliding(mv.estimators.RidgeClassifier(alphas=al), dims=-1).fit(Xt, yt)
     pred = sl.predict(Xt)
     assert pred.shape == (150, 2, 6) and float((pred == yt).float().mean()) > 0.75
+
+
+def test_predictor_sets_share_fold_statistics(monkeypatch):
+    """Hierarchical / Shapley: every predictor set's Gram and cross-moment are slices of the fold's full-predictor
+    statistics (computed once per fold, mvpy_b200/estimators/timedelayed.py:_shared_stats).  Same alphas and scores as
+    fitting every set from scratch; also with a second Scaler-free model and with patterns."""
+    from sklearn.pipeline import make_pipeline
+    from mvpy_b200 import _lib
+    mv = _mv()
+    torch.manual_seed(3)
+    X, y = mv.dataset.make_meeg_continuous(fs=50, n_trials=40, n_channels=6, n_features=6)
+    X, y = X.cuda(), y.cuda()
+    al = torch.logspace(-3, 3, 7)
+    groups = torch.tensor([[1, 1, 0, 0, 0, 0], [0, 0, 1, 1, 0, 0], [0, 0, 0, 0, 1, 1]])
+    calls = {'n': 0}
+    real = _lib.trf_stats
+
+    def counting(*a, **k):
+        calls['n'] += 1
+        return real(*a, **k)
+    monkeypatch.setattr(_lib, 'trf_stats', counting)
+    for make in (lambda: make_pipeline(mv.preprocessing.Scaler().to_torch(), mv.estimators.TimeDelayed(-0.2, 0.0, 50, alphas=al)),
+                 lambda: mv.estimators.TimeDelayed(-0.2, 0.1, 50, alphas=al, patterns=True)):
+        out = {}
+        for share in ('0', '1'):
+            monkeypatch.setenv('MVB_SHARE_STATS', share)
+            calls['n'] = 0
+            h, sc = mv.model_selection.hierarchical_score(make(), X, y, groups=groups, cv=4)
+            torch.manual_seed(11)
+            s, ssc = mv.model_selection.shapley_score(make(), X, y, groups=groups, n_permutations=2, cv=4)
+            alphas = torch.stack([torch.stack([(m[-1] if hasattr(m, 'steps') else m).estimator.alpha_ for m in v.model_]) for v in h.validator_])
+            out[share] = (sc, ssc, alphas, calls['n'])
+        # 7 sets x 4 folds from scratch vs 4 folds once; Shapley: 2 permutations x 3 nested sets x 4 folds vs 2 x 4
+        assert out['0'][3] >= 7 * 4 + 2 * 3 * 4 and out['1'][3] <= 4 + 2 * 4 + 2, (out['0'][3], out['1'][3])
+        assert torch.equal(out['0'][2], out['1'][2])
+        np.testing.assert_allclose(out['1'][0].cpu().numpy(), out['0'][0].cpu().numpy(), rtol=0, atol=2e-5)
+        np.testing.assert_allclose(out['1'][1].cpu().numpy(), out['0'][1].cpu().numpy(), rtol=0, atol=4e-5)
