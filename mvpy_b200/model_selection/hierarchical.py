@@ -111,7 +111,8 @@ class Hierarchical:
         mine = set(_dist.my_units(len(masks))) if shard else set(range(len(masks)))
         Xd, yd = _lib.stage(X), _lib.stage(y)          # one host->device copy for all sets
         self.validator_, local = [], {}
-        shared: dict = {}                              # per-fold statistics of the full predictor set, shared by all sets
+        # per-fold statistics of the full predictor set, shared by all sets this rank fits (pointless for a single set)
+        shared: Optional[dict] = {} if len(mine) > 1 else None
         with _dist.sharded_region():
             for i, mask in enumerate(masks):
                 if i not in mine:
