@@ -1,3 +1,4 @@
+"""Developer probe: per-slice host (enqueue) and total time of Sliding(RidgeDecoder).fit at BASELINE configs[4] slice size,\nplus a bare decoder / RidgeCV fit (run on a GPU box):  [MVB_SLIDING_LANES=n] [MVB_SLIDING_GRAPHS=0] python tools/cfg5_probe.py"""
 import os, sys, time
 sys.path.insert(0, '/root/repo')
 import torch

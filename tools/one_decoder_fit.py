@@ -1,3 +1,4 @@
+"""One RidgeDecoder fit at BASELINE configs[4] slice size between cudaProfilerStart/Stop, for ncu launch lists."""
 import sys
 sys.path.insert(0, '/root/repo')
 import torch
