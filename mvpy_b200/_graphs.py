@@ -29,12 +29,6 @@ _CACHE_MAX = 4
 _broken = False
 
 
-def _tensor_attrs(obj):
-    for name, val in vars(obj).items():
-        if isinstance(val, torch.Tensor) and val.is_cuda:
-            yield name, val
-
-
 def _snapshot(obj, consumer: torch.cuda.Stream):
     """Copy of a fitted estimator whose CUDA tensors no longer alias the lane's static graph outputs."""
     new = copy.copy(obj)
