@@ -149,7 +149,8 @@ SplitPlan plan_contract(int M, int N, int K, int dtype, int symmetric) {
 
 template <typename T>
 int run_contract(const mvb_operand& A, const mvb_operand& B, int M, int N, int K, T* C, int64_t ldc, int symmetric,
-                 void* ws, size_t ws_bytes, cudaStream_t st, int c_block_cols = 0, int64_t c_block_stride = 0) {
+                 void* ws, size_t ws_bytes, cudaStream_t st, int c_block_cols = 0, int64_t c_block_stride = 0,
+                 void* planes = nullptr, size_t planes_bytes = 0) {
   if (M <= 0 || N <= 0) return MVB_OK;
   constexpr int dtype = sizeof(T) == 4 ? MVB_F32 : MVB_F64;
   const SplitPlan pl = plan_contract(M, N, K, dtype, symmetric);
@@ -169,6 +170,17 @@ int run_contract(const mvb_operand& A, const mvb_operand& B, int M, int N, int K
     // a B operand that is larger than L2 (dense basis / coefficient matrices against the small implicit design) is
     // streamed once per wave of M tiles instead of once per few M tiles
     p.raster_m_fast = (!symmetric && (int64_t)N * K * 4 > ((int64_t)64 << 20) && M >= 148 * 128 && N <= 65535 * 128) ? 1 : 0;
+    // Large products against a dense B: B is split into TF32 hi / lo planes once (shared-memory image per 256 x 32 tile)
+    // and every stage's B half then arrives by one TMA bulk copy instead of LDG -> split -> STS in the 512 threads,
+    // which is the bound of this kernel (profiles/r01_tc_gemm2_notes.md); worth one extra pass over B when M is large.
+    static const bool planes_on = [] { const char* e = getenv("MVB_TC_PLANES"); return !e || atoi(e) != 0; }();
+    if (planes && planes_on && !symmetric && N > 128 && M >= 1024 && (double)M * N * K >= 4e9 &&
+        planes_bytes >= mvb::tc_planes_bytes(N, K)) {
+      MVB_CUDA(mvb::tc_presplit_launch(p.B, K, (uint8_t*)planes, st));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      p.b_planes = (const uint8_t*)planes;
+      p.b_planes_nkb = (K + mvb::tc::BK - 1) / mvb::tc::BK;
+    }
     const int slot = prof_begin(2.0 * M * (double)N * K * (symmetric ? 0.5 : 1.0), st);
     MVB_CUDA(mvb::tc_gemm_launch(p, pl.splits, N > 128 ? 256 : 128, st));
     prof_end(slot, st);
@@ -382,6 +394,7 @@ struct BandWs {
   float *Qt, *Tdiag, *Tsub, *Minv, *Nmat, *Pb, *MN, *Z, *h, *U0, *U1, *C1, *C2, *Ct, *Ub, *Xb, *beta, *dd;
   double *mu64, *ybar64, *cz, *mb, *loss_partial, *loss64;
   void* lanczos_ws; void* contract_ws; size_t contract_bytes;
+  void* planes; size_t planes_bytes;      // pre-split TF32 planes of the dense B operand of the large products
   int slabs, P, nb;
 };
 
@@ -436,6 +449,9 @@ void carve_band(Arena& ar, const mvb_design* d, int F, int A, BandWs& w) {
   cb = std::max(cb, plan_contract((int)n, (int)AF, (int)p, MVB_F32, 0).ws_elems);
   w.contract_bytes = cb * 4;
   w.contract_ws = ar.take<char>(w.contract_bytes);
+  w.planes_bytes = std::max(std::max(mvb::tc_planes_bytes((int)P, (int)p), mvb::tc_planes_bytes((int)p, (int)P)),
+                            mvb::tc_planes_bytes((int)AF, (int)p));
+  w.planes = ar.take<char>(w.planes_bytes);
 }
 
 // column-blocked Z [nb][rows][128]: Z[blk][r][c] -= cz[blk * 128 + c]
@@ -564,7 +580,7 @@ int ridge_solve_band(const mvb_design* d, const float* y, int F, float* G, const
   mvb_operand opRows{d->xp, w.row_off, w.col_off, (int)n, 0};
   mvb_operand opQt{w.Qt, w.rowP, w.iota, (int)P, qmode};
   int rc;
-  { ProfScope ps(PC_LEVERAGE_Z); rc = run_contract<float>(opRows, opQt, (int)n, (int)P, (int)p, w.Z, P, 0, w.contract_ws, w.contract_bytes, st, 128, n * 128); }
+  { ProfScope ps(PC_LEVERAGE_Z); rc = run_contract<float>(opRows, opQt, (int)n, (int)P, (int)p, w.Z, P, 0, w.contract_ws, w.contract_bytes, st, 128, n * 128, w.planes, w.planes_bytes); }
   if (rc) return rc;
   mvb::matvec_rows_kernel<float><<<cdiv(P * 32, 256), 256, 0, st>>>(w.Qt, P, P, w.mu64, w.cz);    MVB_LAUNCHED();
   sub_cols_blocked_kernel<<<grid_for(n * P), 256, 0, st>>>(w.Z, n, nb, w.cz);                        MVB_LAUNCHED();
@@ -645,13 +661,13 @@ int ridge_solve_band(const mvb_design* d, const float* y, int F, float* G, const
     mvb_operand opX{w.Xb, w.rowP, w.iota, (int)AF, 2};
     const float* Qc = (const float*)((const char*)w.lanczos_ws + mvb::lb::make_plan((int)p).off_Qc);   // Q^T from the reduction
     mvb_operand opQc{Qc, w.rowP, w.iota, (int)p, 2};          // rows jj of Q^T, contraction k contiguous
-    { ProfScope ps(PC_SMALL); rc = run_contract<float>(opX, opQc, (int)AF, (int)p, (int)P, w.beta, p, 0, w.contract_ws, w.contract_bytes, st); }
+    { ProfScope ps(PC_SMALL); rc = run_contract<float>(opX, opQc, (int)AF, (int)p, (int)P, w.beta, p, 0, w.contract_ws, w.contract_bytes, st, 0, 0, w.planes, w.planes_bytes); }
     if (rc) return rc;
   }
   mvb::matvec_rows_kernel<float><<<cdiv(AF * 32, 256), 256, 0, st>>>(w.beta, AF, p, w.mu64, w.mb);   MVB_LAUNCHED();
   // 6. fitted values for every (alpha, target): R = X_t beta_all^T, LOO losses, selection, coefficients
   mvb_operand opBeta{w.beta, w.iota_p, w.iota, (int)AF, dense_mode(p, (int)p, w.beta, 4)};
-  { ProfScope ps(PC_RESIDUAL); rc = run_contract<float>(opRows, opBeta, (int)n, (int)AF, (int)p, w.Z, AF, 0, w.contract_ws, w.contract_bytes, st); }
+  { ProfScope ps(PC_RESIDUAL); rc = run_contract<float>(opRows, opBeta, (int)n, (int)AF, (int)p, w.Z, AF, 0, w.contract_ws, w.contract_bytes, st, 0, 0, w.planes, w.planes_bytes); }
   if (rc) return rc;
   {
     dim3 grid(cdiv(AF, 128), w.slabs);

@@ -20,6 +20,7 @@
 // releasing a buffer back to the loaders.
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -57,6 +58,10 @@ struct TcGemmParams {
   int64_t c_block_stride;             //      elements between consecutive column blocks (>= M * c_block_cols)
   float* rowsq;                       // optional [TC_ROWSQ_PARTS][batch][M]: += sum over this thread's columns of C[m][n]^2
                                       // (one output tile wide only: N <= BN; split-K not allowed)
+  // ---- pre-split B operand (256-wide tiles only, batch == 1) ----
+  const uint8_t* b_planes;            // optional: B already split into TF32 hi / lo planes, one shared-memory image per
+  int b_planes_nkb;                   //   (256-row tile, 32-k stage), [n_tile][b_planes_nkb][2 * plane bytes] (tc_presplit_launch);
+                                      //   the stage's B half is then one TMA bulk copy instead of LDG -> split -> STS by the threads
 };
 
 inline TcGemmParams tc_gemm_defaults() {
@@ -129,6 +134,14 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
 
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+
+// One TMA bulk copy global -> shared (16-byte aligned, size % 16 == 0), completion counted on `bar` (bytes).
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
 
@@ -308,8 +321,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
   opB.roff += batch_id * p.b_roff_batch; opB.koff += batch_id * p.b_koff_batch;
 
   uint8_t* stage_base[2] = {smem, smem + C_::STAGE};
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::BAR_OFF);  // [0],[1]: buffer free; [2]: all MMAs done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C_::BAR_OFF + 32);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::BAR_OFF);  // [0],[1]: buffer free; [2]: all MMAs done; [3],[4]: B planes landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C_::BAR_OFF + 48);
+  constexpr bool B_TMA = (B_MODE == 3);
+  constexpr uint32_t B_BYTES = 2 * C_::B_PLANE;
+  const uint8_t* b_tiles = B_TMA ? p.b_planes + (int64_t)(n0 / BN) * p.b_planes_nkb * (int64_t)B_BYTES : nullptr;
   int64_t* sroffA = reinterpret_cast<int64_t*>(smem + C_::ROFF_OFF);
   int64_t* sroffB = sroffA + BM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -318,6 +334,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
     mbar_init(smem_u32(&bars[0]), 1);
     mbar_init(smem_u32(&bars[1]), 1);
     mbar_init(smem_u32(&bars[2]), 1);
+    mbar_init(smem_u32(&bars[3]), 1);
+    mbar_init(smem_u32(&bars[4]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -329,7 +347,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
   }
   for (int r = threadIdx.x; r < BM + BN; r += NTHREADS) {
     if (r < BM) sroffA[r] = (m0 + r < opA.rows) ? opA.roff[m0 + r] : 0;
-    else sroffB[r - BM] = (n0 + r - BM < opB.rows) ? opB.roff[n0 + r - BM] : 0;
+    else if (!B_TMA) sroffB[r - BM] = (n0 + r - BM < opB.rows) ? opB.roff[n0 + r - BM] : 0;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -344,10 +362,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
   const int nkb = max(0, kb_end - kb_begin);
 
   Loader<BM, A_MODE> la;
-  Loader<BN, B_MODE> lb;
+  Loader<BN, B_TMA ? 2 : B_MODE> lb;             // unused (and compiled away) when the TMA delivers B
   if (nkb > 0) {
     la.fetch(opA, sroffA, m0, kb_begin * BK, p.K);
-    lb.fetch(opB, sroffB, n0, kb_begin * BK, p.K);
+    if (!B_TMA) lb.fetch(opB, sroffB, n0, kb_begin * BK, p.K);
+    else if (threadIdx.x == 0)
+      bulk_load(smem_u32(stage_base[0] + 2 * C_::A_PLANE), b_tiles + (int64_t)kb_begin * B_BYTES, B_BYTES, smem_u32(&bars[3]));
   }
   constexpr int NACC = BN / NPART;             // columns per thread: warps 4i .. 4i+3 own column part i
   const int q = warp & 3;                      // TMEM lane quarter this warp may access
@@ -363,7 +383,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
     uint8_t* sb = stage_base[s];
     if (p.dbg != 1) {
       la.store(sb, sb + C_::A_PLANE);
-      lb.store(sb + 2 * C_::A_PLANE, sb + 2 * C_::A_PLANE + C_::B_PLANE);
+      if (!B_TMA) lb.store(sb + 2 * C_::A_PLANE, sb + 2 * C_::A_PLANE + C_::B_PLANE);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -371,6 +391,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
     const bool chunk_last = ((it + 1) % DRAIN) == 0 || it == nkb - 1;
     if (threadIdx.x == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (B_TMA) mbar_wait(smem_u32(&bars[3 + s]), (uint32_t)((it >> 1) & 1));      // this stage's B planes have landed
       if (p.dbg != 2) {
         const uint32_t a_hi = smem_u32(sb), a_lo = a_hi + C_::A_PLANE;
         const uint32_t b_hi = a_hi + 2 * C_::A_PLANE, b_lo = b_hi + C_::B_PLANE;
@@ -387,10 +408,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
       }
       mma_commit(smem_u32(&bars[s]));
       if (chunk_last) mma_commit(smem_u32(&bars[2]));
+      if (B_TMA && it + 1 < nkb) {
+        // the other buffer was last read by stage it - 1; once those MMAs are done the next stage's planes can land in it
+        // while this stage's MMAs run
+        const int s1 = s ^ 1;
+        if (it >= 1) mbar_wait(smem_u32(&bars[s1]), (uint32_t)(((it - 1) >> 1) & 1));
+        bulk_load(smem_u32(stage_base[s1] + 2 * C_::A_PLANE), b_tiles + (int64_t)(kb_begin + it + 1) * B_BYTES, B_BYTES,
+                  smem_u32(&bars[3 + s1]));
+      }
     }
     if (it + 1 < nkb && p.dbg != 1) {  // next stage's global loads fly while this stage's MMAs run
       la.fetch(opA, sroffA, m0, (kb_begin + it + 1) * BK, p.K);
-      lb.fetch(opB, sroffB, n0, (kb_begin + it + 1) * BK, p.K);
+      if (!B_TMA) lb.fetch(opB, sroffB, n0, (kb_begin + it + 1) * BK, p.K);
     }
     if (chunk_last) {
       mbar_wait(smem_u32(&bars[2]), (uint32_t)(n_drained & 1));
@@ -467,6 +496,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
   }
 }
 
+// B operand -> TF32 hi / lo planes in the kernel's shared-memory image, one (256-row tile, 32-k stage) at a time:
+// planes[(tile * nkb_total + kb) * 2 * PLANE + plane * PLANE + kc * LBO + r * 16 + (k % 4) * 4], zero-filled outside
+// the operand.  One thread per (tile row, 16-byte chunk); rows [row_begin, row_end) and stages [kb_begin, kb_end) only,
+// so a growing operand (a Lanczos basis) is extended in place.
+__global__ void presplit_kernel(const GatherOperand op, int K, int nkb_total, int row_begin, int row_end, int kb_begin,
+                                int kb_end, uint8_t* __restrict__ planes) {
+  constexpr int BN = 256, LBO = BN * 16 + 16, PLANE = KC * LBO;
+  const int64_t n_rows = row_end - row_begin, n_kb = kb_end - kb_begin;
+  const int64_t total = n_rows * n_kb * KC;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int kc = (int)(e % KC);
+    const int64_t t = e / KC;
+    const int row = row_begin + (int)(t % n_rows);
+    const int kb = kb_begin + (int)(t / n_rows);
+    const int tile = row / BN, r = row % BN;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int k = kb * BK + kc * 4;
+    if (row < op.rows && k < K) {
+      const float* src = op.base + op.roff[row];
+      if (op.lanes_along_k == 2 && k + 3 < K) v = __ldg(reinterpret_cast<const float4*>(src + op.koff[k]));
+      else {
+        v.x = __ldg(src + op.koff[k]);
+        if (k + 1 < K) v.y = __ldg(src + op.koff[k + 1]);
+        if (k + 2 < K) v.z = __ldg(src + op.koff[k + 2]);
+        if (k + 3 < K) v.w = __ldg(src + op.koff[k + 3]);
+      }
+    }
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+    uint8_t* dst = planes + ((int64_t)tile * nkb_total + kb) * (2 * PLANE) + kc * LBO + r * 16;
+    *reinterpret_cast<float4*>(dst) = h;
+    *reinterpret_cast<float4*>(dst + PLANE) = l;
+    if (r == 0) {                                 // the 16 bytes of padding that end every chunk
+      *reinterpret_cast<float4*>(dst + BN * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(dst + PLANE + BN * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
 template <int BN, int AM, int BMODE>
 inline cudaError_t launch_variant(const TcGemmParams& p, int k_splits, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, AM, BMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -480,6 +548,10 @@ inline cudaError_t launch_variant(const TcGemmParams& p, int k_splits, cudaStrea
 
 template <int BN, int AM>
 inline cudaError_t launch_b(const TcGemmParams& p, int k_splits, cudaStream_t st) {
+  if (p.b_planes) {
+    if (BN != 256 || p.batch > 1 || p.symmetric) return cudaErrorInvalidValue;
+    return launch_variant<256, AM, 3>(p, k_splits, st);
+  }
   switch (p.B.lanes_along_k) {
     case 0: return launch_variant<BN, AM, 0>(p, k_splits, st);
     case 1: return launch_variant<BN, AM, 1>(p, k_splits, st);
@@ -513,6 +585,22 @@ inline int tc_choose_splits(int64_t tiles, int nkb, int max_splits, int64_t out_
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
   }
   return best;
+}
+
+// Pre-split planes of a B operand (see TcGemmParams::b_planes): bytes needed, and the (partial) fill.
+inline size_t tc_planes_bytes(int rows, int K) {
+  return (size_t)((rows + 255) / 256) * ((K + tc::BK - 1) / tc::BK) * 2 * tc::Cfg<256>::B_PLANE;
+}
+inline cudaError_t tc_presplit_launch(const GatherOperand& op, int K, uint8_t* planes, cudaStream_t st, int row_begin = 0,
+                                      int row_end = -1, int kb_begin = 0, int kb_end = -1) {
+  const int nkb = (K + tc::BK - 1) / tc::BK;
+  if (row_end < 0) row_end = ((op.rows + 255) / 256) * 256;      // whole tiles: rows past the operand are zero-filled
+  if (kb_end < 0) kb_end = nkb;
+  const int64_t total = (int64_t)(row_end - row_begin) * (kb_end - kb_begin) * tc::KC;
+  if (total <= 0) return cudaSuccess;
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  tc::presplit_kernel<<<grid, 256, 0, st>>>(op, K, nkb, row_begin, row_end, kb_begin, kb_end, planes);
+  return cudaGetLastError();
 }
 
 // Launch helper.  bn = 256 for wide outputs, 128 otherwise; k_splits partial sums go to

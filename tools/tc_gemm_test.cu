@@ -33,7 +33,7 @@ struct HostOp {
 };
 
 static double run_case(const char* name, const HostOp& A, const HostOp& B, int M, int N, int K, int bn,
-                       int splits, int symmetric) {
+                       int splits, int symmetric, int planes = 0) {
   float* dA = to_dev(A.base);
   int64_t* dAr = to_dev(A.roff);
   int64_t* dAk = to_dev(A.koff);
@@ -48,6 +48,13 @@ static double run_case(const char* name, const HostOp& A, const HostOp& B, int M
   p.A = {dA, dAr, dAk, M, A.lanes_along_k};
   p.B = {dB, dBr, dBk, N, B.lanes_along_k};
   p.M = M; p.N = N; p.K = K; p.C = dC; p.ldc = N; p.c_split_stride = (int64_t)csz; p.symmetric = symmetric; p.dbg = 0;
+  uint8_t* dP = nullptr;
+  if (planes) {          // B handed over as pre-split planes (TMA path)
+    CK(cudaMalloc(&dP, mvb::tc_planes_bytes(N, K)));
+    CK(cudaMemset(dP, 0xFF, mvb::tc_planes_bytes(N, K)));
+    CK(mvb::tc_presplit_launch(p.B, K, dP, 0));
+    p.b_planes = dP; p.b_planes_nkb = (K + 31) / 32;
+  }
   CK(mvb::tc_gemm_launch(p, splits, bn, 0));
   CK(cudaDeviceSynchronize());
   std::vector<float> C(csz * splits);
@@ -71,6 +78,7 @@ static double run_case(const char* name, const HostOp& A, const HostOp& B, int M
          name, M, N, K, bn, splits, symmetric, max_err, max_ref, rel, bad,
          (rel < 1.5e-6 && bad == 0) ? "OK" : "FAIL");
   cudaFree(dA); cudaFree(dAr); cudaFree(dAk); if (!symmetric) cudaFree(dB); cudaFree(dBr); cudaFree(dBk); cudaFree(dC);
+  if (dP) cudaFree(dP);
   return (rel < 1.5e-6 && bad == 0) ? 0 : 1;
 }
 
@@ -114,6 +122,14 @@ int main(int argc, char** argv) {
     A.lanes_along_k = 2; B.lanes_along_k = 2;
     fails += run_case("dense vec4 bn256", A, B, 300, 520, 1000, 256, 1, 0);
     fails += run_case("dense vec4 bn128 split2", A, B, 300, 520, 1000, 128, 2, 0);
+    fails += run_case("dense vec4 x planes", A, B, 300, 520, 1000, 256, 1, 0, 1);
+    fails += run_case("dense vec4 x planes split3", A, B, 300, 520, 1000, 256, 3, 0, 1);
+    B.lanes_along_k = 1;
+    fails += run_case("dense vec4 x planes(scalar)", A, B, 300, 520, 1000, 256, 2, 0, 1);
+  }
+  {
+    HostOp A = dense_op(130, 77, 0), B = dense_op(64, 77, 1);
+    fails += run_case("dense RK x planes", A, B, 130, 64, 77, 256, 1, 0, 1);
   }
   {
     HostOp A = dense_op(130, 77, 0), B = dense_op(64, 77, 1);
@@ -130,6 +146,9 @@ int main(int argc, char** argv) {
     fails += run_case("toeplitz gram sym bn256", G1, G1, p, p, K, 256, 1, 1);
     fails += run_case("toeplitz gram sym bn128 s2", G0, G0, p, p, K, 128, 2, 1);
     fails += run_case("toeplitz gram mixed", G1, G0, p, p, K, 256, 1, 0);
+    HostOp D = dense_op(700, K, 1);      // K = 450 is not a multiple of 4: scalar (mode 1) source
+    fails += run_case("toeplitz x dense planes", G0, D, p, 700, K, 256, 1, 0, 1);
+    fails += run_case("toeplitz(k) x dense planes s2", G1, D, p, 700, K, 256, 2, 0, 1);
   }
   if (argc > 1) {  // throughput: dense 8192 x 8192 x 8192
     int M = 8192, N = 8192, K = 8192;
@@ -142,6 +161,26 @@ int main(int argc, char** argv) {
       mvb::TcGemmParams p = mvb::tc_gemm_defaults();
       p.A = {dA, dAr, dAk, M, A.lanes_along_k}; p.B = {dB, dBr, dBk, N, B.lanes_along_k};
       p.M = M; p.N = N; p.K = K; p.C = dC; p.ldc = N; p.c_split_stride = 0; p.symmetric = 0;
+      if (mode == 2) {
+        uint8_t* dP; CK(cudaMalloc(&dP, mvb::tc_planes_bytes(N, K)));
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        CK(mvb::tc_presplit_launch(p.B, K, dP, 0));
+        cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+        float msp; cudaEventElapsedTime(&msp, e0, e1);
+        mvb::TcGemmParams pp = p; pp.b_planes = dP; pp.b_planes_nkb = (K + 31) / 32; pp.dbg = 0;
+        for (int rast = 0; rast < 2; ++rast) {
+          pp.raster_m_fast = rast;
+          CK(mvb::tc_gemm_launch(pp, 1, 256, 0)); CK(cudaDeviceSynchronize());
+          cudaEventRecord(e0);
+          for (int i = 0; i < 5; ++i) CK(mvb::tc_gemm_launch(pp, 1, 256, 0));
+          cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+          float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+          printf("perf PLANES mode=2 A x pre-split B (raster_m_fast=%d): %.3f ms  %.1f TFLOP/s (fp32-equivalent); presplit %.3f ms\n", rast, ms,
+                 2.0 * M * N * K / ms * 1e-9, msp);
+        }
+        cudaFree(dP);
+      }
       for (int dbg = 0; dbg < 3; ++dbg)
       for (int bn : {256, 128}) {
         p.dbg = dbg;
