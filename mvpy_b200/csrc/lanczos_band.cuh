@@ -37,6 +37,9 @@ struct Plan {
   size_t bytes;
   size_t off_Gp, off_Qc, off_Wt, off_Wt2, off_H, off_S, off_J, off_M, off_lam, off_rowP, off_row128, off_iota, off_part, off_ctl;
   size_t part_elems;
+  // pre-split TF32 planes (tc_gemm.cuh, TcGemmParams::b_planes) of the three dense B operands of the big products:
+  // Gp (filled once), Qt and Q^T (extended by one block per step); 0 bytes for small problems
+  size_t off_plG, off_plQt, off_plQc, planes_bytes;
 };
 
 inline Plan make_plan(int p) {
@@ -64,6 +67,11 @@ inline Plan make_plan(int p) {
   if (pl.part_elems < (size_t)8 * NB * P) pl.part_elems = (size_t)8 * NB * P;
   pl.off_part = take(pl.part_elems * 4);
   pl.off_ctl = take(sizeof(bj::Ctl));
+  static const bool planes_on = [] { const char* e = getenv("MVB_LB_PLANES"); return !e || atoi(e) != 0; }();
+  pl.planes_bytes = (planes_on && pl.P >= 2048) ? tc_planes_bytes(pl.P, pl.P) : 0;
+  pl.off_plG = take(pl.planes_bytes);
+  pl.off_plQt = take(pl.planes_bytes);
+  pl.off_plQc = take(pl.planes_bytes);
   pl.bytes = off + 256;
   return pl;
 }
@@ -379,7 +387,7 @@ struct Ctx {
 
 // C[M x N] (ld ldc) = A(M x K) * B(N x K)^T with automatic split-K for skinny outputs
 inline bool gemm(Ctx& cx, const GatherOperand& A, const GatherOperand& B, int M, int N, int K, float* C, int64_t ldc,
-                 const unsigned int* skip = nullptr, bool subtract = false) {
+                 const unsigned int* skip = nullptr, bool subtract = false, const uint8_t* b_planes = nullptr) {
   const int bn = N > 128 ? 256 : 128;
   const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
   int max_splits = (int)std::min<size_t>(64, cx.pl.part_elems / ((size_t)M * N));
@@ -387,6 +395,7 @@ inline bool gemm(Ctx& cx, const GatherOperand& A, const GatherOperand& B, int M,
   const int splits = tc_choose_splits(tiles, (K + tc::BK - 1) / tc::BK, max_splits, (int64_t)M * N);
   TcGemmParams g = tc_gemm_defaults();
   g.A = A; g.B = B; g.M = M; g.N = N; g.K = K; g.skip_flag = skip;
+  if (b_planes && bn == 256) { g.b_planes = b_planes; g.b_planes_nkb = (cx.pl.P + tc::BK - 1) / tc::BK; }
   const bool via_parts = splits > 1 || subtract;      // C -= A B^T always goes through the partial-sum buffer
   if (via_parts) { g.C = cx.f(cx.pl.off_part); g.ldc = N; g.c_split_stride = (int64_t)M * N; }
   else { g.C = C; g.ldc = ldc; }
@@ -452,10 +461,12 @@ inline bool reorth(Ctx& cx, float* W, const float* Qt, int nq, const unsigned in
   const int P = pl.P;
   int64_t *rowP = cx.i64(pl.off_rowP), *iota = cx.i64(pl.off_iota);
   float *H = cx.f(pl.off_H), *W2 = cx.f(pl.off_Wt2);
+  const uint8_t* plQt = pl.planes_bytes ? (const uint8_t*)(cx.base + pl.off_plQt) : nullptr;
+  const uint8_t* plQc = pl.planes_bytes ? (const uint8_t*)(cx.base + pl.off_plQc) : nullptr;
   GatherOperand w{W, rowP, iota, NB, 2}, q{Qt, rowP, iota, nq, 2};
-  if (!gemm(cx, w, q, NB, nq, P, H, P, skip)) return false;
+  if (!gemm(cx, w, q, NB, nq, P, H, P, skip, false, plQt)) return false;
   GatherOperand h{H, rowP, iota, NB, 2}, qc{cx.f(pl.off_Qc), rowP, iota, P, 2};      // rows c of Q^T, k over Q's first nq rows
-  return gemm(cx, h, qc, NB, P, nq, W, P, skip, true);                                // W -= H Q
+  return gemm(cx, h, qc, NB, P, nq, W, P, skip, true, plQc);                          // W -= H Q
 }
 
 // Enqueue the reduction.  G: p x p.  Outputs: Qt (P x P), Tdiag / Tsub ([nblk][128][128]; Tsub[j] = T_{j,j-1}).
@@ -486,6 +497,14 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
   tables_kernel<<<64, 256, 0, st>>>(P, rowP, row128, iota); ++cx.launches;
   diag_mean_kernel<<<1, 256, 0, st>>>(G, p, cx.f(pl.off_lam)); ++cx.launches;
   pad_gram_kernel<<<(int)std::min<int64_t>(148 * 8, ((int64_t)P * P + 255) / 256), 256, 0, st>>>(G, p, P, Gp, cx.f(pl.off_lam)); ++cx.launches;
+  uint8_t *plG = nullptr, *plQt = nullptr, *plQc = nullptr;
+  if (pl.planes_bytes) {
+    plG = (uint8_t*)(cx.base + pl.off_plG); plQt = (uint8_t*)(cx.base + pl.off_plQt); plQc = (uint8_t*)(cx.base + pl.off_plQc);
+    GatherOperand g_all{Gp, rowP, iota, P, 2};
+    LB_CK(tc_presplit_launch(g_all, P, plG, st)); ++cx.launches;
+    LB_CK(cudaMemsetAsync(plQt, 0, pl.planes_bytes, st));       // blocks arrive one per step; rows / stages not yet there read as zero
+    LB_CK(cudaMemsetAsync(plQc, 0, pl.planes_bytes, st));
+  }
   // Q_0: orthonormalised pseudo-random block
   random_block_kernel<<<(int)std::min<int64_t>(148 * 2, ((int64_t)NB * P + 255) / 256), 256, 0, st>>>(Wt, (int64_t)NB * P, 0x9e3779b9u); ++cx.launches;
   LB_OK(svqb(cx, Wt, Qt));
@@ -494,9 +513,14 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
   for (int j = 0; j < nb; ++j) {
     const float* Qj = Qt + (size_t)j * NB * P;
     transpose_block_kernel<<<dim3(P / 32, NB / 32), dim3(32, 8), 0, st>>>(Qj, P, j * NB, cx.f(pl.off_Qc)); ++cx.launches;   // block j is final
+    if (pl.planes_bytes) {        // ... and joins the pre-split copies of Qt (128 new rows) and Q^T (128 new contraction columns)
+      GatherOperand qt_all{Qt, rowP, iota, P, 2}, qc_all{cx.f(pl.off_Qc), rowP, iota, P, 2};
+      LB_CK(tc_presplit_launch(qt_all, P, plQt, st, j * NB, (j + 1) * NB, 0, -1)); ++cx.launches;
+      LB_CK(tc_presplit_launch(qc_all, P, plQc, st, 0, P, j * (NB / tc::BK), (j + 1) * (NB / tc::BK))); ++cx.launches;
+    }
     // W = Q_j Gp ;  H = W Q_{0..j}^T  -> T_jj, T_{j,j-1}
     GatherOperand qj{Qj, rowP, iota, NB, 2}, g{Gp, rowP, iota, P, 2};
-    LB_OK(gemm(cx, qj, g, NB, P, P, Wt, P));
+    LB_OK(gemm(cx, qj, g, NB, P, P, Wt, P, nullptr, false, plG));
     const int nq = (j + 1) * NB;
     // first pass: against all previous blocks, or (pass1_local) only against the two blocks the three-term
     // recurrence couples -- the later full pass on the normalised block removes the drift along the older ones
