@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace mvb {
 
@@ -306,6 +307,60 @@ struct Loader {
   }
 };
 
+// Epilogue shared by the contraction kernels: the thread's NACC register accumulators (row q * 32 + lane of the tile,
+// columns col_half * NACC ..) -> C, with the split-K / batch / column-block / row-square / mirror options of TcGemmParams.
+template <int NACC>
+__device__ __forceinline__ void store_tile(const TcGemmParams& p, const float (&acc)[NACC], int m0, int n0, int BN, int q, int lane,
+                                           int col_half, int batch_id, int split_id) {
+    const int gm = m0 + q * 32 + lane;
+    float* Cz = p.C + (int64_t)split_id * p.c_split_stride;
+    const int64_t crow_off = (gm < p.M) ? (p.c_roff ? p.c_roff[(int64_t)batch_id * p.M + gm]
+                                                     : (int64_t)batch_id * p.c_batch_stride + (int64_t)gm * p.ldc)
+                                        : 0;
+    if (gm < p.M && p.rowsq) {
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < NACC; ++j)
+        if (n0 + col_half * NACC + j < p.N) sq += acc[j] * acc[j];
+      p.rowsq[((int64_t)col_half * p.batch + batch_id) * p.M + gm] += sq;
+    }
+    if (gm < p.M) {
+#pragma unroll
+      for (int cc = 0; cc < NACC / 32; ++cc) {
+        const int c0 = col_half * NACC + cc * 32;
+        if (n0 + c0 < p.N) {
+          float* crow = Cz + crow_off + n0 + c0;
+          if (p.c_block_cols > 0) {
+            const int cg = n0 + c0;   // 32-aligned, so the group never straddles a column block (block width % 32 == 0)
+            crow = Cz + (int64_t)(cg / p.c_block_cols) * p.c_block_stride + (int64_t)gm * p.c_block_cols + (cg % p.c_block_cols);
+          }
+          const int nvalid = min(32, p.N - (n0 + c0));
+          if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(crow + j) =
+                  make_float4(acc[cc * 32 + j], acc[cc * 32 + j + 1], acc[cc * 32 + j + 2], acc[cc * 32 + j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) crow[j] = acc[cc * 32 + j];
+          }
+          if (p.symmetric) {
+            // mirror into tiles that were skipped (row-tile of gn lies strictly above col-tile of gm)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int gn = n0 + c0 + j;
+              if (j < nvalid && gn < p.M && gm < p.N) {
+                const int mt0 = (gn / BM) * BM, nt0 = (gm / BN) * BN;
+                if (nt0 > mt0 + BM - 1) Cz[(int64_t)gn * p.ldc + gm] = acc[cc * 32 + j];
+              }
+            }
+          }
+        }
+      }
+    }
+}
+
 template <int BN, int A_MODE, int B_MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams p) {
   using C_ = Cfg<BN>;
@@ -439,60 +494,190 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
   }
 
   // ---- epilogue: register accumulators -> global ------------------------------------------------
-  {
-    const int gm = m0 + q * 32 + lane;
-    float* Cz = p.C + (int64_t)split_id * p.c_split_stride;
-    const int64_t crow_off = (gm < p.M) ? (p.c_roff ? p.c_roff[(int64_t)batch_id * p.M + gm]
-                                                     : (int64_t)batch_id * p.c_batch_stride + (int64_t)gm * p.ldc)
-                                        : 0;
-    if (gm < p.M && p.rowsq) {
-      float sq = 0.f;
-#pragma unroll
-      for (int j = 0; j < NACC; ++j)
-        if (n0 + col_half * NACC + j < p.N) sq += acc[j] * acc[j];
-      p.rowsq[((int64_t)col_half * p.batch + batch_id) * p.M + gm] += sq;
-    }
-    if (gm < p.M) {
-#pragma unroll
-      for (int cc = 0; cc < NACC / 32; ++cc) {
-        const int c0 = col_half * NACC + cc * 32;
-        if (n0 + c0 < p.N) {
-          float* crow = Cz + crow_off + n0 + c0;
-          if (p.c_block_cols > 0) {
-            const int cg = n0 + c0;   // 32-aligned, so the group never straddles a column block (block width % 32 == 0)
-            crow = Cz + (int64_t)(cg / p.c_block_cols) * p.c_block_stride + (int64_t)gm * p.c_block_cols + (cg % p.c_block_cols);
-          }
-          const int nvalid = min(32, p.N - (n0 + c0));
-          if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(crow + j) =
-                  make_float4(acc[cc * 32 + j], acc[cc * 32 + j + 1], acc[cc * 32 + j + 2], acc[cc * 32 + j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) crow[j] = acc[cc * 32 + j];
-          }
-          if (p.symmetric) {
-            // mirror into tiles that were skipped (row-tile of gn lies strictly above col-tile of gm)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int gn = n0 + c0 + j;
-              if (j < nvalid && gn < p.M && gm < p.N) {
-                const int mt0 = (gn / BM) * BM, nt0 = (gm / BN) * BN;
-                if (nt0 > mt0 + BM - 1) Cz[(int64_t)gn * p.ldc + gm] = acc[cc * 32 + j];
-              }
-            }
-          }
-        }
-      }
-    }
-  }
+  store_tile<NACC>(p, acc, m0, n0, BN, q, lane, col_half, batch_id, split_id);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN)
                  : "memory");
+  }
+}
+
+// ---- A operand in tensor memory, B as pre-split planes by TMA ("TA" kernel) ---------------------------------------------
+// With both operands' hi / lo planes in shared memory a 32-k stage costs 96 KB of staging writes + 144 KB of MMA operand
+// reads against 128 B/clk of shared-memory bandwidth: 1875 cycles, more than the stage's 1536 cycles of MMAs.  Here A never
+// touches shared memory: every thread splits the 8 values it holds of one tile row and writes them to tensor memory
+// (tcgen05.st); the MMAs take A from TMEM (the [a_tmem] operand form) and shared memory carries only B (one 64 KB bulk copy
+// in, 96 KB of MMA reads per stage).  The shared memory this frees holds a third B stage, so a stage's copy is issued two
+// stages of MMAs ahead.  TMEM columns: 0..255 accumulator, 256 + 64 s: stage s of A (hi at +0, lo at +32).
+// 256-wide tiles, batch == 1, not symmetric, A gathers 0 and 2 (mode 1 would need a transposing load; it keeps the
+// shared-memory kernel).  Measured (tools/experimental/tc_gemm_tmema_test): dense 8192^3 214 TFLOP/s against 141.
+struct CfgTA {
+  static constexpr int BN = 256, NS = 3;
+  static constexpr int B_LBO = Cfg<256>::B_LBO, B_PLANE = Cfg<256>::B_PLANE;
+  static constexpr uint32_t B_BYTES = 2 * B_PLANE;
+  static constexpr int BAR_OFF = NS * (int)B_BYTES;         // [0..2] stage free; [3] chunk done; [4..6] B planes landed
+  static constexpr int SMEM_BYTES = BAR_OFF + 128;
+  static constexpr uint32_t COL_A = 256, TMEM_COLS = 512;
+};
+
+__device__ __forceinline__ void mma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(v);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(u[0]),
+               "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+               : "memory");
+}
+
+template <int A_MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_ta_kernel(const TcGemmParams p) {
+  using C_ = CfgTA;
+  static_assert(A_MODE == 0 || A_MODE == 2, "A gather modes 0 and 2 only");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int m0 = (p.raster_m_fast ? blockIdx.x : blockIdx.y) * BM;
+  const int n0 = (p.raster_m_fast ? blockIdx.y : blockIdx.x) * C_::BN;
+  if (p.skip_flag && *p.skip_flag) return;
+  const int splits = gridDim.z, split_id = blockIdx.z;
+  const GatherOperand opA = p.A;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::BAR_OFF);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C_::BAR_OFF + 64);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 7; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(C_::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nkb_total = (p.K + BK - 1) / BK;
+  const int kb_per = (nkb_total + splits - 1) / splits;
+  const int kb_begin = split_id * kb_per;
+  const int kb_end = min(nkb_total, kb_begin + kb_per);
+  const int nkb = max(0, kb_end - kb_begin);
+
+  const uint8_t* b_tiles = p.b_planes + ((int64_t)(n0 / C_::BN) * p.b_planes_nkb + kb_begin) * (int64_t)C_::B_BYTES;
+  const int q = warp & 3, part = warp >> 2;   // TMEM lane quarter; k columns part * 8 .. + 8 of a stage, accumulator columns part * 64 ..
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+  const bool rok = m0 + q * 32 + lane < opA.rows;
+  const float* arow = opA.base + (rok ? opA.roff[m0 + q * 32 + lane] : 0);
+  float av[8];
+  auto fetch = [&](int it) {      // this thread's 8 values of stage it: row q * 32 + lane, k = (kb_begin + it) * BK + part * 8 ..
+    const int k0 = (kb_begin + it) * BK + part * 8;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int kg = k0 + g * 4;
+      if (A_MODE == 2) {          // 4-aligned k groups are contiguous and 16-byte aligned; K % 4 == 0
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rok && kg < p.K) t = __ldg(reinterpret_cast<const float4*>(arow + opA.koff[kg]));
+        av[g * 4 + 0] = t.x; av[g * 4 + 1] = t.y; av[g * 4 + 2] = t.z; av[g * 4 + 3] = t.w;
+      } else {                    // lanes sit on consecutive rows (contiguous in memory): coalesced scalar loads
+        int64_t ko[4];
+        bool kok[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          kok[j] = kg + j < p.K;
+          ko[j] = kok[j] ? opA.koff[kg + j] : 0;
+        }
+        const bool kcontig = kok[3] && (ko[1] - ko[0]) == 1 && (ko[2] - ko[0]) == 2 && (ko[3] - ko[0]) == 3;
+        if (kcontig) {            // warp-uniform: one address, immediate offsets
+          const float* src = arow + ko[0];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) av[g * 4 + j] = rok ? __ldg(src + j) : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) av[g * 4 + j] = (rok && kok[j]) ? __ldg(arow + ko[j]) : 0.f;
+        }
+      }
+    }
+  };
+  auto load_b = [&](int it) {     // thread 0 only
+    const int sb = it % C_::NS;
+    bulk_load(smem_u32(smem + sb * C_::B_BYTES), b_tiles + (int64_t)it * C_::B_BYTES, C_::B_BYTES, smem_u32(&bars[4 + sb]));
+  };
+  if (nkb > 0) {
+    if (threadIdx.x == 0) { load_b(0); if (nkb > 1) load_b(1); }
+    fetch(0);
+  }
+  constexpr int NACC = C_::BN / NPART;
+  float acc[NACC];
+#pragma unroll
+  for (int j = 0; j < NACC; ++j) acc[j] = 0.f;
+  int n_drained = 0;
+
+  for (int it = 0; it < nkb; ++it) {
+    const int s = it % C_::NS;
+    if (it >= C_::NS) mbar_wait(smem_u32(&bars[s]), (uint32_t)(((it / C_::NS) - 1) & 1));   // stage s (A in TMEM, B in smem) is free
+    {
+      float hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_tf32(av[j], hi[j], lo[j]);
+      tmem_st8(lane_addr + C_::COL_A + s * 64 + part * 8, hi);
+      tmem_st8(lane_addr + C_::COL_A + s * 64 + 32 + part * 8, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    const bool chunk_first = (it % DRAIN) == 0;
+    const bool chunk_last = ((it + 1) % DRAIN) == 0 || it == nkb - 1;
+    if (threadIdx.x == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      mbar_wait(smem_u32(&bars[4 + s]), (uint32_t)((it / C_::NS) & 1));                     // this stage's B planes have landed
+      const uint32_t b_hi = smem_u32(smem + s * C_::B_BYTES), b_lo = b_hi + C_::B_PLANE;
+      const uint32_t a_hi = tmem_base + C_::COL_A + s * 64, a_lo = a_hi + 32;
+#pragma unroll
+      for (int j = 0; j < BK / 8; ++j) {
+        const uint64_t db_hi = make_desc(b_hi + 2 * j * C_::B_LBO, C_::B_LBO, 128);
+        const uint64_t db_lo = make_desc(b_lo + 2 * j * C_::B_LBO, C_::B_LBO, 128);
+        mma_tf32_ta(tmem_base, a_lo + j * 8, db_hi, Cfg<256>::IDESC, (!chunk_first || j > 0) ? 1u : 0u);
+        mma_tf32_ta(tmem_base, a_hi + j * 8, db_lo, Cfg<256>::IDESC, 1u);
+        mma_tf32_ta(tmem_base, a_hi + j * 8, db_hi, Cfg<256>::IDESC, 1u);
+      }
+      mma_commit(smem_u32(&bars[s]));
+      if (chunk_last) mma_commit(smem_u32(&bars[3]));
+      if (it + 2 < nkb) {       // buffer (it + 2) % NS was last read by stage it - 1
+        const int s2 = (it + 2) % C_::NS;
+        if (it >= 1) mbar_wait(smem_u32(&bars[s2]), (uint32_t)(((it - 1) / C_::NS) & 1));
+        load_b(it + 2);
+      }
+    }
+    if (it + 1 < nkb) fetch(it + 1);   // next stage's global loads fly while this stage's MMAs run
+    if (chunk_last) {
+      mbar_wait(smem_u32(&bars[3]), (uint32_t)(n_drained & 1));
+      ++n_drained;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int cc = 0; cc < NACC / 32; ++cc) {
+        float v[32];
+        tmem_ld32(lane_addr + (uint32_t)(part * NACC + cc * 32), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += v[j];
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+  }
+
+  store_tile<NACC>(p, acc, m0, n0, C_::BN, q, lane, part, 0, split_id);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C_::TMEM_COLS) : "memory");
   }
 }
 
@@ -546,10 +731,27 @@ inline cudaError_t launch_variant(const TcGemmParams& p, int k_splits, cudaStrea
   return cudaGetLastError();
 }
 
+// MVB_TC_TMEMA=0 in the environment keeps the shared-memory A path for the pre-split-B contractions (A/B comparisons).
+inline bool ta_enabled() {
+  static const bool on = [] { const char* e = getenv("MVB_TC_TMEMA"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+template <int AM>
+inline cudaError_t launch_ta(const TcGemmParams& p, int k_splits, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(tc_gemm_ta_kernel<AM>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgTA::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  const unsigned nt = (p.N + CfgTA::BN - 1) / CfgTA::BN, mt = (p.M + BM - 1) / BM;
+  dim3 grid(p.raster_m_fast ? mt : nt, p.raster_m_fast ? nt : mt, k_splits);
+  tc_gemm_ta_kernel<AM><<<grid, NTHREADS, CfgTA::SMEM_BYTES, st>>>(p);
+  return cudaGetLastError();
+}
+
 template <int BN, int AM>
 inline cudaError_t launch_b(const TcGemmParams& p, int k_splits, cudaStream_t st) {
   if (p.b_planes) {
     if (BN != 256 || p.batch > 1 || p.symmetric) return cudaErrorInvalidValue;
+    if (AM != 1 && ta_enabled()) return launch_ta<AM == 1 ? 0 : AM>(p, k_splits, st);
     return launch_variant<256, AM, 3>(p, k_splits, st);
   }
   switch (p.B.lanes_along_k) {
