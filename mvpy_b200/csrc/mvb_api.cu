@@ -174,8 +174,9 @@ int run_contract(const mvb_operand& A, const mvb_operand& B, int M, int N, int K
     // and every stage's B half then arrives by one TMA bulk copy instead of LDG -> split -> STS in the 512 threads,
     // which is the bound of this kernel (profiles/r01_tc_gemm2_notes.md); worth one extra pass over B when M is large.
     static const bool planes_on = [] { const char* e = getenv("MVB_TC_PLANES"); return !e || atoi(e) != 0; }();
-    if (planes && planes_on && !symmetric && N > 128 && M >= 1024 && (double)M * N * K >= 4e9 &&
-        planes_bytes >= mvb::tc_planes_bytes(N, K)) {
+    // (a symmetric product -- the Gram of the implicit design -- only on the TMEM-A kernel, which takes A gathers 0 and 2)
+    if (planes && planes_on && (!symmetric || (mvb::tc::ta_enabled() && A.contig != 1)) && N > 128 && M >= 1024 &&
+        (double)M * N * K >= 4e9 && planes_bytes >= mvb::tc_planes_bytes(N, K)) {
       MVB_CUDA(mvb::tc_presplit_launch(p.B, K, (uint8_t*)planes, st));
       g_launches.fetch_add(1, std::memory_order_relaxed);
       p.b_planes = (const uint8_t*)planes;
@@ -214,6 +215,7 @@ struct StatsWs {
   int64_t *row_off, *col_off, *yrow_off, *ycol_off;
   double *partial, *mu64, *ybar64;
   void* contract_ws; size_t contract_bytes;
+  void* planes; size_t planes_bytes;      // pre-split TF32 planes of the design (Gram) / of y (X^T y), large fp32 problems only
   int parts;
 };
 
@@ -232,6 +234,9 @@ size_t carve_stats(Arena& ar, const mvb_design* d, int F, StatsWs& w) {
   size_t cb = std::max(plan_contract((int)p, (int)p, (int)n, dt, 1).ws_elems, plan_contract((int)p, F, (int)n, dt, 0).ws_elems) * sizeof(T);
   w.contract_bytes = cb;
   w.contract_ws = ar.take<char>(cb);
+  w.planes_bytes = (sizeof(T) == 4 && p >= 1024 && !force_simt())
+                       ? std::max(mvb::tc_planes_bytes((int)p, (int)n), mvb::tc_planes_bytes(F, (int)n)) : 0;
+  w.planes = w.planes_bytes ? ar.take<char>(w.planes_bytes) : nullptr;
   return ar.off;
 }
 
@@ -268,9 +273,9 @@ int trf_stats_impl(const mvb_design* d, const T* y, int F, int fit_intercept, T*
   const bool y_vec = sizeof(T) == 4 && Tn % 4 == 0 && ((uintptr_t)y & 15) == 0;
   mvb_operand yc{y, w.ycol_off, w.yrow_off, F, y_vec ? 2 : 1};
   int rc;
-  { ProfScope ps(PC_GRAM); rc = run_contract<T>(xc, xc, (int)p, (int)p, (int)n, G, p, 1, w.contract_ws, w.contract_bytes, st); }
+  { ProfScope ps(PC_GRAM); rc = run_contract<T>(xc, xc, (int)p, (int)p, (int)n, G, p, 1, w.contract_ws, w.contract_bytes, st, 0, 0, w.planes, w.planes_bytes); }
   if (rc) return rc;
-  { ProfScope ps(PC_XTY); rc = run_contract<T>(xc, yc, (int)p, F, (int)n, XtY, F, 0, w.contract_ws, w.contract_bytes, st); }
+  { ProfScope ps(PC_XTY); rc = run_contract<T>(xc, yc, (int)p, F, (int)n, XtY, F, 0, w.contract_ws, w.contract_bytes, st, 0, 0, w.planes, w.planes_bytes); }
   if (rc) return rc;
   if (fit_intercept) {
     mvb::centre_moments_kernel<T><<<grid_for(p * p + p * F), 256, 0, st>>>(G, p, XtY, F, w.mu64, w.ybar64, (double)n);

@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
 // (tcgen05.st); the MMAs take A from TMEM (the [a_tmem] operand form) and shared memory carries only B (one 64 KB bulk copy
 // in, 96 KB of MMA reads per stage).  The shared memory this frees holds a third B stage, so a stage's copy is issued two
 // stages of MMAs ahead.  TMEM columns: 0..255 accumulator, 256 + 64 s: stage s of A (hi at +0, lo at +32).
-// 256-wide tiles, batch == 1, not symmetric, A gathers 0 and 2 (mode 1 would need a transposing load; it keeps the
+// 256-wide tiles, batch == 1, A gathers 0 and 2 (mode 1 would need a transposing load; it keeps the
 // shared-memory kernel).  Measured (tools/experimental/tc_gemm_tmema_test): dense 8192^3 214 TFLOP/s against 141.
 struct CfgTA {
   static constexpr int BN = 256, NS = 3;
@@ -545,6 +545,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_ta_kernel(const TcGemmPar
   extern __shared__ __align__(1024) uint8_t smem[];
   const int m0 = (p.raster_m_fast ? blockIdx.x : blockIdx.y) * BM;
   const int n0 = (p.raster_m_fast ? blockIdx.y : blockIdx.x) * C_::BN;
+  if (p.symmetric && n0 > m0 + BM - 1) return;  // strictly above the diagonal: mirrored by the lower tile
   if (p.skip_flag && *p.skip_flag) return;
   const int splits = gridDim.z, split_id = blockIdx.z;
   const GatherOperand opA = p.A;
@@ -750,8 +751,9 @@ inline cudaError_t launch_ta(const TcGemmParams& p, int k_splits, cudaStream_t s
 template <int BN, int AM>
 inline cudaError_t launch_b(const TcGemmParams& p, int k_splits, cudaStream_t st) {
   if (p.b_planes) {
-    if (BN != 256 || p.batch > 1 || p.symmetric) return cudaErrorInvalidValue;
+    if (BN != 256 || p.batch > 1) return cudaErrorInvalidValue;
     if (AM != 1 && ta_enabled()) return launch_ta<AM == 1 ? 0 : AM>(p, k_splits, st);
+    if (p.symmetric) return cudaErrorInvalidValue;      // symmetric products with pre-split planes: TMEM-A kernel only
     return launch_variant<256, AM, 3>(p, k_splits, st);
   }
   switch (p.B.lanes_along_k) {

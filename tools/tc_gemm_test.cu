@@ -146,6 +146,8 @@ int main(int argc, char** argv) {
     fails += run_case("toeplitz gram sym bn256", G1, G1, p, p, K, 256, 1, 1);
     fails += run_case("toeplitz gram sym bn128 s2", G0, G0, p, p, K, 128, 2, 1);
     fails += run_case("toeplitz gram mixed", G1, G0, p, p, K, 256, 1, 0);
+    fails += run_case("toeplitz gram sym x planes", G0, G0, p, p, K, 256, 1, 1, 1);
+    fails += run_case("toeplitz gram sym x planes s2", G0, G0, p, p, K, 256, 2, 1, 1);
     HostOp D = dense_op(700, K, 1);      // K = 450 is not a multiple of 4: scalar (mode 1) source
     fails += run_case("toeplitz x dense planes", G0, D, p, 700, K, 256, 1, 0, 1);
     fails += run_case("toeplitz(k) x dense planes s2", G1, D, p, 700, K, 256, 2, 0, 1);
