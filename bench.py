@@ -352,14 +352,15 @@ def main():
         tot_fl = sum(v['flops'] for v in prof.values())
         tot_n = sum(v['n'] for v in prof.values())
         achieved = tot_fl / (tot_ms * 1e-3) * 1e-12 if tot_ms > 0 else 0.0
-        roof = dict(bound='tensor', kernel='tc::tc_gemm_kernel (all contraction launches of the step)', achieved=achieved,
+        roof = dict(bound='tensor', kernel='tc::tc_gemm_ta_kernel + tc::tc_gemm_kernel (all contraction launches of the step)', achieved=achieved,
                     peak=peak_eff, unit='TFLOP/s', frac=achieved / peak_eff, traffic=None, launches=tot_n, ms_total=tot_ms,
                     share_of_step=tot_ms / ms,
                     note=f'algorithmic 2*M*N*K flops (symmetric Gram counted once) / CUDA-event time of the launches, recorded by '
                          f'the library hook on the launching stream inside the timed region; peak = TF32 dense peak measured '
                          f'here with cuBLAS ({tf32_peak:.0f} TFLOP/s) / 3 MMAs per fp32 product (split-TF32); '
                          f'MEASURED_PEAKS bf16 = {peaks.get("bf16_tflops")} burst / {peaks.get("bf16_tflops_sustained")} sustained; '
-                         f'traffic: see profiles/ (ncu --set full of the Gram launch: dram 635 MB vs 677 MB algorithmic)',
+                         f'traffic per role (by_kernel) from profiles/r01_traffic.json: ncu of the TMEM-A kernel, Z launch dram 4.16 GB vs 3.35 GB '
+                         f'algorithmic, Gram launch 6.14 GB vs 4.7 GB of operand bytes (4 GB of pre-split design planes)',
                     by_kernel={k: dict(ms=v['ms'], n=v['n'], tflops=(v['flops'] / (v['ms'] * 1e-3) * 1e-12 if v['ms'] > 0 else 0.0),
                                        frac=(v['flops'] / (v['ms'] * 1e-3) * 1e-12 / peak_eff if v['ms'] > 0 else 0.0))
                                for k, v in prof.items()})
@@ -370,6 +371,8 @@ def main():
                 if k in roof['by_kernel']:
                     roof['by_kernel'][k]['traffic'] = v['dram_bytes_per_launch']
                     roof['by_kernel'][k]['algorithmic_bytes'] = v['algorithmic_bytes_per_launch']
+                    if 'operand_bytes_per_launch' in v:
+                        roof['by_kernel'][k]['operand_bytes'] = v['operand_bytes_per_launch']
         except Exception:
             pass
     # ---- HBM-bound leg of the path: the fused r2 + pearson scoring kernel on one test fold (CUDA events, 50 launches) ----

@@ -181,6 +181,10 @@ int run_contract(const mvb_operand& A, const mvb_operand& B, int M, int N, int K
       g_launches.fetch_add(1, std::memory_order_relaxed);
       p.b_planes = (const uint8_t*)planes;
       p.b_planes_nkb = (K + mvb::tc::BK - 1) / mvb::tc::BK;
+      // Gram of the design: the planes (8 n p bytes, 4 GB at cfg2) exceed L2, the implicit A operand does not.  Consecutive
+      // CTAs walk the M tiles of one N tile so that a plane tile is streamed from HBM once, not once per wave
+      // (ncu of the N-fastest order: 50 GB of dram reads for this launch, profiles/r01_ncu_full_tmema.md)
+      if (symmetric) p.raster_m_fast = 1;
     }
     const int slot = prof_begin(2.0 * M * (double)N * K * (symmetric ? 0.5 : 1.0), st);
     MVB_CUDA(mvb::tc_gemm_launch(p, pl.splits, N > 128 ? 256 : 128, st));
