@@ -17,7 +17,10 @@
 // staged by the CTA's threads straight into the UMMA canonical K-major
 // no-swizzle layout (8x16B core matrices; LBO padded by 16 B so the stores are
 // bank-conflict free), double buffered, with tcgen05.commit -> mbarrier
-// releasing a buffer back to the loaders.
+// releasing a buffer back to the loaders (tc_gemm_kernel).
+// Products whose B operand is handed over as pre-split planes (TcGemmParams::b_planes) run on tc_gemm_ta_kernel instead:
+// A is split in registers and written to tensor memory (tcgen05.st), the MMAs read it from there, and shared memory
+// holds a three-stage ring of B plane tiles filled by TMA bulk copies.
 #pragma once
 #include <cuda_runtime.h>
 #include <algorithm>

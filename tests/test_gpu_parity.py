@@ -741,3 +741,32 @@ def test_predictor_sets_share_fold_statistics(monkeypatch):
         assert torch.equal(out['0'][2], out['1'][2])
         np.testing.assert_allclose(out['1'][0].cpu().numpy(), out['0'][0].cpu().numpy(), rtol=0, atol=2e-5)
         np.testing.assert_allclose(out['1'][1].cpu().numpy(), out['0'][1].cpu().numpy(), rtol=0, atol=4e-5)
+
+
+def test_stats_tmem_a_planes_path_vs_fp64():
+    """A design with p = 1206 >= 1024 columns and 2 p^2 n = 1.4e10 flop, so that mvb_trf_stats runs the symmetric Gram on the
+    TMEM-A contraction kernel against the design pre-split into planes (tc_gemm.cuh: tc_gemm_ta_kernel, lower tiles + mirror,
+    M-fastest tile order); checked against the same entry point in fp64 (CUDA-core contraction) and against a materialised
+    lag expansion (reference: timedelayed.py:394-431 + ridgecv.py:59-94)."""
+    mv = _mv()
+    from mvpy_b200 import _lib
+    g = torch.Generator().manual_seed(5)
+    N, C, Tn, F = 12, 6, 400, 7
+    X = torch.randn(N, C, Tn, generator=g).cuda()
+    y = torch.randn(N, F, Tn, generator=g).cuda()
+    td = mv.estimators.TimeDelayed(-1.0, 0.0, 200, alphas=torch.tensor([1.0]))
+    p, n = C * 201, N * Tn
+    for icpt in (True, False):
+        G32, b32, mu32, yb32 = _lib.trf_stats(td._design(X), y, icpt)
+        G64, b64, mu64, yb64 = _lib.trf_stats(td._design(X.double()), y.double(), icpt)
+        assert G32.shape == (p, p) and G32.dtype == torch.float32
+        scale = float(G64.abs().max())
+        assert float((G32.double() - G64).abs().max()) / scale < 3e-6
+        assert float((G32 - G32.mT).abs().max()) / scale < 1e-6
+        assert float((b32.double() - b64).abs().max()) / float(b64.abs().max()) < 3e-6
+        np.testing.assert_allclose(mu32.cpu().numpy(), mu64.cpu().numpy(), rtol=0, atol=1e-6)
+    # fp64 statistics against the explicit design: X_t[(trial, t), (c, w)] = X[trial, c, clamp(t + lag_w)]
+    lags = torch.arange(-200, 1, device='cuda')
+    tt = (torch.arange(Tn, device='cuda')[None, :] + lags[:, None]).clamp(0, Tn - 1)           # (W, T)
+    Xt = X.double()[:, :, tt].permute(0, 3, 1, 2).reshape(n, p)
+    assert float((G64 - Xt.mT @ Xt).abs().max()) / float(G64.abs().max()) < 1e-12
