@@ -11,6 +11,15 @@
 // pre-split into planes (8 * 128 * K bytes = 13 MB, L2-resident) and delivered by TMA into a four-stage ring; the accumulator
 // tile (rows = rows of G) is stored transposed so that the output keeps the [128][N] layout the reduction expects.
 // Expected bound: HBM (0.67 GB / ~6.5 TB/s = 0.10 ms per product) instead of 0.41 ms.
+//
+// Integration plan once measured (lanczos_band.cuh, `gemm()`: every call there has M = NB = 128):
+//   * W = Q_j Gp (N = K = P), H = W Qt^T (N = nq, K = P) and W -= H Q (N = P, K = nq; via the partial-sum buffer with
+//     subtract) all have a dense row-major B with ld = P: pass base / ld instead of the gather tables, pre-split the 128-row
+//     A block per call (13 MB, ~10 us) into a scratch of planes128_bytes(P), launch skinny_kernel with the split count from
+//     tc_choose_splits(tiles = N / 128, ...), keep reduce_parts_kernel as it is (the transposed store writes the same
+//     [split][128][N] layout).  The Gp / Qt / Q^T plane copies (3 x 1.34 GB and their incremental presplit launches) go away.
+//   * add `const unsigned int* skip_flag` (early return, as in tc_gemm_ta_kernel) for the conditional clean-up rounds.
+//   * ragged N (nq is a multiple of 128; P is padded to 128) needs no edge code; K = nq is a multiple of 128 as well.
 #pragma once
 #include "../../mvpy_b200/csrc/tc_gemm.cuh"
 
