@@ -1,5 +1,6 @@
-// tc_gemm_skinny.cuh -- EXPERIMENT (not measured yet: written at the end of r01 after the GPU budget was spent; build with
-// `make -C tools tc_gemm_skinny_test`, run on a B200 first thing in r02).
+// tc_gemm_skinny.cuh -- EXPERIMENT, OFF BY DEFAULT (not measured yet: written at the end of r01 after the GPU budget was spent).
+// Standalone check: `make -C tools tc_gemm_skinny_test`, run on a B200 first thing in r02; in the library it is used by the
+// block-Lanczos reduction only when MVB_LB_SKINNY=1 is set (lanczos_band.cuh, gemm()).
 //
 //   W[128][N] = Q[128][K] * G[N][K]^T        (the block-Lanczos products: one 128-row block against a large dense matrix)
 //
@@ -12,16 +13,14 @@
 // tile (rows = rows of G) is stored transposed so that the output keeps the [128][N] layout the reduction expects.
 // Expected bound: HBM (0.67 GB / ~6.5 TB/s = 0.10 ms per product) instead of 0.41 ms.
 //
-// Integration plan once measured (lanczos_band.cuh, `gemm()`: every call there has M = NB = 128):
-//   * W = Q_j Gp (N = K = P), H = W Qt^T (N = nq, K = P) and W -= H Q (N = P, K = nq; via the partial-sum buffer with
-//     subtract) all have a dense row-major B with ld = P: pass base / ld instead of the gather tables, pre-split the 128-row
-//     A block per call (13 MB, ~10 us) into a scratch of planes128_bytes(P), launch skinny_kernel with the split count from
-//     tc_choose_splits(tiles = N / 128, ...), keep reduce_parts_kernel as it is (the transposed store writes the same
-//     [split][128][N] layout).  The Gp / Qt / Q^T plane copies (3 x 1.34 GB and their incremental presplit launches) go away.
-//   * add `const unsigned int* skip_flag` (early return, as in tc_gemm_ta_kernel) for the conditional clean-up rounds.
-//   * ragged N (nq is a multiple of 128; P is padded to 128) needs no edge code; K = nq is a multiple of 128 as well.
+// Integration (lanczos_band.cuh, `gemm()`: every call there has M = NB = 128): W = Q_j Gp (N = K = P), H = W Qt^T (N = nq,
+// K = P) and W -= H Q (N = P, K = nq; via the partial-sum buffer with subtract) all have a dense row-major B with ld = P.
+// With MVB_LB_SKINNY=1 the large ones pre-split their 128-row A block per call (13 MB) into the scratch that otherwise holds
+// the Gp planes and launch skinny_kernel with the split count from tc_choose_splits(tiles = N / 128, ...); reduce_parts_kernel
+// is unchanged (the transposed store writes the same [split][128][N] layout).  Once measured faster, the Gp / Qt / Q^T plane
+// copies (3 x 1.34 GB and their incremental presplit launches) can go.
 #pragma once
-#include "../../mvpy_b200/csrc/tc_gemm.cuh"
+#include "tc_gemm.cuh"
 
 namespace mvb {
 namespace skinny {
@@ -38,7 +37,9 @@ constexpr uint32_t COL_A = 128, TMEM_COLS = 512;             // accumulator: col
 constexpr int NACC = BNQ / NPART;                            // 32 accumulator columns per thread
 
 // Q (128 x K, row-major, ld) -> planes[kb][plane][kc * Q_LBO + r * 16 + (k % 4) * 4]; K % 32 == 0
-__global__ void presplit128_kernel(const float* __restrict__ Q, int64_t ld, int K, uint8_t* __restrict__ planes) {
+__global__ void presplit128_kernel(const float* __restrict__ Q, int64_t ld, int K, uint8_t* __restrict__ planes,
+                                   const unsigned int* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag) return;
   const int64_t total = (int64_t)BNQ * (K / 4);
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int c4 = (int)(e % (K / 4)), r = (int)(e / (K / 4));      // consecutive threads: consecutive 16-byte chunks of one row
@@ -58,8 +59,10 @@ __global__ void presplit128_kernel(const float* __restrict__ Q, int64_t ld, int 
 
 // grid = (N / 128, splits); W + split * w_split_stride receives the partial sum of the split's K range
 __global__ void __launch_bounds__(NTHREADS, 1) skinny_kernel(const float* __restrict__ G, int64_t ldg, const uint8_t* __restrict__ Qplanes,
-                                                             float* __restrict__ W, int64_t ldw, int64_t w_split_stride, int N, int K) {
+                                                             float* __restrict__ W, int64_t ldw, int64_t w_split_stride, int N, int K,
+                                                             const unsigned int* __restrict__ skip_flag) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  if (skip_flag && *skip_flag) return;          // the whole launch is a no-op (conditional clean-up rounds)
   const int n0 = blockIdx.x * BM;
   const int splits = gridDim.y, split_id = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -175,19 +178,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) skinny_kernel(const float* __rest
 
 inline size_t planes128_bytes(int K) { return (size_t)(K / BK) * Q_BYTES; }
 
-inline cudaError_t presplit128_launch(const float* Q, int64_t ld, int K, uint8_t* planes, cudaStream_t st) {
+inline cudaError_t presplit128_launch(const float* Q, int64_t ld, int K, uint8_t* planes, cudaStream_t st,
+                                      const unsigned int* skip_flag = nullptr) {
   if (K % BK) return cudaErrorInvalidValue;
-  presplit128_kernel<<<148, 256, 0, st>>>(Q, ld, K, planes);
+  presplit128_kernel<<<148, 256, 0, st>>>(Q, ld, K, planes, skip_flag);
   return cudaGetLastError();
 }
 
 // W[split][128][ldw] partial sums; N % 128 == 0, K % 32 == 0
 inline cudaError_t skinny_launch(const float* G, int64_t ldg, const uint8_t* Qplanes, float* W, int64_t ldw, int64_t w_split_stride,
-                                 int N, int K, int splits, cudaStream_t st) {
+                                 int N, int K, int splits, cudaStream_t st, const unsigned int* skip_flag = nullptr) {
   if (N % BM || K % BK || splits < 1) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  skinny_kernel<<<dim3(N / BM, splits), NTHREADS, SMEM_BYTES, st>>>(G, ldg, Qplanes, W, ldw, w_split_stride, N, K);
+  skinny_kernel<<<dim3(N / BM, splits), NTHREADS, SMEM_BYTES, st>>>(G, ldg, Qplanes, W, ldw, w_split_stride, N, K, skip_flag);
   return cudaGetLastError();
 }
 
