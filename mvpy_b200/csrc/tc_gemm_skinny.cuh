@@ -11,7 +11,11 @@
 // PF stages of loads in flight per thread, split in registers and written to tensor memory; the 128-row block Q is the B operand,
 // pre-split into planes (8 * 128 * K bytes = 13 MB, L2-resident) and delivered by TMA into a four-stage ring; the accumulator
 // tile (rows = rows of G) is stored transposed so that the output keeps the [128][N] layout the reduction expects.
-// Expected bound: HBM (0.67 GB / ~6.5 TB/s = 0.10 ms per product) instead of 0.41 ms.
+// Expected: HBM needs 0.67 GB / ~6.5 TB/s = 0.10 ms per product; the tensor pipe at the TF32 rate cuBLAS reaches here (738 TFLOP/s,
+// i.e. ~103 cycles per 128 x 128 x 8 MMA, 12 per stage) needs ~0.18 ms with all SMs busy -- against 0.41 ms measured now.
+// Open question for the measurement: each lane reads its own row (32 B per row per warp load, the four column parts of a stage
+// make up one 128-byte line from four warps); if HBM efficiency suffers, let warp group g own whole stages it = g (mod 4)
+// (one 128-byte line per lane, tcgen05.st x32) with a per-group mbarrier instead of the block barrier.
 //
 // Integration (lanczos_band.cuh, `gemm()`: every call there has M = NB = 128): W = Q_j Gp (N = K = P), H = W Qt^T (N = nq,
 // K = P) and W -= H Q (N = P, K = nq; via the partial-sum buffer with subtract) all have a dense row-major B with ld = P.
