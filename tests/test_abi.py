@@ -59,3 +59,27 @@ def test_product_does_not_import_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+[\w.]*oracle', src, flags=re.M), f'{f} imports the oracle'
+
+
+def test_stats_workspace_carries_design_planes_for_large_fp32_problems():
+    """mvb_trf_stats_workspace_bytes is host-only arithmetic: for fp32 designs with p >= 1024 columns it includes the
+    pre-split TF32 planes of the design (8 bytes per entry of the 256-row x 32-k tiled lag expansion, the B operand of
+    the Gram on the TMEM-A contraction kernel); fp64 and small designs do not pay for them."""
+    from mvpy_b200 import _lib
+    lib = _lib.load()
+
+    def ws(n_trials, n_feat, n_time, n_lag, dtype, F=7):
+        d = _lib.mvb_design(0x1000, n_feat * (n_time + n_lag - 1), n_time + n_lag - 1, n_time, n_lag, None, n_trials, None,
+                            n_feat, dtype)          # xp is never dereferenced by the size query
+        return lib.mvb_trf_stats_workspace_bytes(ctypes.byref(d), F)
+
+    n, p = 12 * 400, 6 * 201
+    tiles, stages = -(-p // 256), -(-n // 32)
+    planes = tiles * stages * 2 * 8 * (256 * 16 + 16)
+    big32, big64 = ws(12, 6, 400, 201, 0), ws(12, 6, 400, 201, 1)
+    assert big32 >= planes and big32 - planes < 64 << 20
+    assert big64 < planes                                    # fp64 runs on the CUDA-core contraction: no planes
+    assert ws(12, 5, 400, 201, 0) < planes // 2              # p = 1005 < 1024: shared-memory kernel, no planes
+    # BASELINE configs[1]: 51 tiles x 1200 stages x 65 792 B = 4.03 GB on top of the split-K scratch
+    cfg2 = ws(96, 64, 400, 201, 0, F=306)
+    assert 51 * 1200 * 65792 <= cfg2 < 51 * 1200 * 65792 + (2 << 30)
