@@ -373,6 +373,10 @@ def main():
                     roof['by_kernel'][k]['algorithmic_bytes'] = v['algorithmic_bytes_per_launch']
                     if 'operand_bytes_per_launch' in v:
                         roof['by_kernel'][k]['operand_bytes'] = v['operand_bytes_per_launch']
+            zk = 'Z = X Q^T (leverages)'        # the largest single launch of the step: its ncu dram bytes stand for the kernel
+            if zk in tr and zk in roof['by_kernel']:
+                roof['traffic'] = tr[zk]['dram_bytes_per_launch']
+                roof['traffic_of'] = f'{zk}: one launch, algorithmic bytes {tr[zk]["algorithmic_bytes_per_launch"]}'
         except Exception:
             pass
     # ---- HBM-bound leg of the path: the fused r2 + pearson scoring kernel on one test fold (CUDA events, 50 launches) ----
