@@ -1,9 +1,10 @@
 #!/bin/bash
 # First GPU call of the next round: run the two experiments written (but not run) at the end of r01 and re-measure the baseline.
-#   make -C tools tc_gemm_skinny_test tc_gemm_tmema2_test tc_gemm_tmema_test tc_gemm_test      (here, before gpurun)
+#   make -C tools tc_gemm_skinny_test tc_gemm_tmema2_test tc_gemm_tmema_test tc_gemm_test tma_stream_bench      (here, before gpurun)
 #   gpurun --timeout 600 -- 'bash tools/next_round_checks.sh'
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
+timeout 120 tools/tma_stream_bench > gpurun_out/tma_stream_bench.log 2>&1; echo "tma_stream_bench rc=$?"; tail -40 gpurun_out/tma_stream_bench.log
 for t in tc_gemm_skinny_test tc_gemm_tmema2_test tc_gemm_tmema_test; do
   timeout 120 tools/$t perf > gpurun_out/$t.log 2>&1; echo "$t rc=$?"; grep -E "OK|FAIL|perf|PASSED|FAILED|timeout|error" gpurun_out/$t.log | tail -12
 done
