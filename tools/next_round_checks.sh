@@ -4,6 +4,9 @@
 #   gpurun --timeout 600 -- 'bash tools/next_round_checks.sh'
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
+for t in tc_gemm_skinny_test tc_gemm_tmema2_test tc_gemm_tmema_test tc_gemm_test tma_stream_bench; do
+  [ -x tools/$t ] || { echo "tools/$t is not built: run 'make -C tools $t' in the container before gpurun (no nvcc needed on the box, but the binary must travel)"; exit 1; }
+done
 timeout 120 tools/tma_stream_bench > gpurun_out/tma_stream_bench.log 2>&1; echo "tma_stream_bench rc=$?"; tail -40 gpurun_out/tma_stream_bench.log
 for t in tc_gemm_skinny_test tc_gemm_tmema2_test tc_gemm_tmema_test; do
   timeout 120 tools/$t perf > gpurun_out/$t.log 2>&1; echo "$t rc=$?"; grep -E "OK|FAIL|perf|PASSED|FAILED|timeout|error" gpurun_out/$t.log | tail -12
