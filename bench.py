@@ -165,6 +165,84 @@ def cpu_baseline(X, y, alphas, workload: str):
     return dict(value=value, unit='fits/s', cores=threads, kind='port', sample=sample), sec
 
 
+
+# ------------------------------------------------------------------------ the unmodified reference
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
+
+
+def load_reference():
+    """The UNMODIFIED reference package (pip install --target baseline/_ref of /root/reference, see DESIGN.md section 6;
+    __graft_entry__.build() repeats the install when the tree is missing).  Returns (module, None) or (None, reason)."""
+    if not os.path.isdir(os.path.join(REF_DIR, 'mvpy')):
+        return None, 'baseline/_ref/mvpy is missing (run __graft_entry__.build() where /root/reference exists)'
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        import mvpy
+    except Exception as e:                                                            # pragma: no cover
+        return None, f'import of baseline/_ref/mvpy failed: {e!r}'
+    if not os.path.abspath(mvpy.__file__).startswith(os.path.abspath(REF_DIR)):
+        return None, f'mvpy resolved to {mvpy.__file__}, not to baseline/_ref'
+    return mvpy, None
+
+
+class FoldSubset:
+    """Splitter that yields only the folds ``keep`` of a base splitter (reference Validator API: split() + n_splits,
+    mvpy/crossvalidation/validator.py:296-313).  Used to time ONE full-size fold of a 5-fold cross-validation."""
+
+    def __init__(self, base, keep):
+        self.base, self.keep, self.n_splits = base, tuple(keep), len(tuple(keep))
+
+    def split(self, X, y=None, groups=None):
+        for k, pair in enumerate(self.base.split(X, y, groups) if groups is not None else self.base.split(X, y)):
+            if k in self.keep:
+                yield pair
+
+
+def reference_run(mvpy, X, y, alphas, workload: str, folds, device: str = 'cpu'):
+    """One timed call of the reference's own public API -- cross_val_score(make_pipeline(Scaler().to_torch(),
+    TimeDelayed(-1, 0, 200, alphas)), X, y, cv) (mvpy/crossvalidation/cross_val_score.py:84-99, README flow) -- on the
+    folds ``folds`` of the 5-fold split.  Returns (seconds, scores)."""
+    from sklearn.pipeline import make_pipeline
+    Xr, yr, ar = X.to(device), y.to(device), alphas.to(device)
+    pipe = make_pipeline(mvpy.preprocessing.Scaler().to_torch(), mvpy.estimators.TimeDelayed(-1.0, 0.0, 200, alphas=ar))
+    cv = FoldSubset(mvpy.crossvalidation.KFold(n_splits=N_FOLDS), folds) if len(folds) < N_FOLDS else N_FOLDS
+    if device != 'cpu':
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, sc = mvpy.crossvalidation.cross_val_score(pipe, Xr, yr, cv=cv)
+    if device != 'cpu':
+        torch.cuda.synchronize()
+    return time.perf_counter() - t0, sc
+
+
+def reference_arm(X, y, alphas, workload: str, steps: int, budget_s: float, device: str = 'cpu'):
+    """cfg1: whole 5-fold cross-validations; cfg2: one full-size fold per sample (fold 0; every fold has the same shape:
+    96 training trials -> n = 38 400 rows x p = 12 864 columns; SURVEY 8d allows 'one fold x 5'), no feature sub-sampling,
+    no cost law.  Samples are repeated up to ``steps`` times while the time budget lasts; the value is the MEAN."""
+    mvpy, why = load_reference()
+    if mvpy is None:
+        return None, why
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    folds = tuple(range(N_FOLDS)) if workload == 'cfg1' else (0,)
+    secs, t_start = [], time.perf_counter()
+    for _ in range(max(1, steps)):
+        sec, _ = reference_run(mvpy, X, y, alphas, workload, folds, device)
+        secs.append(sec)
+        if time.perf_counter() - t_start + sec > budget_s:
+            break
+    mean = float(np.mean(secs))
+    value = len(folds) * N_ALPHAS / mean
+    where = f'{threads} host threads' if device == 'cpu' else f'device {device} (cuSOLVER / cuBLAS through torch)'
+    sample = (f'unmodified reference (baseline/_ref) cross_val_score(make_pipeline(Scaler, TimeDelayed)), {len(folds)} of {N_FOLDS} folds at '
+              f'full size (n={(X.shape[0] - X.shape[0] // N_FOLDS) * X.shape[2]} rows x p={X.shape[1] * 201} columns, {y.shape[1]} channels, '
+              f'{N_ALPHAS} alphas), {len(secs)} sample(s) of {", ".join(f"{s:.1f}" for s in secs)} s on {where}; '
+              f'value = folds x alphas / mean seconds (every fold has the same shape)')
+    return dict(value=value, unit='fits/s', cores=threads if device == 'cpu' else 0, kind='reference', sample=sample,
+                seconds=secs, folds=len(folds), device=device), None
+
+
 # ------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -174,6 +252,8 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=list(WORKLOADS))
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--reference-budget', type=float, default=240.0, help='seconds of reference samples (--impl reference)')
+    ap.add_argument('--no-reference-cuda', action='store_true', help='--impl reference: skip the device=cuda incumbent')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -192,19 +272,40 @@ def main():
         if rank != 0:
             return
         X, y = make_data(args.workload)
-        steps = max(1, args.steps)
+        base = dict(metric='TRF ridge fits/s (folds x alphas x sets)', unit='fits/s', impl='reference', n_gpus=args.gpus,
+                    higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', config=config)
+        if args.workload in ('cfg1', 'cfg2'):
+            # the unmodified reference through its own public API on the stated configuration.  A step of this arm is one
+            # bounded sample: a whole cross-validation at cfg1, ONE full-size fold at cfg2 (minutes of CPU time), repeated
+            # while the time budget lasts -- so steps / warmup differ from the GPU arm's (a LAPACK SVD has no warm-up
+            # effect worth minutes; the first sample is kept).
+            cb, why = reference_arm(X, y, alphas, args.workload, args.steps, args.reference_budget)
+            if cb is None:
+                print(json.dumps(dict(impl='reference', unavailable=why)))
+                return
+            line = dict(base, value=cb['value'], steps=len(cb['seconds']), warmup=0, steps_requested=args.steps,
+                        ms_per_step=1e3 * float(np.mean(cb['seconds'])), cpu_baseline=cb,
+                        e2e=dict(value=cb['value'], unit='fits/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                        note='one step = one bounded sample of the workload (see cpu_baseline.sample); value = mean over samples')
+            if torch.cuda.is_available() and not args.no_reference_cuda:
+                # the same-box GPU incumbent: the same unmodified reference with its tensors on device='cuda'
+                try:
+                    reference_run(load_reference()[0], X[:10], y[:10], alphas, args.workload, (0,), 'cuda')      # CUDA / cuSOLVER init
+                    gb, why = reference_arm(X, y, alphas, args.workload, 1, 0.0, 'cuda')
+                    line['reference_cuda'] = gb if gb is not None else dict(unavailable=why)
+                except Exception as e:                                                  # pragma: no cover
+                    line['reference_cuda'] = dict(unavailable=repr(e)[:300])
+            print(json.dumps(line))
+            return
+        # cfg3 / cfg4 / cfg5: the oracle port on a bounded sample (kind = "port"), extrapolation stated in the sample text
+        steps = max(1, min(args.steps, 2))
         secs = []
-        for _ in range(min(args.warmup, 1)):
-            cpu_baseline(X, y, alphas, args.workload)
         cb = None
         for _ in range(steps):
             cb, sec = cpu_baseline(X, y, alphas, args.workload)
             secs.append(sec)
         value = cb['value']
-        print(json.dumps(dict(metric='TRF ridge fits/s (folds x alphas x sets)', value=value, unit='fits/s', impl='reference',
-                              n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 1), ms_per_step=1e3 * float(np.mean(secs)),
-                              higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                              config=config, cpu_baseline=cb,
+        print(json.dumps(dict(base, value=value, steps=steps, warmup=0, ms_per_step=1e3 * float(np.mean(secs)), cpu_baseline=cb,
                               e2e=dict(value=value, unit='fits/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
         return
 

@@ -147,7 +147,7 @@ class _TimeDelayed_torch(sklearn.base.BaseEstimator):
         shared = self._shared_stats(Xd, yd)
         design, stats = shared if shared is not None else (self._design(Xd), None)
         fit = solve_design(design, yd, _lib.to_device(est.alphas).contiguous(), est.fit_intercept, est.alpha_per_target,
-                           stats=stats, keep_gram=self.patterns)
+                           stats=stats, want_loss=True, keep_gram=self.patterns)
         self._finish_fit(fit, design, yd, out_dev)
         return self
 

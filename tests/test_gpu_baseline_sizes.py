@@ -1,0 +1,207 @@
+"""GPU parity at the BASELINE.json sizes: the CUDA path (public API -> ctypes -> C-ABI) against the oracle.
+
+At configs[1] size (n = 38 400 rows, p = 12 864 columns, 306 channels, 20 alphas) the CPU oracle needs minutes per fold, so
+the oracle runs here in fp64 *on the GPU* through torch (``oracle.ridge_loo_fit_chol``: one Cholesky factorisation per
+alpha, pinned against the reference's fixtures in tests/test_oracle_golden.py).  What is compared is what the reference's
+LOO sweep produces (mvpy/estimators/ridgecv.py:241-256): the LOO loss table (alphas x targets), the chosen alpha,
+the coefficients, and the held-out scores of the cross-validation (validator.py:20-115).
+
+Tolerances (north_star; fp32 CUDA path against the fp64 oracle on the same inputs):
+    chosen alpha                    identical
+    LOO losses                      2e-4 relative
+    coefficients                    1e-4 relative (Frobenius, per fold)
+    held-out r2 / pearson           1e-5 absolute
+Set MVB_SKIP_LARGE=1 to skip this file (about three minutes on one B200)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from sklearn.pipeline import make_pipeline
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get('MVB_SKIP_LARGE', '0') == '1', reason='MVB_SKIP_LARGE=1')]
+
+ALPHAS = torch.logspace(-5, 5, 20)
+TOL_LOSS, TOL_COEF, TOL_SCORE = 2e-4, 1e-4, 1e-5
+
+
+def _mv():
+    import mvpy_b200 as mv
+    return mv
+
+
+def _orc():
+    from oracle import mvpy_oracle as orc
+    return orc
+
+
+def _pipe(mv):
+    return make_pipeline(mv.preprocessing.Scaler().to_torch(), mv.estimators.TimeDelayed(-1.0, 0.0, 200, alphas=ALPHAS))
+
+
+_DATA = {}
+
+
+def _cfg2_data():
+    """BASELINE configs[1] inputs: torch.manual_seed(0); make_meeg_continuous(fs=200, n_features=64, n_channels=306)."""
+    if 'cfg2' not in _DATA:
+        mv = _mv()
+        torch.manual_seed(0)
+        X, y = mv.dataset.make_meeg_continuous(fs=200, n_features=64, n_channels=306)
+        _DATA['cfg2'] = (X.contiguous(), y.contiguous())
+    return _DATA['cfg2']
+
+
+def _rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+
+def _free():
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def test_cfg2_cross_val_score_vs_fp64_oracle():
+    """configs[1] itself, all five folds: LOO losses (20 x 306 per fold), chosen alphas, coefficients (306 x 64 x 201) and
+    held-out r2 (5 x 306 x 400) of ``cross_val_score`` against the fp64 oracle on the same inputs."""
+    mv, orc = _mv(), _orc()
+    X, y = _cfg2_data()
+    val, sc = mv.crossvalidation.cross_val_score(_pipe(mv), X.cuda(), y.cuda(), cv=5)
+    got_alpha = torch.stack([m[-1].estimator.alpha_ for m in val.model_]).cpu().double()
+    got_loss = torch.stack([m[-1].estimator.loss_ for m in val.model_]).cpu().double()
+    got_coef = [m[-1].coef_.cpu() for m in val.model_]
+    got_icpt = [m[-1].intercept_.cpu().reshape(-1) for m in val.model_]
+    sc = sc.cpu()
+    del val
+    _free()
+    win = orc.lag_window(-1.0, 0.0, 200)
+    Xd, yd = X.cuda().double(), y.cuda().double()
+    worst = dict(loss=0.0, coef=0.0, r2=0.0, icpt=0.0)
+    for k in range(5):                                            # one fold at a time keeps the fp64 design (4 GB) transient
+        ref = orc.cross_val_trf(Xd, yd, win, ALPHAS.cuda().double(), cv=5, solver=orc.ridge_loo_fit_chol, folds=[k])
+        assert float(got_alpha[k]) == float(ref['alpha'][0].float()), (k, float(got_alpha[k]), float(ref['alpha'][0]))
+        loss_ref = ref['losses'][0].cpu()
+        # the selection the reference makes (first minimum of the mean over targets) must be the same on both tables
+        assert int(got_loss[k].mean(1).argmin()) == int(loss_ref.mean(1).argmin())
+        worst['loss'] = max(worst['loss'], ((got_loss[k] - loss_ref).abs() / loss_ref.abs()).max().item())
+        worst['coef'] = max(worst['coef'], _rel(got_coef[k], ref['coef'][0].cpu()))
+        worst['icpt'] = max(worst['icpt'], (got_icpt[k].double() - ref['intercept'][0].cpu().reshape(-1)).abs().max().item())
+        worst['r2'] = max(worst['r2'], (sc[k].double() - ref['r2'][0].cpu()).abs().max().item())
+        del ref
+        _free()
+    print(f'cfg2 vs fp64 oracle, worst over 5 folds: {worst}')
+    assert worst['loss'] < TOL_LOSS, worst
+    assert worst['coef'] < TOL_COEF, worst
+    assert worst['r2'] < TOL_SCORE, worst
+    assert worst['icpt'] < 1e-5, worst
+
+
+def test_mid_size_fold_vs_cpu_oracle():
+    """16 stimulus features x 306 channels (p = 3216): one fold against the CPU oracle's restatement of the reference's own
+    route (centre, thin SVD of [X, 1], LOO sweep; ridgecv.py:206-290) in fp64."""
+    mv, orc = _mv(), _orc()
+    X, y = _cfg2_data()
+    X = X[:, :16].contiguous()
+    tr, te = orc.kfold_indices(X.shape[0], 5)[0]
+    sc = mv.preprocessing.Scaler().to_torch().fit(X[tr].cuda())
+    td = mv.estimators.TimeDelayed(-1.0, 0.0, 200, alphas=ALPHAS).fit(sc.transform(X[tr].cuda()), y[tr].cuda())
+    yh = td.predict(sc.transform(X[te].cuda()))
+    ref = orc.cross_val_trf(X.double(), y.double(), orc.lag_window(-1.0, 0.0, 200), ALPHAS.double(), cv=5, folds=[0],
+                            metrics=('r2', 'pearsonr'))
+    assert float(td.estimator.alpha_) == float(ref['alpha'][0].float())
+    loss_ref = ref['losses'][0]
+    e_loss = ((td.estimator.loss_.cpu().double() - loss_ref).abs() / loss_ref.abs()).max().item()
+    e_coef = _rel(td.coef_.cpu(), ref['coef'][0])
+    r2 = mv.math.r2(y[te].cuda().movedim(0, -1), yh.movedim(0, -1), y[tr].cuda().mean(0, keepdim=True).movedim(0, -1))
+    pr = mv.math.pearsonr(y[te].cuda().movedim(0, -1), yh.movedim(0, -1))
+    e_r2 = (r2.cpu().double() - ref['r2'][0]).abs().max().item()
+    e_pr = (pr.cpu().double() - ref['pearsonr'][0]).abs().max().item()
+    print(f'mid-size fold vs CPU oracle: loss {e_loss:.1e} coef {e_coef:.1e} r2 {e_r2:.1e} pearson {e_pr:.1e}')
+    assert e_loss < TOL_LOSS and e_coef < TOL_COEF and e_r2 < TOL_SCORE and e_pr < TOL_SCORE
+
+
+def _groups3():
+    g = torch.zeros(4, 64)
+    g[:, :16] = 1                     # the baseline block is in every row; rows 1..3 add one block each
+    for r in range(1, 4):
+        g[r, 16 * r:16 * (r + 1)] = 1
+    return g
+
+
+def test_cfg3_hierarchical_sets_vs_fp64_oracle():
+    """configs[2]: hierarchical_score over the 8 unique predictor sets of the cfg2 data.  Set order and masks against the
+    oracle's enumeration; fold 0 of every set (p = 3216 ... 12 864) against the fp64 oracle: chosen alpha and held-out r2."""
+    mv, orc = _mv(), _orc()
+    X, y = _cfg2_data()
+    g3 = _groups3()
+    h, hs = mv.model_selection.hierarchical_score(_pipe(mv), X.cuda(), y.cuda(), groups=g3.cuda(), cv=5)
+    assert hs.shape == (8, 5, 306, 400)
+    sets, masks = orc.group_masks(g3)
+    assert [tuple(s) for s in h.set_] == [tuple(s) for s in sets] == [(0,), (1,), (2,), (3,), (1, 2), (1, 3), (2, 3), (1, 2, 3)]
+    assert torch.equal(torch.stack(h.mask_).cpu(), masks)
+    got_alpha = [float(v.model_[0][-1].estimator.alpha_) for v in h.validator_]
+    hs0 = hs[:, 0].cpu()
+    del h, hs
+    _free()
+    win = orc.lag_window(-1.0, 0.0, 200)
+    Xd, yd = X.cuda().double(), y.cuda().double()
+    worst = 0.0
+    for i, m in enumerate(masks):
+        ref = orc.cross_val_trf(Xd[:, m.cuda()], yd, win, ALPHAS.cuda().double(), cv=5, solver=orc.ridge_loo_fit_chol, folds=[0])
+        assert got_alpha[i] == float(ref['alpha'][0].float()), (i, got_alpha[i], float(ref['alpha'][0]))
+        worst = max(worst, (hs0[i].double() - ref['r2'][0].cpu()).abs().max().item())
+        del ref
+        _free()
+    print(f'cfg3 fold 0 of 8 sets vs fp64 oracle: max |r2 - oracle| = {worst:.2e}')
+    assert worst < TOL_SCORE
+
+
+def test_cfg4_shapley_permutation_vs_fp64_oracle():
+    """configs[3] unit: one Shapley permutation over 8 groups of 8 features (8 nested sets, p = 1608 ... 12 864).  Host
+    tensors -> the CPU generator draws the group / trial orders exactly like the reference (bit-exact ``order_``); fold 0 of
+    the score increments against the fp64 oracle; contributions sum to the full model's score."""
+    mv, orc = _mv(), _orc()
+    X, y = _cfg2_data()
+    groups = torch.eye(8).repeat_interleave(8, 1)
+    torch.manual_seed(1)
+    s, ss = mv.model_selection.shapley_score(_pipe(mv), X, y, groups=groups, cv=5, n_permutations=1)
+    assert ss.shape == (1, 8, 5, 306, 400)
+    full = s.validator_[0][int(s.order_[0][-1])].score_
+    np.testing.assert_allclose(ss.sum(1)[0].numpy(), full.numpy(), atol=2e-6)
+    order, ss0 = s.order_.clone(), ss[0, :, 0].clone()
+    del s, ss
+    _free()
+    torch.manual_seed(1)
+    ref = orc.shapley_trf(X.cuda().double(), y.cuda().double(), groups, orc.lag_window(-1.0, 0.0, 200), ALPHAS.cuda().double(),
+                          n_permutations=1, cv=5, solver=orc.ridge_loo_fit_chol, folds=[0])
+    assert torch.equal(order, ref['order'])
+    err = (ss0.double() - ref['score'][0, :, 0].cpu()).abs().max().item()
+    print(f'cfg4 permutation, fold 0 increments vs fp64 oracle: max abs err = {err:.2e}')
+    assert err < 2 * TOL_SCORE            # an increment is the difference of two scores
+
+
+def test_cfg5_slices_vs_cpu_oracle():
+    """configs[4] shapes (2000 trials x 306 channels -> 3 targets, 20 alphas per target, 5 folds), 8 of the 500 time slices:
+    per (slice, fold) chosen alphas, coefficients, patterns and held-out scores against the CPU oracle in fp64."""
+    mv, orc = _mv(), _orc()
+    torch.manual_seed(0)
+    N, C, T, F = 2000, 306, 8, 3
+    X = torch.randn(N, C, T)
+    B = torch.randn(C, F) * 0.05
+    y = torch.einsum('nct,cf->nft', X, B) * torch.hann_window(500)[::63][:T] + torch.randn(N, F, T)
+    dec = mv.estimators.Sliding(mv.estimators.RidgeDecoder(alphas=ALPHAS), dims=-1)
+    val, sc = mv.crossvalidation.cross_val_score(dec, X.cuda(), y.cuda(), cv=5, metric=(mv.metrics.r2, mv.metrics.pearsonr))
+    assert sc['r2'].shape == (5, F, T)
+    e_coef = e_pat = e_r2 = e_pr = 0.0
+    for k, (tr, te) in enumerate(orc.kfold_indices(N, 5)):
+        fits = orc.sliding_decoder_fit(X[tr].double(), y[tr].double(), ALPHAS.double())
+        m = val.model_[k]
+        assert torch.equal(m.collect('alpha_').cpu(), torch.stack([f['alpha'] for f in fits]).float()), k
+        e_coef = max(e_coef, _rel(m.collect('coef_').cpu(), torch.stack([f['coef'] for f in fits])))
+        e_pat = max(e_pat, _rel(m.collect('pattern_').cpu(), torch.stack([f['pattern'] for f in fits])))
+        yh = torch.stack([orc.ridge_predict(X[te][..., t].double(), f['coef'], f['intercept']) for t, f in enumerate(fits)], -1)
+        e_r2 = max(e_r2, (sc['r2'][k].cpu().double() - orc.score_fold(y[te].double(), yh, y[tr].double(), 'r2')).abs().max().item())
+        e_pr = max(e_pr, (sc['pearsonr'][k].cpu().double() - orc.score_fold(y[te].double(), yh, y[tr].double(), 'pearsonr')).abs().max().item())
+    print(f'cfg5 slices vs CPU oracle: coef {e_coef:.1e} pattern {e_pat:.1e} r2 {e_r2:.1e} pearson {e_pr:.1e}')
+    assert e_coef < TOL_COEF and e_pat < 2e-4 and e_r2 < TOL_SCORE and e_pr < TOL_SCORE

@@ -21,7 +21,7 @@ def test_lag_window_and_delay_known_answer(golden):
     assert torch.equal(orc.flatten_targets(T(g['yr'])), T(g['yt2']))
 
 
-@pytest.mark.parametrize('solver', [orc.ridge_loo_fit, orc.ridge_loo_fit_primal])
+@pytest.mark.parametrize('solver', [orc.ridge_loo_fit, orc.ridge_loo_fit_primal, orc.ridge_loo_fit_chol])
 def test_ridgecv_reference_cases(golden, solver):
     g = golden('ridgecv.npz')
     alphas = T(g['alphas'])
@@ -105,6 +105,12 @@ def test_trf_small_cross_val(golden):
     out64 = orc.cross_val_trf(X.double(), y.double(), w, al.double(), cv=5, solver=orc.ridge_loo_fit_primal)
     assert torch.equal(out64['alpha'].float(), T(g['cv_alpha']))
     np.testing.assert_allclose(out64['r2'].numpy(), g['cv_score'], atol=2e-5)
+    # the Cholesky-per-alpha restatement (the fp64 checker of the BASELINE-size GPU tests) is the same function
+    outc = orc.cross_val_trf(X.double(), y.double(), w, al.double(), cv=5, solver=orc.ridge_loo_fit_chol)
+    assert torch.equal(outc['alpha'], out64['alpha'])
+    np.testing.assert_allclose(outc['losses'].numpy(), out64['losses'].numpy(), rtol=1e-9)
+    np.testing.assert_allclose(outc['coef'].numpy(), out64['coef'].numpy(), rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(outc['r2'].numpy(), g['cv_score'], atol=2e-5)
 
 
 def test_trf_small_single_fit_and_patterns(golden):
