@@ -390,12 +390,19 @@ def trf_predict(X: torch.Tensor, window: np.ndarray, flat_coef: torch.Tensor, in
 
 def cross_val_trf(X: torch.Tensor, y: torch.Tensor, window: np.ndarray, alphas: torch.Tensor, cv: int = 5,
                   scale: bool = True, metrics: Sequence[str] = ('r2',), solver=ridge_loo_fit,
-                  folds: Optional[Iterable[int]] = None, **ridge_kw) -> Dict[str, object]:
+                  folds: Optional[Iterable[int]] = None, scale_dtype: Optional[torch.dtype] = None, scale_device=None,
+                  **ridge_kw) -> Dict[str, object]:
     """``cross_val_score(make_pipeline(Scaler().to_torch(), TimeDelayed(...)), X, y, cv=cv)``.
 
     reference flow: cross_val_score.py:84-99 -> validator.py:321-400 -> fit_model_ (:20-115):
     per fold fit Scaler on X[train] (statistics over trials), fit TimeDelayed, predict X[test] with
-    the training statistics, score over trials; scores stacked to (K, F, T)."""
+    the training statistics, score over trials; scores stacked to (K, F, T).
+    ``scale_dtype``: dtype the Scaler step works in (default: X's).  A fp64 check of a fp32 pipeline must scale in fp32
+    like the reference does: make_meeg_continuous data holds denormal samples (an AR(1) tail decaying to 1e-45) whose
+    variance is exactly 0 in fp32 (scale -> 1, scaler.py:360) but 4e-91 in fp64 (scale 6e-46), a different input.
+    ``scale_device``: device the Scaler step runs on (default: X's).  torch's fp32 variance accumulates in double on the CPU
+    but in float on CUDA; on the 1e-20-sized samples of the same tails the two differ by 1e-3 relative, so a check against
+    the reference's CPU behaviour scales on the CPU."""
     splits = kfold_indices(X.shape[0], cv)
     res = {m: [] for m in metrics}
     alphas_, coefs_, icpts_, losses_ = [], [], [], []
@@ -404,8 +411,10 @@ def cross_val_trf(X: torch.Tensor, y: torch.Tensor, window: np.ndarray, alphas: 
             continue
         Xtr, Xte = X[tr], X[te]
         if scale:
-            st = scaler_fit(Xtr)
-            Xtr, Xte = scaler_transform(Xtr, st), scaler_transform(Xte, st)
+            sdt, sdev = scale_dtype or X.dtype, scale_device or X.device
+            st = scaler_fit(Xtr.to(device=sdev, dtype=sdt))
+            Xtr = scaler_transform(Xtr.to(device=sdev, dtype=sdt), st).to(device=X.device, dtype=X.dtype)
+            Xte = scaler_transform(Xte.to(device=sdev, dtype=sdt), st).to(device=X.device, dtype=X.dtype)
         fit = trf_fit(Xtr, y[tr], window, alphas, solver=solver, **ridge_kw)
         yh = trf_predict(Xte, window, fit['flat_coef'], fit['intercept'])
         for m in metrics:

@@ -11,6 +11,9 @@ Tolerances (north_star; fp32 CUDA path against the fp64 oracle on the same input
     LOO losses                      2e-4 relative
     coefficients                    1e-4 relative (Frobenius, per fold)
     held-out r2 / pearson           1e-5 absolute
+The oracle's Scaler step runs in fp32 like the reference's (``scale_dtype``): the synthetic stimuli contain denormal samples
+whose variance is exactly zero in fp32 but not in fp64, i.e. a fp64 Scaler would hand the ridge a different input; and on the
+CPU (``scale_device``), because torch's CUDA fp32 variance accumulates in float and differs by 1e-3 on the 1e-20-sized samples.
 Set MVB_SKIP_LARGE=1 to skip this file (about three minutes on one B200)."""
 import os
 
@@ -79,7 +82,7 @@ def test_cfg2_cross_val_score_vs_fp64_oracle():
     Xd, yd = X.cuda().double(), y.cuda().double()
     worst = dict(loss=0.0, coef=0.0, r2=0.0, icpt=0.0)
     for k in range(5):                                            # one fold at a time keeps the fp64 design (4 GB) transient
-        ref = orc.cross_val_trf(Xd, yd, win, ALPHAS.cuda().double(), cv=5, solver=orc.ridge_loo_fit_chol, folds=[k])
+        ref = orc.cross_val_trf(Xd, yd, win, ALPHAS.cuda().double(), cv=5, solver=orc.ridge_loo_fit_chol, folds=[k], scale_dtype=torch.float32, scale_device='cpu')
         assert float(got_alpha[k]) == float(ref['alpha'][0].float()), (k, float(got_alpha[k]), float(ref['alpha'][0]))
         loss_ref = ref['losses'][0].cpu()
         # the selection the reference makes (first minimum of the mean over targets) must be the same on both tables
@@ -108,7 +111,7 @@ def test_mid_size_fold_vs_cpu_oracle():
     td = mv.estimators.TimeDelayed(-1.0, 0.0, 200, alphas=ALPHAS).fit(sc.transform(X[tr].cuda()), y[tr].cuda())
     yh = td.predict(sc.transform(X[te].cuda()))
     ref = orc.cross_val_trf(X.double(), y.double(), orc.lag_window(-1.0, 0.0, 200), ALPHAS.double(), cv=5, folds=[0],
-                            metrics=('r2', 'pearsonr'))
+                            metrics=('r2', 'pearsonr'), scale_dtype=torch.float32, scale_device='cpu')
     assert float(td.estimator.alpha_) == float(ref['alpha'][0].float())
     loss_ref = ref['losses'][0]
     e_loss = ((td.estimator.loss_.cpu().double() - loss_ref).abs() / loss_ref.abs()).max().item()
@@ -116,7 +119,12 @@ def test_mid_size_fold_vs_cpu_oracle():
     r2 = mv.math.r2(y[te].cuda().movedim(0, -1), yh.movedim(0, -1), y[tr].cuda().mean(0, keepdim=True).movedim(0, -1))
     pr = mv.math.pearsonr(y[te].cuda().movedim(0, -1), yh.movedim(0, -1))
     e_r2 = (r2.cpu().double() - ref['r2'][0]).abs().max().item()
-    e_pr = (pr.cpu().double() - ref['pearsonr'][0]).abs().max().item()
+    # pearson is NaN where the prediction does not vary over the test trials (pearsonr.py:55-56 has no guard): before
+    # stimulus onset the design is zero or of the size of the 1e-20 AR(1) tails, which fp32 adds to the intercept without
+    # trace (NaN, as in the reference's fp32) while fp64 keeps a meaningless 1e-40 variance -- compare the informative cells
+    both = torch.isfinite(pr.cpu()) & torch.isfinite(ref['pearsonr'][0])
+    assert both.float().mean().item() > 0.7
+    e_pr = (pr.cpu().double() - ref['pearsonr'][0])[both].abs().max().item()
     print(f'mid-size fold vs CPU oracle: loss {e_loss:.1e} coef {e_coef:.1e} r2 {e_r2:.1e} pearson {e_pr:.1e}')
     assert e_loss < TOL_LOSS and e_coef < TOL_COEF and e_r2 < TOL_SCORE and e_pr < TOL_SCORE
 
@@ -148,7 +156,7 @@ def test_cfg3_hierarchical_sets_vs_fp64_oracle():
     Xd, yd = X.cuda().double(), y.cuda().double()
     worst = 0.0
     for i, m in enumerate(masks):
-        ref = orc.cross_val_trf(Xd[:, m.cuda()], yd, win, ALPHAS.cuda().double(), cv=5, solver=orc.ridge_loo_fit_chol, folds=[0])
+        ref = orc.cross_val_trf(Xd[:, m.cuda()], yd, win, ALPHAS.cuda().double(), cv=5, solver=orc.ridge_loo_fit_chol, folds=[0], scale_dtype=torch.float32, scale_device='cpu')
         assert got_alpha[i] == float(ref['alpha'][0].float()), (i, got_alpha[i], float(ref['alpha'][0]))
         worst = max(worst, (hs0[i].double() - ref['r2'][0].cpu()).abs().max().item())
         del ref
@@ -174,7 +182,7 @@ def test_cfg4_shapley_permutation_vs_fp64_oracle():
     _free()
     torch.manual_seed(1)
     ref = orc.shapley_trf(X.cuda().double(), y.cuda().double(), groups, orc.lag_window(-1.0, 0.0, 200), ALPHAS.cuda().double(),
-                          n_permutations=1, cv=5, solver=orc.ridge_loo_fit_chol, folds=[0])
+                          n_permutations=1, cv=5, solver=orc.ridge_loo_fit_chol, folds=[0], scale_dtype=torch.float32, scale_device='cpu')
     assert torch.equal(order, ref['order'])
     err = (ss0.double() - ref['score'][0, :, 0].cpu()).abs().max().item()
     print(f'cfg4 permutation, fold 0 increments vs fp64 oracle: max abs err = {err:.2e}')
