@@ -10,6 +10,7 @@
 #include "../../include/mvb.h"
 #include "mvb_kernels.cuh"
 #include "tc_gemm.cuh"
+#include "toeplitz_gram.cuh"
 #include "jacobi_block.cuh"
 #include "lanczos_band.cuh"
 #include "band_loo.cuh"
@@ -174,17 +175,13 @@ int run_contract(const mvb_operand& A, const mvb_operand& B, int M, int N, int K
     // and every stage's B half then arrives by one TMA bulk copy instead of LDG -> split -> STS in the 512 threads,
     // which is the bound of this kernel (profiles/r01_tc_gemm2_notes.md); worth one extra pass over B when M is large.
     static const bool planes_on = [] { const char* e = getenv("MVB_TC_PLANES"); return !e || atoi(e) != 0; }();
-    // (a symmetric product -- the Gram of the implicit design -- only on the TMEM-A kernel, which takes A gathers 0 and 2)
-    if (planes && planes_on && (!symmetric || (mvb::tc::ta_enabled() && A.contig != 1)) && N > 128 && M >= 1024 &&
+    // (symmetric products never take planes: the Gram of a lag-expanded design has its own kernel, toeplitz_gram.cuh)
+    if (planes && planes_on && !symmetric && N > 128 && M >= 1024 &&
         (double)M * N * K >= 4e9 && planes_bytes >= mvb::tc_planes_bytes(N, K)) {
       MVB_CUDA(mvb::tc_presplit_launch(p.B, K, (uint8_t*)planes, st));
       g_launches.fetch_add(1, std::memory_order_relaxed);
       p.b_planes = (const uint8_t*)planes;
       p.b_planes_nkb = (K + mvb::tc::BK - 1) / mvb::tc::BK;
-      // Gram of the design: the planes (8 n p bytes, 4 GB at cfg2) exceed L2, the implicit A operand does not.  Consecutive
-      // CTAs walk the M tiles of one N tile so that a plane tile is streamed from HBM once, not once per wave
-      // (ncu of the N-fastest order: 50 GB of dram reads for this launch, profiles/r01_ncu_full_tmema.md)
-      if (symmetric) p.raster_m_fast = 1;
     }
     const int slot = prof_begin(2.0 * M * (double)N * K * (symmetric ? 0.5 : 1.0), st);
     MVB_CUDA(mvb::tc_gemm_launch(p, pl.splits, N > 128 ? 256 : 128, st));
@@ -219,9 +216,20 @@ struct StatsWs {
   int64_t *row_off, *col_off, *yrow_off, *ycol_off;
   double *partial, *mu64, *ybar64;
   void* contract_ws; size_t contract_bytes;
-  void* planes; size_t planes_bytes;      // pre-split TF32 planes of the design (Gram) / of y (X^T y), large fp32 problems only
+  void* planes; size_t planes_bytes;      // pre-split TF32 planes of y (the dense B operand of X^T y), large fp32 problems only
+  float* pack; size_t pack_bytes;         // TF32 planes of the four shifted copies of the training series (toeplitz_gram.cuh)
   int parts;
 };
+
+// The Gram of a lag-expanded design runs on the implicit-Toeplitz kernel (toeplitz_gram.cuh) whenever its shape allows:
+// fp32, tensor cores, whole 8-sample MMA steps per trial, enough tiles to fill the SMs.  MVB_TOEPLITZ_GRAM=0 keeps the
+// generic gather kernel (A/B measurements), =2 takes it for every shape it can compute, however few tiles (tests).
+bool use_toeplitz_gram(const mvb_design* d) {
+  const char* e = getenv("MVB_TOEPLITZ_GRAM");
+  const int mode = e ? atoi(e) : 1;
+  if (mode == 0 || d->dtype != MVB_F32 || force_simt()) return false;
+  return mvb::tg::usable(d->n_time, d->n_lag, d->n_feat, mode == 2);
+}
 
 template <typename T>
 size_t carve_stats(Arena& ar, const mvb_design* d, int F, StatsWs& w) {
@@ -238,9 +246,10 @@ size_t carve_stats(Arena& ar, const mvb_design* d, int F, StatsWs& w) {
   size_t cb = std::max(plan_contract((int)p, (int)p, (int)n, dt, 1).ws_elems, plan_contract((int)p, F, (int)n, dt, 0).ws_elems) * sizeof(T);
   w.contract_bytes = cb;
   w.contract_ws = ar.take<char>(cb);
-  w.planes_bytes = (sizeof(T) == 4 && p >= 1024 && !force_simt())
-                       ? std::max(mvb::tc_planes_bytes((int)p, (int)n), mvb::tc_planes_bytes(F, (int)n)) : 0;
+  w.planes_bytes = (sizeof(T) == 4 && p >= 1024 && !force_simt()) ? mvb::tc_planes_bytes(F, (int)n) : 0;
   w.planes = w.planes_bytes ? ar.take<char>(w.planes_bytes) : nullptr;
+  w.pack_bytes = use_toeplitz_gram(d) ? mvb::tg::pack_bytes(d->n_trials, d->n_feat, d->n_time + d->n_lag - 1) : 0;
+  w.pack = w.pack_bytes ? (float*)ar.take<char>(w.pack_bytes) : nullptr;
   return ar.off;
 }
 
@@ -277,7 +286,33 @@ int trf_stats_impl(const mvb_design* d, const T* y, int F, int fit_intercept, T*
   const bool y_vec = sizeof(T) == 4 && Tn % 4 == 0 && ((uintptr_t)y & 15) == 0;
   mvb_operand yc{y, w.ycol_off, w.yrow_off, F, y_vec ? 2 : 1};
   int rc;
-  { ProfScope ps(PC_GRAM); rc = run_contract<T>(xc, xc, (int)p, (int)p, (int)n, G, p, 1, w.contract_ws, w.contract_bytes, st, 0, 0, w.planes, w.planes_bytes); }
+  if constexpr (sizeof(T) == 4) {
+    if (w.pack_bytes) {
+      // X^T X straight from the padded stimulus: the training series are split into TF32 planes once (8 shifted / split
+      // copies, 130 MB at configs[1]) and the kernel's operands are windows of them -- nothing of the size of the lag
+      // expansion (timedelayed.py:415-423: 1.98 GB) exists at any point
+      namespace tg = mvb::tg;
+      const int Tp = Tn + d->n_lag - 1, Tpp = tg::pack_pitch(Tp);
+      tg::pack_kernel<<<148 * 8, 256, 0, st>>>((const float*)d->xp, d->trial_idx, d->n_trials, d->trial_stride, d->feat_idx, d->n_feat,
+                                               d->feat_stride, Tp, Tpp, w.pack);
+      MVB_LAUNCHED();
+      tg::Params tp{};
+      tp.pack = w.pack; tp.L = (int64_t)d->n_trials * d->n_feat * Tpp; tp.n_trials = d->n_trials; tp.n_feat = d->n_feat; tp.Tpp = Tpp;
+      tp.nblk_f = (d->n_lag + 31) / 32; tp.n_vblk = d->n_feat * tp.nblk_f; tp.W = d->n_lag; tp.T = Tn;
+      tg::chunk_plan(Tn, tp.n_chunks, tp.chunk_len);
+      tp.G = (float*)G; tp.ldg = p;
+      ProfScope ps(PC_GRAM);
+      const int slot = prof_begin((double)n * (double)p * (double)p, st);
+      MVB_CUDA(tg::launch(tp, st));
+      prof_end(slot, st);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      rc = MVB_OK;
+    } else {
+      ProfScope ps(PC_GRAM); rc = run_contract<T>(xc, xc, (int)p, (int)p, (int)n, G, p, 1, w.contract_ws, w.contract_bytes, st);
+    }
+  } else {
+    ProfScope ps(PC_GRAM); rc = run_contract<T>(xc, xc, (int)p, (int)p, (int)n, G, p, 1, w.contract_ws, w.contract_bytes, st);
+  }
   if (rc) return rc;
   { ProfScope ps(PC_XTY); rc = run_contract<T>(xc, yc, (int)p, F, (int)n, XtY, F, 0, w.contract_ws, w.contract_bytes, st, 0, 0, w.planes, w.planes_bytes); }
   if (rc) return rc;

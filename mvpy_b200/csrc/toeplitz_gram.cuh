@@ -221,8 +221,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) toeplitz_gram_kernel(const Params
 }
 
 // shapes this kernel takes: whole MMA K steps per trial, and enough tiles to fill the machine without split-K
-inline bool usable(int n_time, int n_lag, int n_feat) {
+inline bool usable(int n_time, int n_lag, int n_feat, bool any_size = false) {
   if (n_time % 8 != 0 || n_time < 8 || n_lag < 2) return false;
+  if (any_size) return true;
   const int64_t nvb = (int64_t)n_feat * ((n_lag + 31) / 32);
   const int64_t mt = (nvb + 3) / 4;
   return mt * (mt + 2) / 4 >= 2 * 148;          // ~ lower-triangle tile count

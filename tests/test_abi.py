@@ -61,10 +61,11 @@ def test_product_does_not_import_oracle():
                 assert not re.search(r'^\s*(from|import)\s+[\w.]*oracle', src, flags=re.M), f'{f} imports the oracle'
 
 
-def test_stats_workspace_carries_design_planes_for_large_fp32_problems():
-    """mvb_trf_stats_workspace_bytes is host-only arithmetic: for fp32 designs with p >= 1024 columns it includes the
-    pre-split TF32 planes of the design (8 bytes per entry of the 256-row x 32-k tiled lag expansion, the B operand of
-    the Gram on the TMEM-A contraction kernel); fp64 and small designs do not pay for them."""
+def test_stats_workspace_never_holds_the_lag_expansion():
+    """mvb_trf_stats_workspace_bytes is host-only arithmetic.  The Gram of a lag-expanded design is built from the padded
+    stimulus itself (toeplitz_gram.cuh): the only design-sized scratch is the "pack" -- 2 TF32 planes x 4 shifted copies of
+    the training series, 32 bytes per padded sample -- never anything of the size of the lag expansion
+    (n x p x 4 bytes = 1.98 GB at BASELINE configs[1]; timedelayed.py:415-423 materialises exactly that)."""
     from mvpy_b200 import _lib
     lib = _lib.load()
 
@@ -73,13 +74,12 @@ def test_stats_workspace_carries_design_planes_for_large_fp32_problems():
                             n_feat, dtype)          # xp is never dereferenced by the size query
         return lib.mvb_trf_stats_workspace_bytes(ctypes.byref(d), F)
 
-    n, p = 12 * 400, 6 * 201
-    tiles, stages = -(-p // 256), -(-n // 32)
-    planes = tiles * stages * 2 * 8 * (256 * 16 + 16)
-    big32, big64 = ws(12, 6, 400, 201, 0), ws(12, 6, 400, 201, 1)
-    assert big32 >= planes and big32 - planes < 64 << 20
-    assert big64 < planes                                    # fp64 runs on the CUDA-core contraction: no planes
-    assert ws(12, 5, 400, 201, 0) < planes // 2              # p = 1005 < 1024: shared-memory kernel, no planes
-    # BASELINE configs[1]: 51 tiles x 1200 stages x 65 792 B = 4.03 GB on top of the split-K scratch
+    # BASELINE configs[1] (96 training trials x 64 features x 400 samples, 201 lags, 306 channels)
     cfg2 = ws(96, 64, 400, 201, 0, F=306)
-    assert 51 * 1200 * 65792 <= cfg2 < 51 * 1200 * 65792 + (2 << 30)
+    expansion = 96 * 400 * 64 * 201 * 4
+    pitch = -(-(400 + 200 + 64) // 4) * 4
+    pack = 96 * 64 * pitch * 8 * 4
+    assert pack <= cfg2 < (1 << 30) and cfg2 < expansion // 2, (cfg2, pack, expansion)
+    assert ws(96, 64, 400, 201, 1, F=306) < cfg2 - pack + (64 << 20)     # fp64: CUDA-core contraction, no pack
+    assert ws(96, 64, 404, 201, 0, F=306) < cfg2 - pack + (64 << 20)     # 404 samples: no whole MMA K steps per trial -> gather kernel, no pack
+    assert ws(12, 5, 400, 201, 0) < (64 << 20)                           # small design: gather kernel with split-K

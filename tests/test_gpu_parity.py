@@ -743,30 +743,50 @@ def test_predictor_sets_share_fold_statistics(monkeypatch):
         np.testing.assert_allclose(out['1'][1].cpu().numpy(), out['0'][1].cpu().numpy(), rtol=0, atol=4e-5)
 
 
-def test_stats_tmem_a_planes_path_vs_fp64():
-    """A design with p = 1206 >= 1024 columns and 2 p^2 n = 1.4e10 flop, so that mvb_trf_stats runs the symmetric Gram on the
-    TMEM-A contraction kernel against the design pre-split into planes (tc_gemm.cuh: tc_gemm_ta_kernel, lower tiles + mirror,
-    M-fastest tile order); checked against the same entry point in fp64 (CUDA-core contraction) and against a materialised
-    lag expansion (reference: timedelayed.py:394-431 + ridgecv.py:59-94)."""
+@pytest.mark.parametrize('shape', [(6, 20, 400, -1.0, 200, None, None),          # 201 lags: 7 blocks per feature, 9 rows in the last
+                                   (5, 40, 152, -0.315, 200, [4, 0, 2], None),      # 64 lags, two unequal K chunks, a training subset
+                                   (4, 24, 256, -0.5, 200, None, [0, 3, 4, 7, 8, 11, 12, 15, 16, 19, 20, 21, 22, 23, 1, 2, 5, 6, 9, 10])])
+def test_stats_toeplitz_gram_vs_fp64(shape, monkeypatch):
+    """Designs large enough that mvb_trf_stats builds X^T X on the implicit-Toeplitz kernel (toeplitz_gram.cuh: windows of
+    the padded stimulus by TMA, overlapping UMMA descriptors, lower tiles + mirror): against the same entry point in fp64
+    (CUDA-core contraction over offset tables) and against a materialised lag expansion (reference: timedelayed.py:394-431 +
+    ridgecv.py:59-94); with trial and feature subsets."""
     mv = _mv()
     from mvpy_b200 import _lib
+    monkeypatch.setenv('MVB_TOEPLITZ_GRAM', '2')           # also for designs too small to fill the SMs without split-K
+    N, C, Tn, t_min, fs, trials, feats = shape
     g = torch.Generator().manual_seed(5)
-    N, C, Tn, F = 12, 6, 400, 7
-    X = torch.randn(N, C, Tn, generator=g).cuda()
+    F = 7
+    X = (torch.randn(N, C, Tn, generator=g) + 0.3).cuda()
     y = torch.randn(N, F, Tn, generator=g).cuda()
-    td = mv.estimators.TimeDelayed(-1.0, 0.0, 200, alphas=torch.tensor([1.0]))
-    p, n = C * 201, N * Tn
+    td = mv.estimators.TimeDelayed(t_min, 0.0, fs, alphas=torch.tensor([1.0]))
+    W = td.window.shape[0]
+    ti = None if trials is None else torch.tensor(trials)
+    fi = None if feats is None else torch.tensor(feats)
+    n_tr, n_f = (N if ti is None else len(trials)), (C if fi is None else len(feats))
+    p, n = n_f * W, n_tr * Tn
+    d32 = td._design(X).subset(trial_idx=ti, feat_idx=fi)
+    d64 = td._design(X.double()).subset(trial_idx=ti, feat_idx=fi)
+    cs = d32.c_struct()
+    import ctypes
+    ws_bytes = _lib.load().mvb_trf_stats_workspace_bytes(ctypes.byref(cs), F)
+    assert ws_bytes < n * p * 4 // 2 + (64 << 20)          # nothing of the size of the lag expansion
     for icpt in (True, False):
-        G32, b32, mu32, yb32 = _lib.trf_stats(td._design(X), y, icpt)
-        G64, b64, mu64, yb64 = _lib.trf_stats(td._design(X.double()), y.double(), icpt)
+        G32, b32, mu32, yb32 = _lib.trf_stats(d32, y, icpt)
+        G64, b64, mu64, yb64 = _lib.trf_stats(d64, y.double(), icpt)
         assert G32.shape == (p, p) and G32.dtype == torch.float32
         scale = float(G64.abs().max())
         assert float((G32.double() - G64).abs().max()) / scale < 3e-6
         assert float((G32 - G32.mT).abs().max()) / scale < 1e-6
         assert float((b32.double() - b64).abs().max()) / float(b64.abs().max()) < 3e-6
         np.testing.assert_allclose(mu32.cpu().numpy(), mu64.cpu().numpy(), rtol=0, atol=1e-6)
-    # fp64 statistics against the explicit design: X_t[(trial, t), (c, w)] = X[trial, c, clamp(t + lag_w)]
-    lags = torch.arange(-200, 1, device='cuda')
+    # fp64 statistics (without intercept) against the explicit design: X_t[(trial, t), (c, w)] = X[trial, c, clamp(t + lag_w)]
+    lags = td.window.to('cuda').long()
     tt = (torch.arange(Tn, device='cuda')[None, :] + lags[:, None]).clamp(0, Tn - 1)           # (W, T)
-    Xt = X.double()[:, :, tt].permute(0, 3, 1, 2).reshape(n, p)
+    Xs = X.double()
+    if ti is not None:
+        Xs = Xs[ti.cuda()]
+    if fi is not None:
+        Xs = Xs[:, fi.cuda()]
+    Xt = Xs[:, :, tt].permute(0, 3, 1, 2).reshape(n, p)
     assert float((G64 - Xt.mT @ Xt).abs().max()) / float(G64.abs().max()) < 1e-12
