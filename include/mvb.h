@@ -68,6 +68,12 @@ int mvb_scaler_apply(const void* X, int64_t R, int64_t K, int dtype, const void*
  * a pure shift.  mvb_transpose: [R][C] -> [C][R] (dense 2-D designs become "series" rows).      */
 int mvb_trf_pad(const void* X, int N, int C, int T, int left, int right, int dtype, void* Xp, void* stream);
 int mvb_transpose(const void* X, int64_t R, int64_t C, int dtype, void* out, void* stream);
+/* mvb_trf_shift: centring before multiplying (ridgecv.py:59-94 subtracts the column means from the design itself).
+ * shift[c] = mean of feature c of the padded stimulus (N,C,Tp contiguous) over the selected trials; out = xp - shift[c].
+ * The centred statistics of mvb_trf_stats are invariant under a per-column shift, so fitting on `out` and adding
+ * shift back into the column means / intercept gives the same model without the n mu mu^T cancellation in fp32.     */
+int mvb_trf_shift(const void* xp, int N, int C, int Tp, const int32_t* trial_idx, int n_trials, int dtype, void* shift, void* out,
+                  void* stream);
 
 /* ---- the implicit lag-expanded design -----------------------------------------------------------
  * Column j = (f, w) of row i = (s, t) is  xp[trial(s)*trial_stride + feat(f)*feat_stride + t + w]:

@@ -51,6 +51,7 @@ _SIGNATURES = {
     'mvb_scaler_apply': (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'mvb_trf_pad': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'mvb_transpose': (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    'mvb_trf_shift': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'mvb_contract_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'mvb_contract': (c_int, [POINTER(mvb_operand), POINTER(mvb_operand), c_int, c_int, c_int, c_int, c_void_p, c_int64,
                              c_int, c_void_p, c_size_t, c_void_p]),
@@ -247,6 +248,25 @@ def trf_pad(X: torch.Tensor, left: int, right: int) -> torch.Tensor:
     out = torch.empty((N, C, T + left + right), dtype=X.dtype, device=X.device)
     check(load().mvb_trf_pad(_ptr(X), N, C, T, left, right, dtype_code(X), _ptr(out), _stream(X)), 'mvb_trf_pad')
     return out
+
+
+def shift_design(design: 'Design'):
+    """Centring before multiplying: subtract from every feature of the padded stimulus its mean over the design's trials.
+    Returns (design on the shifted array, shift (C_all,)); column (c, w) of the shifted design is the original minus
+    shift[c], which leaves the centred Gram / cross-moment unchanged (see ``mvb_trf_shift``)."""
+    xp = design.xp
+    N, C, Tp = xp.shape
+    shift = torch.empty(C, dtype=xp.dtype, device=xp.device)
+    out = torch.empty_like(xp)
+    check(load().mvb_trf_shift(_ptr(xp), N, C, Tp, _ptr(design.trial_idx), design.n_trials, dtype_code(xp), _ptr(shift), _ptr(out),
+                               _stream(xp)), 'mvb_trf_shift')
+    return Design(out, design.n_time, design.n_lag, design.trial_idx, design.feat_idx), shift
+
+
+def shift_columns(design: 'Design', shift: torch.Tensor) -> torch.Tensor:
+    """The per-column (c, w) view of a per-feature shift: (p,)."""
+    s = shift if design.feat_idx is None else shift[design.feat_idx.long()]
+    return s.repeat_interleave(design.n_lag)
 
 
 def transpose(X2: torch.Tensor) -> torch.Tensor:

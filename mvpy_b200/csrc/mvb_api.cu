@@ -912,6 +912,24 @@ int mvb_trf_pad(const void* X, int N, int C, int T, int left, int right, int dty
   return MVB_OK;
 }
 
+int mvb_trf_shift(const void* xp, int N, int C, int Tp, const int32_t* trial_idx, int n_trials, int dtype, void* shift, void* out,
+                  void* stream) {
+  if (!xp || !shift || !out || N < 1 || C < 1 || Tp < 1 || n_trials < 1) return fail(MVB_E_ARG, "trf_shift: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = (int64_t)N * C * Tp;
+  if (dtype == MVB_F32) {
+    mvb::feature_pivot_kernel<float><<<C, 256, 0, st>>>((const float*)xp, trial_idx, n_trials, (int64_t)C * Tp, Tp, Tp, (float*)shift);
+    MVB_LAUNCHED();
+    mvb::feature_shift_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)xp, total, C, Tp, (const float*)shift, (float*)out);
+  } else if (dtype == MVB_F64) {
+    mvb::feature_pivot_kernel<double><<<C, 256, 0, st>>>((const double*)xp, trial_idx, n_trials, (int64_t)C * Tp, Tp, Tp, (double*)shift);
+    MVB_LAUNCHED();
+    mvb::feature_shift_kernel<double><<<grid_for(total), 256, 0, st>>>((const double*)xp, total, C, Tp, (const double*)shift, (double*)out);
+  } else return fail(MVB_E_UNSUPPORTED, "trf_shift: dtype %d", dtype);
+  MVB_LAUNCHED();
+  return MVB_OK;
+}
+
 int mvb_transpose(const void* X, int64_t R, int64_t C, int dtype, void* out, void* stream) {
   if (!X || !out || R < 1 || C < 1) return fail(MVB_E_ARG, "transpose: bad argument");
   cudaStream_t st = (cudaStream_t)stream;

@@ -80,6 +80,34 @@ __global__ void pad_kernel(const T* __restrict__ X, int64_t rows, int Tn, int le
   }
 }
 
+// Per-feature pivot of the padded stimulus: shift[c] = mean over the selected trials and all Tp samples of feature c (fp64
+// accumulation), one block per feature.  Centring "before multiplying" (ridgecv.py:59-94 centres the design itself): the
+// centred Gram / cross-moment do not change when a constant is subtracted from a column, and every column (c, w) of the
+// lag-expanded design has a mean within edge effects of its feature's mean, so subtracting the pivot from the stimulus removes
+// the n mu mu^T cancellation from the rank-1 centring correction of G for inputs whose mean dwarfs their spread.
+template <typename T>
+__global__ void feature_pivot_kernel(const T* __restrict__ xp, const int32_t* __restrict__ trial_idx, int n_trials, int64_t trial_stride,
+                                     int64_t feat_stride, int Tp, T* __restrict__ shift) {
+  __shared__ double red[256];
+  const int c = blockIdx.x;
+  double s = 0.0;
+  const int64_t total = (int64_t)n_trials * Tp;
+  for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
+    const int i = (int)(e / Tp), j = (int)(e - (int64_t)i * Tp);
+    s += (double)xp[(int64_t)(trial_idx ? trial_idx[i] : i) * trial_stride + (int64_t)c * feat_stride + j];
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) shift[c] = (T)(red[0] / (double)total);
+}
+// out[n][c][j] = xp[n][c][j] - shift[c]   (all trials of the array, contiguous (N, C, Tp))
+template <typename T>
+__global__ void feature_shift_kernel(const T* __restrict__ xp, int64_t total, int C, int Tp, const T* __restrict__ shift, T* __restrict__ out) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    out[e] = xp[e] - shift[(e / Tp) % C];
+}
+
 template <typename T>
 __global__ void transpose_kernel(const T* __restrict__ X, int64_t R, int64_t C, T* out) {
   __shared__ T tile[32][33];

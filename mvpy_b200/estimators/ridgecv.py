@@ -25,26 +25,119 @@ def _as_alphas(alphas) -> torch.Tensor:
     return alphas
 
 
+def _finish_shift(out: Dict, design: _lib.Design, shift: Optional[torch.Tensor]) -> Dict:
+    """Undo the pivot shift of ``_lib.shift_design`` in the quantities that depend on it: column means and intercept
+    (coefficients, losses and the centred Gram are shift-invariant)."""
+    if shift is None:
+        return out
+    s_col = _lib.shift_columns(design, shift)
+    out['intercept'] = out['intercept'] - out['coef'] @ s_col
+    out['mu'] = out['mu'] + s_col
+    return out
+
+
 def solve_design(design: _lib.Design, y: torch.Tensor, alphas: torch.Tensor, fit_intercept: bool, alpha_per_target: bool,
-                 stats=None, want_loss: bool = False, keep_gram: bool = True):
+                 stats=None, want_loss: bool = False, keep_gram: bool = True, shift: Optional[torch.Tensor] = None):
     """Shared fit core: y is (N, F, T) on the device of ``design``.  Returns dict with flat coef (F, p),
-    intercept (F,), alpha (0-d or (F,)), best, loss, and the centred Gram (for patterns)."""
-    if (stats is None and design.xp.dtype == torch.float32 and design.n_rows <= design.n_cols + int(fit_intercept)
-            and design.n_cols <= 2048):
+    intercept (F,), alpha (0-d or (F,)), best, loss, and the centred Gram (for patterns).
+
+    ``stats`` / ``shift``: precomputed statistics of a design that was already pivot-shifted by ``shift`` (predictor-set
+    drivers share them per fold).  Otherwise, with an intercept, the design is shifted here: the reference centres the
+    design before any product (ridgecv.py:59-94, on a clone); forming G - n mu mu^T from uncentred fp32 products instead
+    loses (mean/std)^2 eps, so each feature's mean is taken out of the stimulus first (``mvb_trf_shift``)."""
+    wide = design.n_rows <= design.n_cols + int(fit_intercept)
+    if stats is None and design.xp.dtype == torch.float32 and wide:
         # No more rows than unknowns: every training row is (nearly) interpolated, 1 - leverage is of order
         # alpha / eigenvalue and fp32 cannot form it (the reference's dual route for n <= p, ridgecv.py:135-190, never
-        # does).  This regime is small by construction (the Gram is p x p with p >= n), so it runs on the fp64 kernels.
-        wide = _lib.Design(design.xp.double(), design.n_time, design.n_lag, design.trial_idx, design.feat_idx)
-        out = solve_design(wide, y.double(), alphas.double(), fit_intercept, alpha_per_target, None, want_loss, keep_gram)
+        # does).  Small column counts run the primal route on the fp64 kernels; larger ones the dual (n x n) route, fp64 too.
+        d64 = _lib.Design(design.xp.double(), design.n_time, design.n_lag, design.trial_idx, design.feat_idx)
+        if design.n_cols <= 2048:
+            out = solve_design(d64, y.double(), alphas.double(), fit_intercept, alpha_per_target, None, want_loss, keep_gram)
+        else:
+            out = solve_design_dual(d64, y.double(), alphas.double(), fit_intercept, alpha_per_target, keep_gram)
         return {k: (v.float() if isinstance(v, torch.Tensor) and v.dtype == torch.float64 else v) for k, v in out.items()}
+    if stats is None and wide and design.n_cols > 2048:
+        return solve_design_dual(design, y, alphas, fit_intercept, alpha_per_target, keep_gram)
     if stats is None:
+        if fit_intercept:
+            design, shift = _lib.shift_design(design)
         stats = _lib.trf_stats(design, y, fit_intercept)
     G, XtY, mu, ybar = stats
     Gkeep = G.clone() if keep_gram else None          # the solve may overwrite G; patterns need cov(X) = G / (n - 1)
     coef, icpt, alpha, best, loss = _lib.ridge_solve(design, y, G, XtY, mu, ybar, alphas, fit_intercept, alpha_per_target,
                                                      want_loss=want_loss)
-    return dict(coef=coef, intercept=icpt, alpha=alpha if alpha_per_target else alpha.reshape(()), best=best, loss=loss,
-                gram=Gkeep, mu=mu, ybar=ybar)
+    out = dict(coef=coef, intercept=icpt, alpha=alpha if alpha_per_target else alpha.reshape(()), best=best, loss=loss,
+               gram=Gkeep, mu=mu, ybar=ybar)
+    return _finish_shift(out, design, shift)
+
+
+DUAL_MAX_ROWS = 2048
+
+
+def solve_design_dual(design: _lib.Design, y: torch.Tensor, alphas: torch.Tensor, fit_intercept: bool, alpha_per_target: bool,
+                      keep_gram: bool = False):     # the p x p Gram is never built here: callers that need it (patterns) rebuild it
+    """n <= p: the reference's dual route (ridgecv.py:135-205) -- eigendecomposition of the n x n kernel matrix
+    K = X_c X_c^T (+ 1 1^T for the unpenalised constant direction), duals = Q diag(w) Q^T y_c, LOO error = dual / diag,
+    coef = duals^T X_c.  K and duals^T X come from the contraction kernel over the implicit design (both orientations),
+    the eigensolve from the batched Jacobi kernel; everything else is n x n sized tensor algebra.  fp64 only (the caller
+    promotes fp32 inputs); at most ``DUAL_MAX_ROWS`` rows -- beyond that the n x n eigensolve has no kernel here."""
+    if design.xp.dtype != torch.float64:
+        raise _lib.MvbError('solve_design_dual works on float64 designs')
+    n, p, F = design.n_rows, design.n_cols, y.shape[1]
+    if n > DUAL_MAX_ROWS:
+        raise _lib.MvbError(f'ridge fit with no more rows than columns (n = {n} <= p = {p}) and more than {DUAL_MAX_ROWS} rows: the dual '
+                            f'(n x n) eigensolve this regime needs (ridgecv.py:135-190) is only implemented up to {DUAL_MAX_ROWS} rows, '
+                            f'and the Gram route cannot form 1 - leverage there.  Use more training samples than columns.')
+    dev, dt = design.xp.device, design.xp.dtype
+    shift = None
+    if fit_intercept:
+        design, shift = _lib.shift_design(design)
+    xp = design.xp
+    tri = torch.arange(design.n_trials, device=dev) if design.trial_idx is None else design.trial_idx.long()
+    fti = torch.arange(design.n_feat, device=dev) if design.feat_idx is None else design.feat_idx.long()
+    row_off = (tri[:, None] * xp.stride(0) + torch.arange(design.n_time, device=dev)[None, :]).reshape(-1).contiguous()
+    col_off = (fti[:, None] * xp.stride(1) + torch.arange(design.n_lag, device=dev)[None, :]).reshape(-1).contiguous()
+    yt = (y if design.trial_idx is None else y[tri]).permute(0, 2, 1).reshape(n, F)
+    K = _lib.contract(xp, row_off, col_off, 0, xp, row_off, col_off, 0, n, n, p, symmetric=True)         # X X^T
+    ones_off = torch.zeros(1, dtype=torch.int64, device=dev)
+    ones = torch.ones(n, dtype=dt, device=dev)
+    k_iota = torch.arange(n, device=dev)
+    col_sum = _lib.contract(ones, ones_off, k_iota, 1, xp, col_off, row_off, 0, 1, p, n)[0]              # 1^T X
+    if fit_intercept:
+        mu, ybar = col_sum / n, yt.mean(0)
+        v = K.mean(1)                                       # X mu
+        K = K - v[:, None] - v[None, :] + v.mean() + 1.0    # X_c X_c^T + 1 1^T   (ridgecv.py:139-141)
+        yc = yt - ybar
+    else:
+        mu, ybar = torch.zeros(p, dtype=dt, device=dev), torch.zeros(F, dtype=dt, device=dev)
+        yc = yt
+    Vt, lam = _lib.eigh(K[None].contiguous())
+    Q, lam = Vt[0].mT, lam[0]
+    Qty = Q.mT @ yc
+    W = 1.0 / (lam[None, :] + alphas[:, None])              # (A, n)
+    if fit_intercept:
+        unit = torch.full((n,), n ** -0.5, dtype=dt, device=dev)
+        k0 = int((Q.mT @ unit).abs().argmax())              # the constant direction is not penalised (ridgecv.py:147-150)
+        W[:, k0] = 0.0
+    duals = torch.einsum('ik,ak,kf->aif', Q, W, Qty)
+    diag = (Q * Q) @ W.mT                                   # (n, A)
+    loss = (duals / diag.mT[:, :, None]).square().mean(1)   # (A, F)
+    if alpha_per_target:
+        best = loss.argmin(0)
+        dual = torch.stack([duals[int(best[f]), :, f] for f in range(F)], 1)
+        alpha = alphas[best]
+    else:
+        best = loss.mean(1).argmin().reshape(1)
+        dual = duals[int(best)]
+        alpha = alphas[best].reshape(())
+    dT = dual.mT.contiguous()                               # (F, n)
+    f_off = torch.arange(F, device=dev) * n
+    coef = _lib.contract(dT, f_off, k_iota, 1, xp, col_off, row_off, 0, F, p, n)                        # duals^T X
+    if fit_intercept:
+        coef = coef - dT.sum(1)[:, None] * mu[None, :]      # ... - (duals^T 1) mu^T = duals^T X_c
+    icpt = ybar - coef @ mu if fit_intercept else torch.zeros(F, dtype=dt, device=dev)
+    out = dict(coef=coef.contiguous(), intercept=icpt, alpha=alpha, best=best.to(torch.int32), loss=loss, gram=None, mu=mu, ybar=ybar)
+    return _finish_shift(out, design, shift)
 
 
 class _RidgeCV_torch(sklearn.base.BaseEstimator):

@@ -43,13 +43,13 @@ class _RidgeDecoder_torch(sklearn.base.BaseEstimator):
         # cov(X) is the centred Gram the fit already built (always demeaned for patterns)
         n = X.shape[0]
         out_dev = X.device
-        if self.fit_intercept:
+        if self.fit_intercept and est._gram is not None:
             Sx = est._gram / float(n - 1)
         else:
             Xd = _lib.to_device(X)
             xs = _lib.transpose(Xd.contiguous()).reshape(1, Xd.shape[1], n)
             yd = _lib.transpose(_lib.to_device(y).to(Xd.dtype).contiguous()).reshape(1, y.shape[1], n)
-            Sx = _lib.trf_stats(_lib.Design(xs, n_time=n, n_lag=1), yd, True)[0] / float(n - 1)
+            Sx = _lib.trf_stats(_lib.shift_design(_lib.Design(xs, n_time=n, n_lag=1))[0], yd, True)[0] / float(n - 1)
         coef = _lib.to_device(self.coef_).to(Sx.dtype)
         if y.shape[1] > 1:
             yd = _lib.to_device(y).to(Sx.dtype)

@@ -73,8 +73,8 @@ class _TimeDelayed_torch(sklearn.base.BaseEstimator):
         built; the (f x f) target covariance and its inverse are tiny device-side tensor algebra."""
         n = design.n_rows
         gram = fit['gram']
-        if not self.estimator.fit_intercept:         # the reference always demeans for the patterns
-            gram = _lib.trf_stats(design, yd, True)[0]
+        if gram is None or not self.estimator.fit_intercept:         # the reference always demeans for the patterns
+            gram = _lib.trf_stats(_lib.shift_design(design)[0], yd, True)[0]
         Sx = gram / float(n - 1)
         coef = fit['coef']
         yt = yd.permute(0, 2, 1).reshape(-1, yd.shape[1]) if design.trial_idx is None else \
@@ -125,13 +125,15 @@ class _TimeDelayed_torch(sklearn.base.BaseEstimator):
             X_tr = X_all[train.to(X_all.device)]
             for step in pre:
                 X_tr = step.clone().fit_transform(X_tr)
-            full = self._design(X_tr.contiguous())
-            entry = (full, _lib.trf_stats(full, yd, self.estimator.fit_intercept))
+            full, shift = self._design(X_tr.contiguous()), None
+            if self.estimator.fit_intercept:
+                full, shift = _lib.shift_design(full)             # centring before multiplying (ridgecv.solve_design)
+            entry = (full, _lib.trf_stats(full, yd, self.estimator.fit_intercept), shift)
             par['shared'][key] = entry
-        full, (G, XtY, mu, ybar) = entry
+        full, (G, XtY, mu, ybar), shift = entry
         cols = (idx.to(G.device)[:, None] * W + torch.arange(W, device=G.device)[None, :]).reshape(-1)
         stats = (G[cols][:, cols].contiguous(), XtY[cols].contiguous(), mu[cols].contiguous(), ybar)
-        return full.subset(feat_idx=idx), stats
+        return full.subset(feat_idx=idx), stats, shift
 
     def fit(self, X: torch.Tensor, y: torch.Tensor):
         if (len(X.shape) != 3) | (len(y.shape) != 3):
@@ -145,9 +147,9 @@ class _TimeDelayed_torch(sklearn.base.BaseEstimator):
         est = self.estimator
         est.alphas = est.alphas.to(X.dtype).to(X.device)              # ridgecv.py:125
         shared = self._shared_stats(Xd, yd)
-        design, stats = shared if shared is not None else (self._design(Xd), None)
+        design, stats, shift = shared if shared is not None else (self._design(Xd), None, None)
         fit = solve_design(design, yd, _lib.to_device(est.alphas).contiguous(), est.fit_intercept, est.alpha_per_target,
-                           stats=stats, want_loss=True, keep_gram=self.patterns)
+                           stats=stats, want_loss=True, keep_gram=self.patterns, shift=shift)
         self._finish_fit(fit, design, yd, out_dev)
         return self
 

@@ -790,3 +790,69 @@ def test_stats_toeplitz_gram_vs_fp64(shape, monkeypatch):
         Xs = Xs[:, fi.cuda()]
     Xt = Xs[:, :, tt].permute(0, 3, 1, 2).reshape(n, p)
     assert float((G64 - Xt.mT @ Xt).abs().max()) / float(G64.abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize('kind', ['dense', 'trf'])
+def test_inputs_with_large_means_are_centred_before_multiplying(kind):
+    """fp32 inputs whose column means dwarf their spread (mean 1e3, std 1; no Scaler in front): the reference centres a copy
+    of the design before any product (ridgecv.py:59-94, 123).  Forming G - n mu mu^T from uncentred fp32 products would lose
+    eps (mean/std)^2 = 6e-2 here; the per-feature pivot shift (mvb_trf_shift) keeps the fp32 path at its usual distance from
+    the fp64 oracle: chosen alpha identical, LOO losses / coefficients 1e-4, intercept and predictions to fp32 rounding of the
+    1e3-sized inputs."""
+    mv, orc = _mv(), _orc()
+    g = torch.Generator().manual_seed(3)
+    alphas = torch.logspace(-3, 4, 12)
+    if kind == 'dense':
+        n, p, F = 700, 160, 5                                    # p >= 128: band route
+        X = torch.randn(n, p, generator=g) + 1e3 * (1 + torch.arange(p) % 3)
+        B = torch.randn(p, F, generator=g) * 0.3
+        y = (X - X.mean(0)) @ B + 3 * torch.randn(n, F, generator=g) + 50.0
+        m = mv.estimators.RidgeCV(alphas=alphas).fit(X.cuda(), y.cuda())
+        ref = orc.ridge_loo_fit(X.double(), y.double(), alphas.double(), True, False)
+        coef, icpt, loss, alpha = m.coef_, m.intercept_, m.loss_, m.alpha_
+        pred, pred_ref = m.predict(X.cuda()).cpu().double(), orc.ridge_predict(X.double(), ref['coef'], ref['intercept'])
+    else:
+        N, C, Tn, F = 24, 6, 120, 4
+        X = torch.randn(N, C, Tn, generator=g) + torch.tensor([1e3, -2e3, 5e2, 0.0, 3e3, 1e3])[None, :, None]
+        y = torch.randn(N, F, Tn, generator=g) + 0.3 * (X[:, :F] - X[:, :F].mean((0, 2), keepdim=True)) + 7.0
+        td = mv.estimators.TimeDelayed(-0.25, 0.0, 100, alphas=alphas).fit(X.cuda(), y.cuda())       # 26 lags, p = 156
+        win = orc.lag_window(-0.25, 0.0, 100)
+        ref = orc.trf_fit(X.double(), y.double(), win, alphas.double())
+        ref['coef'] = ref['flat_coef']
+        coef, icpt, loss, alpha = td.estimator.coef_, td.intercept_, td.estimator.loss_, td.estimator.alpha_
+        pred, pred_ref = td.predict(X.cuda()).cpu().double(), orc.trf_predict(X.double(), win, ref['flat_coef'], ref['intercept'])
+    assert float(alpha) == float(ref['alpha'].float())
+    assert ((loss.cpu().double() - ref['losses']).abs() / ref['losses']).max().item() < 1e-4
+    assert ((coef.cpu().double() - ref['coef']).norm() / ref['coef'].norm()).item() < 1e-4
+    # the intercept absorbs mean * coef (1e3-sized terms): compare at the rounding of those terms
+    scale = float((ref['coef'].abs() @ (X.double().reshape(-1, coef.shape[1]).abs().mean(0) if kind == 'dense' else
+                                        torch.full((coef.shape[1],), 1.5e3, dtype=torch.float64))).max())
+    assert (icpt.cpu().double().reshape(-1) - ref['intercept'].reshape(-1)).abs().max().item() < 2e-6 * scale
+    assert ((pred - pred_ref).norm() / (pred_ref - pred_ref.mean()).norm()).item() < 1e-3
+
+
+def test_wide_problem_beyond_2048_columns_takes_the_dual_route():
+    """No more rows than columns with p > 2048 (a TRF with few training trials): the reference switches to the n x n dual
+    eigendecomposition (ridgecv.py:135-205); the Gram route cannot form 1 - leverage in fp32 there.  fp32 inputs, fp64 dual
+    route on the library's kernels: chosen alpha identical, coefficients (the minimum-norm solution duals^T X) and
+    predictions against the oracle's restatement of the same branch; beyond 2048 rows the regime is refused loudly."""
+    mv, orc = _mv(), _orc()
+    g = torch.Generator().manual_seed(9)
+    N, C, Tn, F = 4, 12, 100, 3                                   # n = 400 rows, p = 12 * 201 = 2412 columns
+    X = torch.randn(N, C, Tn, generator=g)
+    y = torch.randn(N, F, Tn, generator=g) + 0.5 * X[:, :F]
+    alphas = torch.logspace(-2, 4, 10)
+    win = orc.lag_window(-1.0, 0.0, 200)
+    for icpt, per_target in ((True, False), (False, True)):
+        td = mv.estimators.TimeDelayed(-1.0, 0.0, 200, alphas=alphas, fit_intercept=icpt, alpha_per_target=per_target).fit(X.cuda(), y.cuda())
+        ref = orc.trf_fit(X.double(), y.double(), win, alphas.double(), fit_intercept=icpt, alpha_per_target=per_target)
+        assert torch.equal(td.estimator.alpha_.cpu().reshape(-1), ref['alpha'].float().reshape(-1))
+        assert td.estimator.coef_.dtype == torch.float32
+        assert ((td.estimator.coef_.cpu().double() - ref['flat_coef']).norm() / ref['flat_coef'].norm()).item() < 1e-5
+        yh = td.predict(X.cuda()).cpu().double()
+        yh_ref = orc.trf_predict(X.double(), win, ref['flat_coef'], ref['intercept'])
+        assert ((yh - yh_ref).norm() / yh_ref.norm()).item() < 1e-5
+    from mvpy_b200 import _lib
+    Xb = torch.randn(6, 13, 400, generator=g)                     # n = 2400 rows <= p = 2613 columns, more than 2048 rows
+    with pytest.raises(_lib.MvbError, match='no more rows than columns'):
+        mv.estimators.TimeDelayed(-1.0, 0.0, 200, alphas=alphas).fit(Xb.cuda(), torch.randn(6, 2, 400, generator=g).cuda())
