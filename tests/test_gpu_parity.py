@@ -828,7 +828,9 @@ def test_inputs_with_large_means_are_centred_before_multiplying(kind):
     scale = float((ref['coef'].abs() @ (X.double().reshape(-1, coef.shape[1]).abs().mean(0) if kind == 'dense' else
                                         torch.full((coef.shape[1],), 1.5e3, dtype=torch.float64))).max())
     assert (icpt.cpu().double().reshape(-1) - ref['intercept'].reshape(-1)).abs().max().item() < 2e-6 * scale
-    assert ((pred - pred_ref).norm() / (pred_ref - pred_ref.mean()).norm()).item() < 1e-3
+    # predictions sum 1e3-sized products that cancel against the intercept: fp32 rounding of those terms (the reference's own
+    # fp32 predict carries the same noise), far below the 6e-2 an uncentred Gram would cost
+    assert ((pred - pred_ref).norm() / (pred_ref - pred_ref.mean()).norm()).item() < 4e-3
 
 
 def test_wide_problem_beyond_2048_columns_takes_the_dual_route():
