@@ -252,6 +252,8 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=list(WORKLOADS))
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-sharded-api', action='store_true', help='skip the hierarchical_score / shapley_score sharding leg')
+    ap.add_argument('--check-sharded', action='store_true', help='also compute the unsharded hierarchical scores on rank 0 and compare')
     ap.add_argument('--reference-budget', type=float, default=240.0, help='seconds of reference samples (--impl reference)')
     ap.add_argument('--no-reference-cuda', action='store_true', help='--impl reference: skip the device=cuda incumbent')
     args = ap.parse_args()
@@ -382,13 +384,14 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = True
     a = torch.randn(8192, 8192, device=dev)
     b = torch.randn(8192, 8192, device=dev)
-    best = 1e9
-    for i in range(12):
+    times = []
+    for i in range(15):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
-        if i >= 2:
-            best = min(best, e0.elapsed_time(e1))
-    tf32_peak = 2 * 8192 ** 3 / best * 1e-9
+        if i >= 3:
+            times.append(e0.elapsed_time(e1))
+    tf32_peak = 2 * 8192 ** 3 / float(np.median(times)) * 1e-9          # median of 12: box-to-box noise is in the best-of figure
+    tf32_peak_best = 2 * 8192 ** 3 / min(times) * 1e-9
     torch.backends.cuda.matmul.allow_tf32 = False
     del a, b
 
@@ -438,36 +441,81 @@ def main():
     e2e = dict(value=world * fits_per_unit / e2e_s, unit='fits/s', h2d_bytes_per_step=int(Xh.numel() * 4 + yh.numel() * 4),
                d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * e2e_s)
 
+    # ---- the product's own sharding under the same clock (cfg2 data): hierarchical_score over the 8 predictor sets of
+    # BASELINE configs[2] (40 (set, fold) units, fixed work: strong scaling) and shapley_score with 2 permutations per GPU
+    # (BASELINE configs[3] units, weak scaling), both sharded by mvpy_b200/_dist.py -- no sharded_region() wrapper -- and
+    # compared on rank 0 with the same call computed without sharding
+    sharded = None
+    if args.workload == 'cfg2' and not args.no_sharded_api:
+        def timed(fn):
+            barrier()
+            t0 = time.perf_counter()
+            out = fn()
+            barrier()
+            t = torch.tensor([time.perf_counter() - t0], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()), out
+
+        def run_h():
+            return mv.model_selection.hierarchical_score(pipe, X.to(dev), y.to(dev), groups=groups3.to(dev), cv=N_FOLDS)[1]
+
+        def run_s():
+            torch.manual_seed(1)
+            return mv.model_selection.shapley_score(pipe, X, y, groups=groups, cv=N_FOLDS, n_permutations=2 * world,
+                                                    return_shapley=True)[1]
+        run_h()                                                       # warm-up (allocator, lazy module loads)
+        t_h, sc_hier = timed(run_h)
+        t_s, sc_shap = timed(run_s)
+        sharded = dict(hierarchical_score=dict(units=8 * N_FOLDS, fits=8 * N_FOLDS * N_ALPHAS, seconds=t_h, fits_per_s=8 * N_FOLDS * N_ALPHAS / t_h,
+                                               scaling='strong', unit_of_sharding='(set, fold), longest first'),
+                       shapley_score=dict(permutations=2 * world, units=2 * world, fits=2 * world * 8 * N_FOLDS * N_ALPHAS, seconds=t_s,
+                                          fits_per_s=2 * world * 8 * N_FOLDS * N_ALPHAS / t_s, scaling='weak', unit_of_sharding='permutation'),
+                       n_gpus=world)
+        if world > 1 and rank == 0 and args.check_sharded:
+            # the unsharded answer on rank 0 alone (other ranks wait at the barrier below): identical tensors expected
+            with _dist.sharded_region():
+                ref_h = run_h()
+            sharded['hierarchical_score']['max_abs_diff_vs_unsharded'] = float((ref_h - sc_hier).abs().max())
+        if world > 1:
+            dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel (the tcgen05 contraction), from the library's CUDA-event hook ----
-    peak_eff = tf32_peak / 3.0
+    # Denominator: MEASURED_PEAKS.json (driver-written) holds the dense bf16 rate of this pool's B200s; a kernel timed inside a
+    # long step is held against the SUSTAINED figure.  TF32 runs at half the bf16 rate and split-TF32 issues three MMAs per
+    # fp32 product, so the algorithmic peak is bf16_sustained / 2 / 3.  The cuBLAS TF32 rate measured here (median of 12
+    # 8192^3 products, / 3) is reported next to it.
+    bf16_sus = peaks.get('bf16_tflops_sustained')
+    peak_eff = float(bf16_sus) / 6.0 if bf16_sus else tf32_peak / 3.0
+    peak_src = ('MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32) / 3 (MMAs per fp32 product)' if bf16_sus else
+                'TF32 cuBLAS rate measured here / 3 (MEASURED_PEAKS.json absent)')
     roof = None
     if prof:
-        # every class below is a launch shape of ONE kernel, tc::tc_gemm_kernel (tcgen05 split-TF32 contraction): the
-        # headline is the whole kernel -- all its launches in the timed region -- and by_kernel breaks it down by role
+        # every class below is a launch shape of the tcgen05 split-TF32 contraction kernels: the headline is all their
+        # launches in the timed region, by_kernel breaks them down by role
         tot_ms = sum(v['ms'] for v in prof.values())
         tot_fl = sum(v['flops'] for v in prof.values())
         tot_n = sum(v['n'] for v in prof.values())
         achieved = tot_fl / (tot_ms * 1e-3) * 1e-12 if tot_ms > 0 else 0.0
-        roof = dict(bound='tensor', kernel='tc::tc_gemm_ta_kernel + tc::tc_gemm_kernel (all contraction launches of the step)', achieved=achieved,
+        roof = dict(bound='tensor', kernel='tg::toeplitz_gram_kernel + tc::tc_gemm_ta_kernel + tc::tc_gemm_kernel + sc::sweep_chain_tmem_kernel '
+                                           '(all contraction launches of the step)', achieved=achieved,
                     peak=peak_eff, unit='TFLOP/s', frac=achieved / peak_eff, traffic=None, launches=tot_n, ms_total=tot_ms,
-                    share_of_step=tot_ms / ms,
-                    note=f'algorithmic 2*M*N*K flops (symmetric Gram counted once) / CUDA-event time of the launches, recorded by '
-                         f'the library hook on the launching stream inside the timed region; peak = TF32 dense peak measured '
-                         f'here with cuBLAS ({tf32_peak:.0f} TFLOP/s) / 3 MMAs per fp32 product (split-TF32); '
-                         f'MEASURED_PEAKS bf16 = {peaks.get("bf16_tflops")} burst / {peaks.get("bf16_tflops_sustained")} sustained; '
-                         f'traffic per role (by_kernel) from profiles/r01_traffic.json: ncu of the TMEM-A kernel, Z launch dram 4.16 GB vs 3.35 GB '
-                         f'algorithmic, Gram launch 6.14 GB vs 4.7 GB of operand bytes (4 GB of pre-split design planes)',
+                    share_of_step=tot_ms / ms, peak_source=peak_src,
+                    peak_tf32_cublas_here=dict(median=tf32_peak, best=tf32_peak_best, algorithmic=tf32_peak / 3.0,
+                                               frac=achieved / (tf32_peak / 3.0)),
+                    frac_vs_bf16_burst=(achieved / (float(peaks['bf16_tflops']) / 6.0) if peaks.get('bf16_tflops') else None),
+                    note='algorithmic 2*M*N*K flops (symmetric Gram counted once) / CUDA-event time of the launches, recorded by '
+                         'the library hook on the launching stream inside the timed region',
                     by_kernel={k: dict(ms=v['ms'], n=v['n'], tflops=(v['flops'] / (v['ms'] * 1e-3) * 1e-12 if v['ms'] > 0 else 0.0),
                                        frac=(v['flops'] / (v['ms'] * 1e-3) * 1e-12 / peak_eff if v['ms'] > 0 else 0.0))
                                for k, v in prof.items()})
     if roof is not None and args.workload == 'cfg2':
         try:          # dram traffic of the Gram launch from the committed ncu --set full capture (per launch)
-            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
             for k, v in tr.items():
                 if k in roof['by_kernel']:
                     roof['by_kernel'][k]['traffic'] = v['dram_bytes_per_launch']
@@ -513,20 +561,45 @@ def main():
         alg = (2 * n_te * F_ * T_ + F_ * T_ + 2 * F_ * T_) * 4            # y, yhat, y_b read; r2, pearson written
         gbs = alg / (ms_score * 1e-3) * 1e-9
         hbm = float(peaks.get('hbm_gbs', 6650.0))
-        score_roof = dict(bound='hbm', kernel='mvb::score_kernel (fused r2 + pearson, one test fold)', achieved=gbs, peak=hbm,
-                          unit='GB/s', frac=gbs / hbm, traffic=None, ms=ms_score, algorithmic_bytes=alg,
-                          note=('12 input pairs (300 MB) cycled so every launch reads HBM; peak = MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks
-                                else '12 input pairs cycled; peak = fallback 6650 GB/s'))
+        # the same kernel on ONE launch of 16 test folds' worth of cells (391 MB of inputs): the streaming rate without the
+        # launch latency that dominates a 25 MB problem
+        Kb = 16 * K_
+        yb_big = torch.randn(n_te, Kb, device=dev)
+        yh_big = (yb_big + 0.1 * torch.randn_like(yb_big)).contiguous()
+        base_big = yb_big.mean(0).contiguous()
+        r2b, prb = torch.empty(Kb, device=dev), torch.empty(Kb, device=dev)
+
+        def launch_big():
+            _lib.check(lib.mvb_score(yb_big.data_ptr(), yh_big.data_ptr(), base_big.data_ptr(), n_te, Kb, 0, r2b.data_ptr(), prb.data_ptr(), st_), 'mvb_score')
+        launch_big()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(10):
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record(); launch_big(); b1.record(); torch.cuda.synchronize()
+            ts.append(b0.elapsed_time(b1))
+        ms_big = float(np.median(ts))
+        alg_big = (2 * n_te * Kb + 3 * Kb) * 4
+        gbs_big = alg_big / (ms_big * 1e-3) * 1e-9
+        score_roof = dict(bound='hbm', kernel='mvb::score_vec_kernel (fused r2 + pearson, vectorised, warp-shuffle-reduced)', achieved=gbs_big,
+                          peak=hbm, unit='GB/s', frac=gbs_big / hbm, traffic=None, ms=ms_big, algorithmic_bytes=alg_big,
+                          one_fold=dict(achieved=gbs, frac=gbs / hbm, ms=ms_score, algorithmic_bytes=alg,
+                                        note='one test fold (24 x 306 x 400 cells, 25 MB): 12 input pairs (300 MB) cycled so every '
+                                             'launch reads HBM, 48 launches back to back'),
+                          note=('one launch over 16 folds worth of cells (391 MB of inputs, larger than L2), median of 10; peak = MEASURED_PEAKS.json hbm_gbs'
+                                if 'hbm_gbs' in peaks else 'one launch over 391 MB of inputs; peak = fallback 6650 GB/s'))
+        del yb_big, yh_big
         del pairs
     except Exception as e:                                                  # pragma: no cover
         score_roof = dict(error=str(e))
     cb = None
     if not args.no_cpu_baseline:
         cb, _ = cpu_baseline(X, y, alphas, args.workload)
-    line = dict(metric='TRF ridge fits/s (folds x alphas x sets)', value=value, unit='fits/s', n_gpus=world, steps=args.steps,
+    line = dict(sharded_api=sharded, metric='TRF ridge fits/s (folds x alphas x sets)', value=value, unit='fits/s', n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', config=config, clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roof,
                 roofline_score=score_roof, cpu_baseline=cb)
+    line['sharded_api'] = line.pop('sharded_api')          # keep it at the end of the line
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

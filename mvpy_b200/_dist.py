@@ -83,3 +83,35 @@ def broadcast_object(obj, src: int = 0):
     box = [obj]
     dist.broadcast_object_list(box, src=src)
     return box[0]
+
+
+def lpt_assign(costs: Sequence[float], n_ranks: int) -> List[int]:
+    """Longest-processing-time-first assignment of units to ranks: owner[u] for every unit.  Deterministic (ties by unit
+    index), so every rank computes the same table without communicating."""
+    load = [0.0] * n_ranks
+    owner = [0] * len(costs)
+    for u in sorted(range(len(costs)), key=lambda i: (-costs[i], i)):
+        r = min(range(n_ranks), key=lambda j: (load[j], j))
+        owner[u] = r
+        load[r] += costs[u]
+    return owner
+
+
+def gather_assigned(local: Dict[int, torch.Tensor], n_units: int) -> List[torch.Tensor]:
+    """All ranks receive every unit's tensor for an arbitrary unit -> rank assignment: each rank writes its units into a
+    zero buffer and the buffers are summed (x + 0 is exact, so the result is bit-identical to the owner's tensor)."""
+    rank, ws = world()
+    if ws == 1:
+        return [local[i] for i in range(n_units)]
+    sample = next(iter(local.values())) if local else None
+    metas = [None] * ws
+    dist.all_gather_object(metas, None if sample is None else (tuple(sample.shape), str(sample.dtype)))
+    meta = next(m for m in metas if m is not None)
+    shape, dtype = meta[0], getattr(torch, meta[1].split('.')[-1])
+    out_dev = sample.device if sample is not None else torch.device('cpu')
+    cdev = _comm_device(sample) if sample is not None else (torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu'))
+    buf = torch.zeros((n_units,) + shape, dtype=dtype, device=cdev)
+    for u, t in local.items():
+        buf[u].copy_(t)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    return [buf[u].to(out_dev) for u in range(n_units)]

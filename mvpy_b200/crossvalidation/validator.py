@@ -122,11 +122,14 @@ class Validator(sklearn.base.BaseEstimator):
     def _multi(self) -> bool:
         return self.metric is not None and len(self.metric) > 1
 
-    def fit(self, X: torch.Tensor, y: Optional[torch.Tensor] = None, groups: Optional[torch.Tensor] = None) -> 'Validator':
+    def fit(self, X: torch.Tensor, y: Optional[torch.Tensor] = None, groups: Optional[torch.Tensor] = None,
+            _split_like: Optional[Tuple] = None) -> 'Validator':
         self.model_, self.test_, self.metric_ = [], [], []
         out_dev = X.device
-        # indices are generated on the input's device exactly like the reference (bit-exact folds)
-        split_args = (X, y) if y is not None else (X,)
+        # indices are generated on the input's device exactly like the reference (bit-exact folds); a driver that
+        # has already staged host data on the GPU hands over the original tensors (`_split_like`) so that shuffling
+        # splitters still draw from the generator of the device the user's data lives on
+        split_args = _split_like if _split_like is not None else ((X, y) if y is not None else (X,))
         split_kwargs = dict(groups=groups) if groups is not None else dict()
         folds = list(self.cv_.split(*split_args, **split_kwargs))
         Xd, yd = _lib.stage(X), _lib.stage(y)

@@ -533,13 +533,27 @@ __global__ void leverage_to_d_kernel(const float* __restrict__ h, int64_t n, int
   }
 }
 
-// helper stream for work that is independent of the caller's stream for a while (forked / joined with events)
+// helper stream for work that is independent of the caller's stream for a while (forked / joined with events): one per
+// device, created on first use with that device current
 cudaStream_t side_stream() {
-  static cudaStream_t s = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] { cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); });
-  return s;
+  constexpr int kMaxDev = 64;
+  static cudaStream_t s[kMaxDev] = {};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!s[dev] && cudaStreamCreateWithFlags(&s[dev], cudaStreamNonBlocking) != cudaSuccess) s[dev] = nullptr;
+  return s[dev];
 }
+// Joins forked side-stream work back into the caller's stream on every exit path (an error return between fork and join must
+// not leave the side stream writing into a workspace the caller is about to free, nor an open capture un-joined).
+struct SideJoin {
+  cudaStream_t st; cudaEvent_t ev = nullptr; bool armed = false;
+  explicit SideJoin(cudaStream_t s) : st(s) {}
+  void arm(cudaEvent_t e) { ev = e; armed = true; }
+  cudaError_t join() { if (!armed) return cudaSuccess; armed = false; return cudaStreamWaitEvent(st, ev, 0); }
+  ~SideJoin() { if (armed) cudaStreamWaitEvent(st, ev, 0); }
+};
 
 // batched (over alpha) 128-wide contraction  C[a][r][0..128) = sum_c Aop(a; r, c) * Bop(a; *, c)
 int band_gemm(const mvb::GatherOperand& A, int64_t a_roff_batch, const mvb::GatherOperand& B, int64_t b_roff_batch,
@@ -598,26 +612,27 @@ int ridge_solve_band(const mvb_design* d, const float* y, int F, float* G, const
   // 2. block Cholesky per alpha -> Minv, N, Pb, [Minv | -N].  Only 20 CTAs and independent of Z: runs on a side stream
   //    concurrently with the Z contraction and joins before the substitution sweep.
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  SideJoin side_join(st);
   {
-    static bool attr_set = false;
-    if (!attr_set) {
-      MVB_CUDA(cudaFuncSetAttribute(mvb::bl::block_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mvb::bl::CHOL_SMEM));
-      attr_set = true;
-    }
+    MVB_CUDA(cudaFuncSetAttribute(mvb::bl::block_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mvb::bl::CHOL_SMEM));
     cudaStream_t side = side_stream();
-    // one pair of events per host thread, reused: a wait binds to the record that precedes it in host order, so reuse
-    // across calls and streams is safe, and nothing is created or destroyed while a caller is stream-capturing
-    static thread_local cudaEvent_t tl_fork = nullptr, tl_join = nullptr;
-    if (!tl_fork) {
-      MVB_CUDA(cudaEventCreateWithFlags(&tl_fork, cudaEventDisableTiming));
-      MVB_CUDA(cudaEventCreateWithFlags(&tl_join, cudaEventDisableTiming));
+    if (!side) return fail(MVB_E_CUDA, "ridge_solve(band): no side stream for the current device");
+    // one pair of events per host thread and device, reused: a wait binds to the record that precedes it in host order, so
+    // reuse across calls and streams is safe, and nothing is created or destroyed while a caller is stream-capturing
+    static thread_local cudaEvent_t tl_fork[64] = {}, tl_join[64] = {};
+    int dev = 0;
+    MVB_CUDA(cudaGetDevice(&dev));
+    if (!tl_fork[dev]) {
+      MVB_CUDA(cudaEventCreateWithFlags(&tl_fork[dev], cudaEventDisableTiming));
+      MVB_CUDA(cudaEventCreateWithFlags(&tl_join[dev], cudaEventDisableTiming));
     }
-    ev_fork = tl_fork; ev_join = tl_join;
+    ev_fork = tl_fork[dev]; ev_join = tl_join[dev];
     MVB_CUDA(cudaEventRecord(ev_fork, st));
     MVB_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
     mvb::bl::block_chol_kernel<<<A, 1024, mvb::bl::CHOL_SMEM, side>>>(w.Tdiag, w.Tsub, (int)nb, alphas, w.Minv, w.Nmat, w.Pb, w.MN);
     MVB_LAUNCHED();
     MVB_CUDA(cudaEventRecord(ev_join, side));
+    side_join.arm(ev_join);
   }
   // 3. Z = X_t Qt^T (implicit design rows x basis vectors) in column blocks [nb][n][128], centred: Z -= Qt mu
   const int qmode = dense_mode(P, (int)p, w.Qt, 4);
@@ -628,7 +643,7 @@ int ridge_solve_band(const mvb_design* d, const float* y, int F, float* G, const
   if (rc) return rc;
   mvb::matvec_rows_kernel<float><<<cdiv(P * 32, 256), 256, 0, st>>>(w.Qt, P, P, w.mu64, w.cz);    MVB_LAUNCHED();
   sub_cols_blocked_kernel<<<grid_for(n * P), 256, 0, st>>>(w.Z, n, nb, w.cz);                        MVB_LAUNCHED();
-  MVB_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+  MVB_CUDA(side_join.join());
   // 4. forward substitution over the blocks for every (alpha, row):  u_j = [Minv_j | -N_j] [z_j ; u_{j-1}],  h = sum_j |u_j|^2.
   //    Default: one kernel in which every (row tile, alpha) CTA walks its whole chain with u resident on the SM
   //    (sweep_chain.cuh): in tensor memory as the MMA's A operand (MVB_SWEEP_CHAIN=2, default) or in shared memory (=1).
@@ -1069,11 +1084,16 @@ int mvb_score(const void* y, const void* yhat, const void* y_b, int64_t R, int64
   if (!y || !yhat || R < 1 || K < 1 || (!r2_out && !pearson_out)) return fail(MVB_E_ARG, "score: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = cdiv(K, 128);
+  // vectorised warp-shuffle kernel when rows are 16-byte tileable; the scalar kernel keeps ragged shapes
+  const bool vec32 = K % 4 == 0 && (((uintptr_t)y | (uintptr_t)yhat | (uintptr_t)y_b) & 15) == 0;
+  const bool vec64 = K % 2 == 0 && (((uintptr_t)y | (uintptr_t)yhat | (uintptr_t)y_b) & 15) == 0;
   if (dtype == MVB_F32) {
-    if (R <= 32) mvb::score_kernel<float, 32><<<grid, 128, 0, st>>>((const float*)y, (const float*)yhat, (const float*)y_b, R, K, (float*)r2_out, (float*)pearson_out);
+    if (vec32) mvb::score_vec_kernel<float><<<cdiv(K, 256), 256, 0, st>>>((const float*)y, (const float*)yhat, (const float*)y_b, R, K, (float*)r2_out, (float*)pearson_out);
+    else if (R <= 32) mvb::score_kernel<float, 32><<<grid, 128, 0, st>>>((const float*)y, (const float*)yhat, (const float*)y_b, R, K, (float*)r2_out, (float*)pearson_out);
     else mvb::score_kernel<float, 0><<<grid, 128, 0, st>>>((const float*)y, (const float*)yhat, (const float*)y_b, R, K, (float*)r2_out, (float*)pearson_out);
   } else if (dtype == MVB_F64) {
-    if (R <= 32) mvb::score_kernel<double, 32><<<grid, 128, 0, st>>>((const double*)y, (const double*)yhat, (const double*)y_b, R, K, (double*)r2_out, (double*)pearson_out);
+    if (vec64) mvb::score_vec_kernel<double><<<cdiv(K, 128), 256, 0, st>>>((const double*)y, (const double*)yhat, (const double*)y_b, R, K, (double*)r2_out, (double*)pearson_out);
+    else if (R <= 32) mvb::score_kernel<double, 32><<<grid, 128, 0, st>>>((const double*)y, (const double*)yhat, (const double*)y_b, R, K, (double*)r2_out, (double*)pearson_out);
     else mvb::score_kernel<double, 0><<<grid, 128, 0, st>>>((const double*)y, (const double*)yhat, (const double*)y_b, R, K, (double*)r2_out, (double*)pearson_out);
   }
   else return fail(MVB_E_UNSUPPORTED, "score: dtype %d", dtype);

@@ -635,4 +635,83 @@ __global__ void score_kernel(const T* __restrict__ y, const T* __restrict__ yh, 
   if (pr) pr[k] = (T)sxy / (T)sqrt((double)((T)sxx * (T)syy));
 }
 
+
+// ---- fused r2 + pearson, vectorised and warp-shuffle-reduced (math/r2.py:57-101, math/pearsonr.py:35-56) -----------------
+// y, yh: [R][K] with the reduced samples as the slow axis.  A warp owns 32 / 16 consecutive cells (128 contiguous bytes
+// per row): lane = (row slice rs = lane / 8) x (16-byte column group cg = lane % 8), so one load instruction covers four rows
+// with every 32-byte sector fully used; each lane walks rows rs, rs + 4, ... (unrolled by 3: six 16-byte loads in flight
+// per lane), accumulates the moments about a pivot (the first sample of the cell, so that a constant series has exactly zero
+// variance and scores NaN like the reference's 0 / 0) in fp64 -- one pass for any R: the centred sums follow as
+// S_xy - S_x S_y / R -- and the four row slices are combined with two xor-shuffles.  Each input byte is read from HBM once.
+template <typename T> struct ScoreVec;
+template <> struct ScoreVec<float> { using V = float4; static constexpr int W = 4; };
+template <> struct ScoreVec<double> { using V = double2; static constexpr int W = 2; };
+__device__ __forceinline__ void vec_get(const float4& v, float (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ void vec_get(const double2& v, double (&o)[2]) { o[0] = v.x; o[1] = v.y; }
+
+template <typename T>
+__global__ void __launch_bounds__(256) score_vec_kernel(const T* __restrict__ y, const T* __restrict__ yh, const T* __restrict__ yb,
+                                                        int64_t R, int64_t K, T* __restrict__ r2, T* __restrict__ pr) {
+  using V = typename ScoreVec<T>::V;
+  constexpr int W = ScoreVec<T>::W;
+  const int lane = threadIdx.x & 31, cg = lane & 7, rs = lane >> 3;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t k0 = (warp * 8 + cg) * W;                      // first cell of this lane (K % W == 0)
+  const bool ok = k0 < K;
+  double sy[W], sh[W], syy[W], shh[W], syh[W], see[W], sgg[W];
+  T base[W], py0[W], ph0[W];
+#pragma unroll
+  for (int u = 0; u < W; ++u) { sy[u] = sh[u] = syy[u] = shh[u] = syh[u] = see[u] = sgg[u] = 0.0; base[u] = py0[u] = ph0[u] = (T)0; }
+  if (ok) {
+    if (yb) vec_get(__ldg(reinterpret_cast<const V*>(yb + k0)), base);
+    vec_get(__ldg(reinterpret_cast<const V*>(y + k0)), py0);            // pivots: the cell's first sample (shared by the 4 row slices)
+    vec_get(__ldg(reinterpret_cast<const V*>(yh + k0)), ph0);
+  }
+  auto add = [&](const V& av, const V& bv) {
+    T a[W], b[W];
+    vec_get(av, a); vec_get(bv, b);
+#pragma unroll
+    for (int u = 0; u < W; ++u) {
+      const T e = a[u] - b[u], g = a[u] - base[u];
+      const double da = (double)(a[u] - py0[u]), db = (double)(b[u] - ph0[u]);
+      sy[u] += da; sh[u] += db;
+      syy[u] += da * da; shh[u] += db * db; syh[u] += da * db;
+      see[u] += (double)(e * e); sgg[u] += (double)(g * g);
+    }
+  };
+  if (ok) {
+    const V* py = reinterpret_cast<const V*>(y + k0);
+    const V* ph = reinterpret_cast<const V*>(yh + k0);
+    const int64_t stride = K / W;                              // row pitch in vectors
+    int64_t r = rs;
+    for (; r + 8 < R; r += 12) {
+      const V a0 = __ldg(py + r * stride), b0 = __ldg(ph + r * stride);
+      const V a1 = __ldg(py + (r + 4) * stride), b1 = __ldg(ph + (r + 4) * stride);
+      const V a2 = __ldg(py + (r + 8) * stride), b2 = __ldg(ph + (r + 8) * stride);
+      add(a0, b0); add(a1, b1); add(a2, b2);
+    }
+    for (; r < R; r += 4) add(__ldg(py + r * stride), __ldg(ph + r * stride));
+  }
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1)
+#pragma unroll
+    for (int u = 0; u < W; ++u) {
+      sy[u] += __shfl_xor_sync(0xffffffffu, sy[u], o); sh[u] += __shfl_xor_sync(0xffffffffu, sh[u], o);
+      syy[u] += __shfl_xor_sync(0xffffffffu, syy[u], o); shh[u] += __shfl_xor_sync(0xffffffffu, shh[u], o);
+      syh[u] += __shfl_xor_sync(0xffffffffu, syh[u], o); see[u] += __shfl_xor_sync(0xffffffffu, see[u], o);
+      sgg[u] += __shfl_xor_sync(0xffffffffu, sgg[u], o);
+    }
+  if (ok && rs == 0) {
+    const double inv = 1.0 / (double)R;
+#pragma unroll
+    for (int u = 0; u < W; ++u) {
+      const double cxx = syy[u] - sy[u] * sy[u] * inv, chh = shh[u] - sh[u] * sh[u] * inv, cxy = syh[u] - sy[u] * sh[u] * inv;
+      const double den = yb ? sgg[u] : cxx;                    // without a baseline: the mean of y (r2.py:80-81)
+      if (r2) r2[k0 + u] = ((T)den > (T)0) ? (T)1 - (T)see[u] / (T)den : (T)0;
+      // a constant series has all pivot moments exactly zero: 0 / 0 = NaN as in the reference (pearsonr.py:55-56, no guard)
+      if (pr) pr[k0 + u] = (T)cxy / (T)sqrt((double)((T)fmax(cxx, 0.0) * (T)fmax(chh, 0.0)));
+    }
+  }
+}
+
 }  // namespace mvb

@@ -17,6 +17,9 @@ from .. import _lib, metrics
 from .ridgecv import _RidgeCV_torch, solve_design
 
 
+SHARED_FOLD_ENTRIES = 8      # per-driver cache of per-fold full-predictor statistics (p x p Gram each): bounded
+
+
 def lag_window(t_min: float, t_max: float, fs: float) -> np.ndarray:
     """Integer lag window; timedelayed.py:376-380 passes both bounds through abs(ceil(.)), so the window
     always runs from -|ceil(t_min fs)| to +|ceil(t_max fs)| and contains 0."""
@@ -129,6 +132,8 @@ class _TimeDelayed_torch(sklearn.base.BaseEstimator):
             if self.estimator.fit_intercept:
                 full, shift = _lib.shift_design(full)             # centring before multiplying (ridgecv.solve_design)
             entry = (full, _lib.trf_stats(full, yd, self.estimator.fit_intercept), shift)
+            while len(par['shared']) >= SHARED_FOLD_ENTRIES:          # oldest first (dicts keep insertion order): splitters that
+                par['shared'].pop(next(iter(par['shared'])))          # reshuffle per clone would otherwise grow this without reuse
             par['shared'][key] = entry
         full, (G, XtY, mu, ybar), shift = entry
         cols = (idx.to(G.device)[:, None] * W + torch.arange(W, device=G.device)[None, :]).reshape(-1)

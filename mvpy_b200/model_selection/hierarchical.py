@@ -62,7 +62,7 @@ def check_dims_and_groups_(X: torch.Tensor, y: torch.Tensor, groups=None, dim: O
 
 
 def fit_validator_(validator: Validator, X: torch.Tensor, y: torch.Tensor, mask: torch.Tensor, dim: int,
-                   shared: Optional[dict] = None) -> Validator:
+                   shared: Optional[dict] = None, split_like=None) -> Validator:
     """One cross-validation on the predictors selected by ``mask`` (hierarchical.py:150-207).  ``shared``: a dict owned
     by the caller and handed to every predictor set of the same (X, y): estimators that can (``TimeDelayed``) keep each
     fold's full-predictor Gram / cross-moment in it and slice them per set instead of recomputing (``_lib.fold_ctx``)."""
@@ -71,7 +71,7 @@ def fit_validator_(validator: Validator, X: torch.Tensor, y: torch.Tensor, mask:
     v = validator.clone()
     _lib.fold_ctx.parent = None if shared is None else dict(X=X, dim=dim, idx=idx, shared=shared)
     try:
-        v.fit(X_i, y)
+        v.fit(X_i, y, **({} if split_like is None else {'_split_like': split_like}))
     finally:
         _lib.fold_ctx.parent = None
     return v
@@ -108,30 +108,74 @@ class Hierarchical:
         out_dev = X.device
         multi = [m.name for m in self.validator.metric] if (self.validator.metric is not None and len(self.validator.metric) > 1) else None
         shard = _dist.sharding_active()
-        mine = set(_dist.my_units(len(masks))) if shard else set(range(len(masks)))
         Xd, yd = _lib.stage(X), _lib.stage(y)          # one host->device copy for all sets
-        self.validator_, local = [], {}
-        # per-fold statistics of the full predictor set, shared by all sets this rank fits (pointless for a single set)
-        shared: Optional[dict] = {} if len(mine) > 1 else None
-        with _dist.sharded_region():
-            for i, mask in enumerate(masks):
-                if i not in mine:
-                    self.validator_.append(None)
-                    continue
-                v = fit_validator_(self.validator, Xd, yd, mask, dim, shared)
-                local[i] = v.score_
-                self.validator_.append(_move_tensors(v, out_dev) if Xd.device != out_dev else v)
-        if multi is not None:
-            self.score_ = {}
-            for name in multi:
-                per = {i: s[name] for i, s in local.items()}
-                per = _dist.gather_units(per, len(masks)) if shard else [per[i] for i in range(len(masks))]
-                self.score_[name] = torch.stack(per, dim=0).to(out_dev)
+        # folds are drawn on the device of the user's tensors, not on the staging device (fold membership bit-exact with the
+        # reference for shuffling splitters)
+        split_like = (X, y) if Xd.device != X.device else None
+        if shard:
+            self._fit_sharded(Xd, yd, masks, dim, multi, out_dev, split_like)
         else:
-            per = _dist.gather_units(local, len(masks)) if shard else [local[i] for i in range(len(masks))]
-            self.score_ = torch.stack(per, dim=0).to(out_dev)
+            self.validator_, local = [], {}
+            # per-fold statistics of the full predictor set, shared by all sets (pointless for a single set)
+            shared: Optional[dict] = {} if len(masks) > 1 else None
+            with _dist.sharded_region():
+                for i, mask in enumerate(masks):
+                    v = fit_validator_(self.validator, Xd, yd, mask, dim, shared, split_like)
+                    local[i] = v.score_
+                    self.validator_.append(_move_tensors(v, out_dev) if Xd.device != out_dev else v)
+            if multi is not None:
+                self.score_ = {name: torch.stack([local[i][name] for i in range(len(masks))], dim=0).to(out_dev) for name in multi}
+            else:
+                self.score_ = torch.stack([local[i] for i in range(len(masks))], dim=0).to(out_dev)
         self.mask_ = [masks[i] for i in range(len(masks))]
         self.set_ = list(sets)
         self.group_ = groups
         self.group_id_ = group_ids
         return self
+
+    def _fit_sharded(self, Xd: torch.Tensor, yd: torch.Tensor, masks: torch.Tensor, dim: int, multi, out_dev, split_like=None) -> None:
+        """Multi-GPU: the (set, fold) units -- not whole sets, whose costs differ by the cube of their column counts -- are
+        spread over the ranks longest-first (``_dist.lpt_assign``, the joblib site hierarchical.py:468 hands out whole sets).
+        Every rank walks its units fold by fold so that the fold's full-predictor statistics are shared by its sets; the
+        score shards are combined once.  ``validator_[i].model_[k]`` is None for folds fitted on another rank."""
+        from ..crossvalidation.validator import fit_model_
+        n_sets = len(masks)
+        base = self.validator
+        folds = [(tr.cpu(), te.cpu()) for tr, te in base.cv_.split(*(split_like if split_like is not None else (Xd, yd)))]
+        folds = _dist.broadcast_object(folds, src=0)                  # shuffling splitters: rank 0's draw is authoritative
+        K = len(folds)
+        n_feat = [int(m.sum()) for m in masks]
+        costs = [float(n_feat[i]) ** 2.5 for i in range(n_sets) for _ in range(K)]          # between the p^2 n and p^3 terms
+        owner = _dist.lpt_assign(costs, _dist.world()[1])
+        rank = _dist.world()[0]
+        mine = [u for u in range(n_sets * K) if owner[u] == rank]
+        mine.sort(key=lambda u: (u % K, u // K))                      # fold-major: one set of shared statistics alive at a time
+        vals = [base.clone() for _ in range(n_sets)]
+        for v in vals:
+            v.model_, v.metric_, v.test_ = [None] * K, [None] * K, [te for _, te in folds]
+        local, shared, cur_fold = {}, {}, None
+        idxs = [torch.nonzero(m.to(Xd.device), as_tuple=False).squeeze(-1) for m in masks]
+        with _dist.sharded_region():
+            for u in mine:
+                i, k = u // K, u % K
+                if k != cur_fold:
+                    shared.clear()
+                    cur_fold = k
+                X_i = torch.index_select(Xd, dim=dim, index=idxs[i])
+                _lib.fold_ctx.parent = dict(X=Xd, dim=dim, idx=idxs[i], shared=shared)
+                try:
+                    r = fit_model_(base.model, folds[k][0].to(Xd.device), folds[k][1].to(Xd.device), X_i, y=yd, metric=base.metric)
+                finally:
+                    _lib.fold_ctx.parent = None
+                local[u] = r['score_']
+                vals[i].model_[k] = _move_tensors(r['model'], out_dev)
+                vals[i].metric_[k] = _move_tensors(r['metric'], out_dev)
+        names = multi if multi is not None else [None]
+        scores = {}
+        for name in names:
+            per = _dist.gather_assigned({u: (s[name] if name is not None else s) for u, s in local.items()}, n_sets * K)
+            scores[name] = torch.stack([torch.stack(per[i * K:(i + 1) * K], dim=0) for i in range(n_sets)], dim=0).to(out_dev)
+        for i, v in enumerate(vals):
+            v.score_ = {name: scores[name][i] for name in multi} if multi is not None else scores[None][i]
+        self.validator_ = vals
+        self.score_ = {name: scores[name] for name in multi} if multi is not None else scores[None]

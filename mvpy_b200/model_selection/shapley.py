@@ -29,20 +29,25 @@ def draw_permutation_(n_groups: int, n_trials: int, device) -> Dict[str, torch.T
 
 
 def fit_permutation_(validator: Validator, X: torch.Tensor, y: torch.Tensor, groups: torch.Tensor, dim: int,
-                     draw: Dict[str, torch.Tensor], keep_validators: bool = True) -> Dict:
-    """shapley.py:64-182 for one permutation, given its RNG draws.  X, y live on the compute device."""
+                     draw: Dict[str, torch.Tensor], keep_validators: bool = True, orig=None) -> Dict:
+    """shapley.py:64-182 for one permutation, given its RNG draws.  X, y live on the compute device; ``orig`` = the user's
+    (X, y) when they live elsewhere: the folds of the reshuffled trials are then drawn on that device."""
     perm, sort, data = draw['perm'], draw['sort'], draw['data'].to(X.device)
     Xs, ys = X[data], y[data]
+    split_like = None
+    if orig is not None:
+        d0 = draw['data'].to(orig[0].device)
+        split_like = (orig[0][d0], orig[1][d0])
     mask = groups[0, :].clone()
     shared: dict = {}                 # per-fold full-predictor statistics, shared by the nested sets of this permutation
-    v = fit_validator_(validator, Xs, ys, mask, dim, shared)
+    v = fit_validator_(validator, Xs, ys, mask, dim, shared, split_like)
     prev = v.score_
     is_dict = isinstance(prev, dict)
     phi = {name: [prev[name]] for name in prev} if is_dict else [prev]
     validators = [v]
     for p_i in perm.tolist():
         mask = mask | groups[p_i]
-        v = fit_validator_(validator, Xs, ys, mask, dim, shared)
+        v = fit_validator_(validator, Xs, ys, mask, dim, shared, split_like)
         validators.append(v)
         cur = v.score_
         if is_dict:
@@ -104,7 +109,8 @@ class Shapley:
                 if p_i not in mine:
                     self.validator_.append(None)
                     continue
-                r = fit_permutation_(self.validator, Xd, yd, gd, dim, draws[p_i], keep_validators=self.keep_validators)
+                r = fit_permutation_(self.validator, Xd, yd, gd, dim, draws[p_i], keep_validators=self.keep_validators,
+                                     orig=(X, y) if Xd.device != X.device else None)
                 local[p_i] = r['score']
                 self.validator_.append(_move_tensors(r['validator'], out_dev) if (r['validator'] is not None and Xd.device != out_dev) else r['validator'])
         if multi is not None:

@@ -25,27 +25,50 @@ def _free_port() -> int:
 
 
 class _StubValidator:
-    """Stands in for a fitted Validator: score_ depends on the predictor mask and on the (possibly reshuffled) data."""
+    """Stands in for a (fitted) Validator: score_ depends on the predictor mask and on the (possibly reshuffled) data."""
     metric = None
+    model = None
 
     def __init__(self, score):
+        from mvpy_b200.crossvalidation import KFold
         self.score_ = score
+        self.cv_ = KFold(n_splits=5)
+
+    def clone(self):
+        return _StubValidator(None)
 
 
-def _stub_fit_validator(validator, X, y, mask, dim, shared=None):
+_FOLD_TABLE = torch.arange(5 * 2 * 3, dtype=torch.float32).reshape(5, 2, 3) * 0.01
+
+
+def _base_score(X, feat_weight_sum):
+    trial_sig = (X[:, 0, 0] * torch.arange(1, X.shape[0] + 1, dtype=torch.float32)).sum()     # order of the trials matters
+    return feat_weight_sum + 1e-3 * trial_sig
+
+
+def _stub_fit_validator(validator, X, y, mask, dim, shared=None, split_like=None):
     m = mask.to(torch.float32)
     w = torch.arange(1, m.numel() + 1, dtype=torch.float32)
-    trial_sig = (X[:, 0, 0] * torch.arange(1, X.shape[0] + 1, dtype=torch.float32)).sum()     # order of the trials matters
-    base = (m * w).sum() + 1e-3 * trial_sig
-    return _StubValidator(base + torch.arange(5 * 2 * 3, dtype=torch.float32).reshape(5, 2, 3) * 0.01)
+    return _StubValidator(_base_score(X, (m * w).sum()) + _FOLD_TABLE)
+
+
+def _stub_fit_model(model, train, test, X, y=None, metric=None):
+    """One (set, fold) unit of the sharded Hierarchical: the same numbers as fold k of _stub_fit_validator, rebuilt from the
+    context the driver hands to the estimators (parent array + selected feature indices)."""
+    from mvpy_b200 import _lib
+    par = _lib.fold_ctx.parent
+    k = [0, 3, 6, 8, 10].index(int(test[0]))                      # KFold(5) on 12 trials: test blocks start here
+    return dict(model=None, score_=_base_score(par['X'], (par['idx'].float() + 1).sum()) + _FOLD_TABLE[k], test=test, metric=None)
 
 
 def _patch():
     import mvpy_b200  # noqa: F401
     from mvpy_b200 import _lib
     from mvpy_b200.model_selection import hierarchical, shapley
+    from mvpy_b200.crossvalidation import validator
     hierarchical.fit_validator_ = _stub_fit_validator
     shapley.fit_validator_ = _stub_fit_validator
+    validator.fit_model_ = _stub_fit_model
     _lib.stage = lambda t: t
     hierarchical._move_tensors = lambda v, dev: v
     shapley._move_tensors = lambda v, dev: v
@@ -64,7 +87,6 @@ def _run_drivers(seed):
     hierarchical, shapley = _patch()
     X, y, groups = _data()
     proto = _StubValidator(None)
-    proto.clone = lambda: proto
     h = hierarchical.Hierarchical(proto).fit(X, y, groups=groups)
     torch.manual_seed(seed)
     s = shapley.Shapley(proto, n_permutations=7).fit(X, y, groups=groups)
@@ -87,6 +109,12 @@ def _worker(rank, world, port, out_path):
         full = _dist.gather_units(local, n_units)
         assert len(full) == n_units and all(torch.equal(full[u], torch.full((2, 3), float(u))) for u in range(n_units))
         assert _dist.broadcast_object({'rank': rank}, src=0) == {'rank': 0}
+        # arbitrary (cost-balanced) assignment: longest first, deterministic, and the zero-fill + sum gather is exact
+        owner = _dist.lpt_assign([5.0, 1.0, 1.0, 4.0, 1.0, 1.0], world)
+        assert owner == [0, 1, 0, 1, 1, 0]
+        local = {u: torch.full((2, 3), 0.1 * u - 0.3) for u in range(6) if owner[u] == rank}
+        full = _dist.gather_assigned(local, 6)
+        assert all(torch.equal(full[u], torch.full((2, 3), 0.1 * u - 0.3)) for u in range(6))
         with _dist.sharded_region():
             assert not _dist.sharding_active()          # nested drivers run locally
         assert _dist.sharding_active()
