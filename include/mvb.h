@@ -186,6 +186,15 @@ int mvb_penalised_solve(const void* G, const void* reg, const void* alphas, int 
 int mvb_accuracy(const void* y, const void* yhat, int64_t R, int64_t K, int dtype, void* out, void* stream);
 int mvb_roc_auc(const void* positive, const void* score, int64_t R, int64_t K, int dtype, void* out, void* stream);
 
+/* mvb_pairwise_coupling: multiclass probabilities of a one-versus-one classifier from its pairwise probabilities,
+ * replaces _pairwise_coupling_torch + _compute_Qr_torch (estimators/classifier.py:527-653; call site :958-975).
+ * pairwise [n_samples][K][K] (entry [j][k] = probability of class j in the (j, k) classifier), out [n_samples][K].
+ * All samples iterate until the largest change over the batch is < tol, like the reference; K <= 16.
+ * The repeated-index in-place updates of the reference (last write wins) are reproduced.                        */
+size_t mvb_pairwise_coupling_workspace_bytes(int64_t n_samples, int n_classes, int max_iter);
+int mvb_pairwise_coupling(const void* pairwise, int64_t n_samples, int n_classes, int max_iter, double eps, double tol, int dtype,
+                          void* out, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

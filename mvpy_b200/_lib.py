@@ -73,6 +73,9 @@ _SIGNATURES = {
     'mvb_rank': (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     'mvb_accuracy': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     'mvb_roc_auc': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    'mvb_pairwise_coupling_workspace_bytes': (c_size_t, [c_int64, c_int, c_int]),
+    'mvb_pairwise_coupling': (c_int, [c_void_p, c_int64, c_int, c_int, ctypes.c_double, ctypes.c_double, c_int, c_void_p, c_void_p, c_size_t,
+                                      c_void_p]),
     'mvb_rf_assemble': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'mvb_sum_slabs': (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'mvb_penalised_solve': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -350,6 +353,18 @@ def roc_auc_rows(pos2: torch.Tensor, score2: torch.Tensor) -> torch.Tensor:
     R, K = pos2.shape
     out = torch.empty(K, dtype=pos2.dtype, device=pos2.device)
     check(load().mvb_roc_auc(_ptr(pos2), _ptr(score2), R, K, dtype_code(pos2), _ptr(out), _stream(pos2)), 'mvb_roc_auc')
+    return out
+
+
+def pairwise_coupling(p_pair: torch.Tensor, max_iter: int, eps: float, tol: float) -> torch.Tensor:
+    """p_pair (N, K, K) pairwise probabilities -> (N, K) coupled class probabilities (Wu-Lin, reference semantics)."""
+    p_pair = p_pair.contiguous()
+    N, K, _ = p_pair.shape
+    out = torch.empty((N, K), dtype=p_pair.dtype, device=p_pair.device)
+    lib = load()
+    ws = _workspace(lib.mvb_pairwise_coupling_workspace_bytes(N, K, max_iter), p_pair.device)
+    check(lib.mvb_pairwise_coupling(_ptr(p_pair), N, K, int(max_iter), float(eps), float(tol), dtype_code(p_pair), _ptr(out), _ptr(ws),
+                                    ws.numel(), _stream(p_pair)), 'mvb_pairwise_coupling')
     return out
 
 

@@ -1088,11 +1088,11 @@ int mvb_score(const void* y, const void* yhat, const void* y_b, int64_t R, int64
   const bool vec32 = K % 4 == 0 && (((uintptr_t)y | (uintptr_t)yhat | (uintptr_t)y_b) & 15) == 0;
   const bool vec64 = K % 2 == 0 && (((uintptr_t)y | (uintptr_t)yhat | (uintptr_t)y_b) & 15) == 0;
   if (dtype == MVB_F32) {
-    if (vec32) mvb::score_vec_kernel<float><<<cdiv(K, 256), 256, 0, st>>>((const float*)y, (const float*)yhat, (const float*)y_b, R, K, (float*)r2_out, (float*)pearson_out);
+    if (vec32) mvb::score_vec_kernel<float><<<cdiv(K, 128), 128, 0, st>>>((const float*)y, (const float*)yhat, (const float*)y_b, R, K, (float*)r2_out, (float*)pearson_out);
     else if (R <= 32) mvb::score_kernel<float, 32><<<grid, 128, 0, st>>>((const float*)y, (const float*)yhat, (const float*)y_b, R, K, (float*)r2_out, (float*)pearson_out);
     else mvb::score_kernel<float, 0><<<grid, 128, 0, st>>>((const float*)y, (const float*)yhat, (const float*)y_b, R, K, (float*)r2_out, (float*)pearson_out);
   } else if (dtype == MVB_F64) {
-    if (vec64) mvb::score_vec_kernel<double><<<cdiv(K, 128), 256, 0, st>>>((const double*)y, (const double*)yhat, (const double*)y_b, R, K, (double*)r2_out, (double*)pearson_out);
+    if (vec64) mvb::score_vec_kernel<double><<<cdiv(K, 64), 128, 0, st>>>((const double*)y, (const double*)yhat, (const double*)y_b, R, K, (double*)r2_out, (double*)pearson_out);
     else if (R <= 32) mvb::score_kernel<double, 32><<<grid, 128, 0, st>>>((const double*)y, (const double*)yhat, (const double*)y_b, R, K, (double*)r2_out, (double*)pearson_out);
     else mvb::score_kernel<double, 0><<<grid, 128, 0, st>>>((const double*)y, (const double*)yhat, (const double*)y_b, R, K, (double*)r2_out, (double*)pearson_out);
   }
@@ -1163,6 +1163,34 @@ int mvb_accuracy(const void* y, const void* yhat, int64_t R, int64_t K, int dtyp
   if (dtype == MVB_F32) mvb::accuracy_kernel<float><<<cdiv(K, 128), 128, 0, st>>>((const float*)y, (const float*)yhat, R, K, (float*)out);
   else if (dtype == MVB_F64) mvb::accuracy_kernel<double><<<cdiv(K, 128), 128, 0, st>>>((const double*)y, (const double*)yhat, R, K, (double*)out);
   else return fail(MVB_E_UNSUPPORTED, "accuracy: dtype %d", dtype);
+  MVB_LAUNCHED();
+  return MVB_OK;
+}
+
+size_t mvb_pairwise_coupling_workspace_bytes(int64_t n_samples, int n_classes, int max_iter) {
+  return (size_t)(2 * n_samples * n_classes + max_iter) * sizeof(double) + 256;
+}
+
+int mvb_pairwise_coupling(const void* pairwise, int64_t n_samples, int n_classes, int max_iter, double eps, double tol, int dtype,
+                          void* out, void* ws, size_t ws_bytes, void* stream) {
+  if (!pairwise || !out || !ws || n_samples < 1 || n_classes < 2 || max_iter < 1) return fail(MVB_E_ARG, "pairwise_coupling: bad argument");
+  if (n_classes > mvb::COUPLING_MAX_K) return fail(MVB_E_UNSUPPORTED, "pairwise_coupling: %d classes (at most %d)", n_classes, mvb::COUPLING_MAX_K);
+  if (ws_bytes < mvb_pairwise_coupling_workspace_bytes(n_samples, n_classes, max_iter))
+    return fail(MVB_E_WORKSPACE, "pairwise_coupling: workspace %zu too small", ws_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = n_samples * n_classes;
+  double* buf[2] = {(double*)ws, (double*)ws + total};
+  double* maxdiff = (double*)ws + 2 * total;
+  MVB_CUDA(cudaMemsetAsync(maxdiff, 0, (size_t)max_iter * sizeof(double), st));
+  const int grid = cdiv(n_samples, 64);
+  for (int it = 0; it < max_iter; ++it) {
+    if (dtype == MVB_F32) mvb::coupling_step_kernel<float><<<grid, 64, 0, st>>>((const float*)pairwise, (int)n_samples, n_classes, eps, tol, it, buf[it & 1], buf[(it + 1) & 1], maxdiff);
+    else if (dtype == MVB_F64) mvb::coupling_step_kernel<double><<<grid, 64, 0, st>>>((const double*)pairwise, (int)n_samples, n_classes, eps, tol, it, buf[it & 1], buf[(it + 1) & 1], maxdiff);
+    else return fail(MVB_E_UNSUPPORTED, "pairwise_coupling: dtype %d", dtype);
+    MVB_LAUNCHED();
+  }
+  if (dtype == MVB_F32) mvb::coupling_finish_kernel<float><<<grid_for(total), 256, 0, st>>>(buf[0], buf[1], maxdiff, max_iter, tol, total, (float*)out);
+  else mvb::coupling_finish_kernel<double><<<grid_for(total), 256, 0, st>>>(buf[0], buf[1], maxdiff, max_iter, tol, total, (double*)out);
   MVB_LAUNCHED();
   return MVB_OK;
 }

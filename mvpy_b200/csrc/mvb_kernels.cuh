@@ -650,7 +650,7 @@ __device__ __forceinline__ void vec_get(const float4& v, float (&o)[4]) { o[0] =
 __device__ __forceinline__ void vec_get(const double2& v, double (&o)[2]) { o[0] = v.x; o[1] = v.y; }
 
 template <typename T>
-__global__ void __launch_bounds__(256) score_vec_kernel(const T* __restrict__ y, const T* __restrict__ yh, const T* __restrict__ yb,
+__global__ void __launch_bounds__(128) score_vec_kernel(const T* __restrict__ y, const T* __restrict__ yh, const T* __restrict__ yb,
                                                         int64_t R, int64_t K, T* __restrict__ r2, T* __restrict__ pr) {
   using V = typename ScoreVec<T>::V;
   constexpr int W = ScoreVec<T>::W;
@@ -667,30 +667,48 @@ __global__ void __launch_bounds__(256) score_vec_kernel(const T* __restrict__ y,
     vec_get(__ldg(reinterpret_cast<const V*>(y + k0)), py0);            // pivots: the cell's first sample (shared by the 4 row slices)
     vec_get(__ldg(reinterpret_cast<const V*>(yh + k0)), ph0);
   }
+  // Moments of up to CH rows per lane are summed in T (pivot-shifted values, a dozen terms: 1e-7 relative) and then folded
+  // into the fp64 accumulators: fp64 conversions / adds per element would otherwise, not HBM, bound the kernel.
+  T ty[W], th[W], tyy[W], thh[W], tyh[W], tee[W], tgg[W];
+  auto clear = [&]() {
+#pragma unroll
+    for (int u = 0; u < W; ++u) ty[u] = th[u] = tyy[u] = thh[u] = tyh[u] = tee[u] = tgg[u] = (T)0;
+  };
+  auto flush = [&]() {
+#pragma unroll
+    for (int u = 0; u < W; ++u) {
+      sy[u] += (double)ty[u]; sh[u] += (double)th[u]; syy[u] += (double)tyy[u]; shh[u] += (double)thh[u];
+      syh[u] += (double)tyh[u]; see[u] += (double)tee[u]; sgg[u] += (double)tgg[u];
+    }
+    clear();
+  };
   auto add = [&](const V& av, const V& bv) {
     T a[W], b[W];
     vec_get(av, a); vec_get(bv, b);
 #pragma unroll
     for (int u = 0; u < W; ++u) {
-      const T e = a[u] - b[u], g = a[u] - base[u];
-      const double da = (double)(a[u] - py0[u]), db = (double)(b[u] - ph0[u]);
-      sy[u] += da; sh[u] += db;
-      syy[u] += da * da; shh[u] += db * db; syh[u] += da * db;
-      see[u] += (double)(e * e); sgg[u] += (double)(g * g);
+      const T e = a[u] - b[u], g = a[u] - base[u], da = a[u] - py0[u], db = b[u] - ph0[u];
+      ty[u] += da; th[u] += db;
+      tyy[u] = fma(da, da, tyy[u]); thh[u] = fma(db, db, thh[u]); tyh[u] = fma(da, db, tyh[u]);
+      tee[u] = fma(e, e, tee[u]); tgg[u] = fma(g, g, tgg[u]);
     }
   };
+  clear();
   if (ok) {
     const V* py = reinterpret_cast<const V*>(y + k0);
     const V* ph = reinterpret_cast<const V*>(yh + k0);
     const int64_t stride = K / W;                              // row pitch in vectors
     int64_t r = rs;
+    int pending = 0;
     for (; r + 8 < R; r += 12) {
       const V a0 = __ldg(py + r * stride), b0 = __ldg(ph + r * stride);
       const V a1 = __ldg(py + (r + 4) * stride), b1 = __ldg(ph + (r + 4) * stride);
       const V a2 = __ldg(py + (r + 8) * stride), b2 = __ldg(ph + (r + 8) * stride);
       add(a0, b0); add(a1, b1); add(a2, b2);
+      if (++pending == 4) { flush(); pending = 0; }            // 12 rows per lane between folds
     }
     for (; r < R; r += 4) add(__ldg(py + r * stride), __ldg(ph + r * stride));
+    flush();
   }
 #pragma unroll
   for (int o = 8; o <= 16; o <<= 1)
@@ -712,6 +730,91 @@ __global__ void __launch_bounds__(256) score_vec_kernel(const T* __restrict__ y,
       if (pr) pr[k0 + u] = (T)cxy / (T)sqrt((double)((T)fmax(cxx, 0.0) * (T)fmax(chh, 0.0)));
     }
   }
+}
+
+
+// ---- Wu-Lin pairwise coupling of one-versus-one probabilities (estimators/classifier.py:527-653) ----------------------
+// One thread per sample, K <= COUPLING_MAX_K classes, double arithmetic.  The reference builds Q and r with in-place adds
+// over index tensors that repeat (Q[:, j_i, j_i] += ..., r[:, j_i] += ... with j_i = [1, 2, 2, 3, 3, 3, ...]): such an update
+// keeps the LAST write per index instead of accumulating, so the diagonal of Q and r receive, for class j, only the
+// contributions of the pairs (j, j - 1) [as the larger index] and (K - 1, j) [as the smaller]; the off-diagonal entries are
+// per pair.  That is what the reference computes, and what is reproduced here.
+// The reference stops all samples at the first iteration whose largest change over the batch is < tol: iteration `it` is
+// a launch that returns at once when an earlier iteration's maximum (maxdiff[j], j < it) was below tol.
+constexpr int COUPLING_MAX_K = 16;
+template <typename T>
+__global__ void coupling_step_kernel(const T* __restrict__ P, int N, int K, double eps, double tol, int it,
+                                     const double* __restrict__ p_in, double* __restrict__ p_out, double* maxdiff) {
+  for (int j = 0; j < it; ++j)
+    if (maxdiff[j] < tol) return;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  constexpr int KM = COUPLING_MAX_K;
+  double A[KM + 1][KM + 2], p[KM];
+  const T* Pn = P + (int64_t)n * K * K;
+  for (int j = 0; j < K; ++j) p[j] = it == 0 ? 1.0 / K : p_in[(int64_t)n * K + j];
+  for (int a = 0; a <= K; ++a)
+    for (int b = 0; b <= K + 1; ++b) A[a][b] = 0.0;
+  auto terms = [&](int j, int k, double& pij, double& pji, double& w, double& denom) {
+    pij = (double)Pn[j * K + k]; pji = (double)Pn[k * K + j];
+    const double pr = pij * pji;
+    w = 1.0 / (pr < eps ? eps : pr);
+    denom = p[j] + p[k] + eps;
+  };
+  double pij, pji, w, denom;
+  for (int j = 1; j < K; ++j) {                       // "relative to j": the last pair with the larger index j is (j, j - 1)
+    terms(j, j - 1, pij, pji, w, denom);
+    A[j][j] = w * pji / (denom * denom);
+    A[j][K + 1] = w * (pij - p[j] / denom);
+  }
+  for (int k = 0; k < K - 1; ++k) {                   // "relative to k": the last pair with the smaller index k is (K - 1, k)
+    terms(K - 1, k, pij, pji, w, denom);
+    A[k][k] += w * pij / (denom * denom);
+    A[k][K + 1] += w * (pji - p[k] / denom);
+  }
+  for (int j = 1; j < K; ++j)
+    for (int k = 0; k < j; ++k) {
+      terms(j, k, pij, pji, w, denom);
+      A[j][k] -= w * pji / (denom * denom);
+      A[k][j] -= w * pij / (denom * denom);
+    }
+  for (int j = 0; j < K; ++j) { A[j][j] += 1e-9; A[j][K] = 1.0; A[K][j] = 1.0; }      // KKT system [[Q + 1e-9 I, 1], [1^T, 0]]
+  A[K][K] = 0.0; A[K][K + 1] = 0.0;
+  const int M = K + 1;
+  for (int c = 0; c < M; ++c) {                       // Gaussian elimination with partial pivoting (torch.linalg.solve)
+    int piv = c;
+    double best = fabs(A[c][c]);
+    for (int rr = c + 1; rr < M; ++rr) if (fabs(A[rr][c]) > best) { best = fabs(A[rr][c]); piv = rr; }
+    if (piv != c) for (int b = c; b <= M; ++b) { const double t = A[c][b]; A[c][b] = A[piv][b]; A[piv][b] = t; }
+    const double inv = 1.0 / A[c][c];
+    for (int rr = c + 1; rr < M; ++rr) {
+      const double f = A[rr][c] * inv;
+      if (f != 0.0) for (int b = c; b <= M; ++b) A[rr][b] -= f * A[c][b];
+    }
+  }
+  double x[KM + 1];
+  for (int c = M - 1; c >= 0; --c) {
+    double s = A[c][M];
+    for (int b = c + 1; b < M; ++b) s -= A[c][b] * x[b];
+    x[c] = s / A[c][c];
+  }
+  double pn[KM], sum = 0.0, diff = 0.0;
+  for (int j = 0; j < K; ++j) { pn[j] = p[j] + x[j]; if (pn[j] < 0.0) pn[j] = 0.0; sum += pn[j]; }
+  for (int j = 0; j < K; ++j) {
+    pn[j] = sum > eps ? pn[j] / sum : 1.0 / K;
+    diff += fabs(pn[j] - p[j]);
+    p_out[(int64_t)n * K + j] = pn[j];
+  }
+  atomicMax(reinterpret_cast<unsigned long long*>(maxdiff + it), (unsigned long long)__double_as_longlong(diff));   // diff >= 0: bit order = value order
+}
+// the estimate of the iteration that stopped the loop (or of the last one)
+template <typename T>
+__global__ void coupling_finish_kernel(const double* __restrict__ buf0, const double* __restrict__ buf1, const double* __restrict__ maxdiff,
+                                       int max_iter, double tol, int64_t total, T* __restrict__ out) {
+  int c = max_iter - 1;
+  for (int j = 0; j < max_iter; ++j) if (maxdiff[j] < tol) { c = j; break; }
+  const double* src = ((c + 1) & 1) ? buf1 : buf0;          // iteration it reads buf[it & 1], writes buf[(it + 1) & 1]
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) out[e] = (T)src[e];
 }
 
 }  // namespace mvb

@@ -4,7 +4,8 @@
 ``OvR`` hands the labels to one estimator (which binarises them itself and takes the largest decision value per label
 feature).  ``OvO`` fits one estimator per pair of classes of every label feature on the samples of those two classes
 and predicts by majority vote.  Host-side orchestration only: every fit / prediction is the wrapped estimator's CUDA
-path.  ``predict_proba`` for ``OvO`` (Wu-Lin pairwise coupling, classifier.py:573-653) is not provided."""
+path.  ``predict_proba`` for ``OvO`` couples the pairwise probabilities (Wu-Lin, classifier.py:573-653, 913-1000) on the
+``mvb_pairwise_coupling`` kernel."""
 from __future__ import annotations
 
 from typing import Any, Dict, List, Optional, Tuple, Union
@@ -12,7 +13,7 @@ from typing import Any, Dict, List, Optional, Tuple, Union
 import sklearn.base
 import torch
 
-from .. import metrics
+from .. import _lib, metrics
 from ..preprocessing.labelbinariser import _LabelBinariser_torch
 
 
@@ -103,7 +104,20 @@ class _Classifier_torch(sklearn.base.BaseEstimator):
         self._check('predict')
         if self.method == 'OvR':
             return self.estimators_.predict_proba(X)
-        raise NotImplementedError('OvO probabilities (Wu-Lin pairwise coupling) are not part of the B200 build.')
+        out_dev = X.device
+        p_ind = 1 / (1 + torch.exp(-_lib.to_device(self.decision_function(X))))              # (pairs, n, 2)
+        ijk, p = 0, []
+        for i in range(self.binariser_.n_features_):
+            K = int(self.binariser_.n_classes_[i])
+            j_i, k_i = torch.tril_indices(K, K, offset=-1, device=p_ind.device)             # pairwise estimators: lower-triangle order
+            span = torch.arange(ijk, ijk + j_i.shape[0], device=p_ind.device)
+            p_i = torch.zeros((X.shape[0], K, K), dtype=p_ind.dtype, device=p_ind.device)
+            p_i[:, k_i, j_i] = p_ind[span, :, 0].t()
+            p_i[:, j_i, k_i] = p_ind[span, :, 1].t()
+            ijk += j_i.shape[0]
+            eps = 5e-3 / K
+            p.append(_lib.pairwise_coupling(p_i, max(100, K), eps, eps))
+        return torch.cat(p, dim=-1).to(out_dev)
 
     def score(self, X: torch.Tensor, y: torch.Tensor, metric: Optional[Union[metrics.Metric, Tuple[metrics.Metric]]] = None
               ) -> Union[torch.Tensor, Dict[str, torch.Tensor]]:

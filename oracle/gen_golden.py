@@ -24,6 +24,8 @@ Fixtures (all produced through the reference's public classes/functions):
                    penalties, patterns, no edge correction / intercept, causal-only and anticausal-only lag ranges.
   clf.npz          LabelBinariser, math.accuracy / roc_auc, the Roc_auc metric (reference), RidgeClassifier OvR / OvO composed
                    from the reference's binariser and _RidgeCV_torch.
+  coupling.npz     Wu-Lin pairwise coupling (classifier.py:_pairwise_coupling_torch, needs MVPY_COMPILE_TORCH=0) on random pairwise
+                   probabilities, and the one-versus-one predict_proba flow of classifier.py:913-1000 on the clf.npz problem.
   encoder.npz      RidgeEncoder 2-D and 3-D (expanded design).
   cfg1_summary.npz config 1 (README flow, fs=200): per-fold alphas, mean scores, strided score samples.
 """
@@ -448,6 +450,50 @@ def gen_rf():
 
 
 # ---------------------------------------------------------------------------------------- encoder
+def gen_coupling():
+    """One-versus-one probabilities.  The coupling routine itself runs through the reference (plain Python with
+    MVPY_COMPILE_TORCH=0); the predict_proba flow around it (classifier.py:941-975) is composed from the reference's
+    binariser + _RidgeCV_torch because RidgeClassifier cannot be constructed at this commit."""
+    assert os.environ.get('MVPY_COMPILE_TORCH') == '0', 'run with MVPY_COMPILE_TORCH=0 (no C++ toolchain for inductor here)'
+    from mvpy.estimators.classifier import _pairwise_coupling_torch
+    from mvpy.preprocessing.labelbinariser import _LabelBinariser_torch
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    for tag, (N, K, dt) in {'a': (50, 3, torch.float64), 'b': (30, 5, torch.float64), 'c': (12, 2, torch.float64), 'd': (40, 4, torch.float32),
+                            'e': (25, 7, torch.float32)}.items():
+        j_i, k_i = torch.tril_indices(K, K, offset=-1)
+        pind = (torch.rand(len(j_i), N, generator=g, dtype=torch.float64) * 0.96 + 0.02).to(dt)
+        p_i = torch.zeros(N, K, K, dtype=dt)
+        p_i[:, k_i, j_i] = pind.t()
+        p_i[:, j_i, k_i] = (1 - pind).t()
+        eps = 5e-3 / K
+        out[f'{tag}_pair'] = p_i
+        out[f'{tag}_p'] = _pairwise_coupling_torch(p_i, j_i, k_i, max_iter=max(100, K), eps=eps, tol=eps)
+    c = np.load(os.path.join(OUT, 'clf.npz'))
+    X, y, alphas = torch.from_numpy(c['X']), torch.from_numpy(c['y']), torch.from_numpy(c['alphas'])
+    N = X.shape[0]
+    probs = []
+    for i, labels in enumerate((torch.tensor([0.0, 1.0, 2.0]), torch.tensor([5.0, 9.0]))):
+        K = len(labels)
+        dec = []
+        for j in range(K):
+            for k in range(K):
+                if j <= k:
+                    continue
+                sel = (y[:, i] == labels[j]) | (y[:, i] == labels[k])
+                L2 = _LabelBinariser_torch(neg_label=-1.0, pos_label=1.0).fit_transform(y[sel, i][:, None])
+                dec.append(_RidgeCV_torch(alphas=alphas, fit_intercept=True, alpha_per_target=False).fit(X[sel], L2).predict(X))
+        p_ind = 1 / (1 + torch.exp(-torch.stack(dec)))                       # (pairs, n, 2)
+        j_i, k_i = torch.tril_indices(K, K, offset=-1)
+        p_i = torch.zeros((N, K, K), dtype=X.dtype)
+        p_i[:, k_i, j_i] = p_ind[:, :, 0].t()
+        p_i[:, j_i, k_i] = p_ind[:, :, 1].t()
+        eps = 5e-3 / K
+        probs.append(_pairwise_coupling_torch(p_i, j_i, k_i, max_iter=max(100, K), eps=eps, tol=eps))
+    out['ovo_proba'] = torch.cat(probs, dim=-1)
+    save('coupling.npz', **out)
+
+
 def gen_encoder():
     g = torch.Generator().manual_seed(31)
     N, F, T, D = 30, 4, 5, 3
@@ -477,6 +523,6 @@ def gen_cfg1():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['ridgecv', 'delay', 'scaler', 'kfold', 'splitters', 'stratified', 'metrics', 'rank', 'trf_small', 'decoder', 'b2b', 'rf', 'clf', 'encoder', 'cfg1']
+    which = sys.argv[1:] or ['ridgecv', 'delay', 'scaler', 'kfold', 'splitters', 'stratified', 'metrics', 'rank', 'trf_small', 'decoder', 'b2b', 'rf', 'clf', 'coupling', 'encoder', 'cfg1']
     for w in which:
         globals()['gen_' + w]()

@@ -485,6 +485,58 @@ def shapley_trf(X, y, groups, window, alphas, n_permutations=10, cv=5, **kw) -> 
 
 
 # --------------------------------------------------------------------------------------------
+# one-versus-one probabilities: Wu-Lin pairwise coupling      (mvpy/estimators/classifier.py:527-653)
+# --------------------------------------------------------------------------------------------
+
+
+def pairwise_coupling(p_pair: torch.Tensor, max_iter: int, eps: float, tol: float) -> torch.Tensor:
+    """p_pair (N, K, K) -> class probabilities (N, K).  Restates ``_pairwise_coupling_torch`` (classifier.py:573-653) with
+    ``_compute_Qr_torch`` (:527-571) written out per index: the reference's in-place adds over repeated index tensors
+    (``Q[:, j_i, j_i] += ...``, ``r[:, j_i] += ...`` with j_i = [1, 2, 2, 3, 3, 3, ...]) keep the last write per index, so
+    class j's diagonal / right-hand side only see the pairs (j, j - 1) and (K - 1, j); off-diagonal entries are per pair."""
+    N, K, _ = p_pair.shape
+    dt = p_pair.dtype
+    p = torch.full((N, K), 1.0 / K, dtype=dt)
+    eye = torch.eye(K, dtype=dt)
+    ones = torch.ones((N, K, 1), dtype=dt)
+    zeros = torch.zeros((N, 1, 1), dtype=dt)
+
+    def terms(j, k):
+        pij, pji = p_pair[:, j, k], p_pair[:, k, j]
+        w = 1.0 / torch.clamp(pij * pji, min=eps)
+        denom = p[:, j] + p[:, k] + eps
+        return pij, pji, w, denom
+
+    for _ in range(max_iter):
+        Q = torch.zeros((N, K, K), dtype=dt)
+        r = torch.zeros((N, K), dtype=dt)
+        for j in range(1, K):
+            pij, pji, w, denom = terms(j, j - 1)
+            Q[:, j, j] = w * pji / denom ** 2
+            r[:, j] = w * (pij - p[:, j] / denom)
+        for k in range(K - 1):
+            pij, pji, w, denom = terms(K - 1, k)
+            Q[:, k, k] += w * pij / denom ** 2
+            r[:, k] += w * (pji - p[:, k] / denom)
+        for j in range(1, K):
+            for k in range(j):
+                pij, pji, w, denom = terms(j, k)
+                Q[:, j, k] -= w * pji / denom ** 2
+                Q[:, k, j] -= w * pij / denom ** 2
+        A = Q + 1e-9 * eye
+        kkt = torch.cat([torch.cat([A, ones], 2), torch.cat([ones.transpose(1, 2), zeros], 2)], 1)
+        delta = torch.linalg.solve(kkt, torch.cat([r, zeros[:, :, 0]], 1).unsqueeze(2)).squeeze(2)[:, :K]
+        p_n = torch.clamp(p + delta, min=0)
+        s = p_n.sum(1, keepdim=True)
+        p_n = torch.where(s > eps, p_n / s, torch.full_like(p_n, 1.0 / K))
+        done = torch.max(torch.sum(torch.abs(p_n - p), dim=1)) < tol
+        p = p_n
+        if done:
+            break
+    return p
+
+
+# --------------------------------------------------------------------------------------------
 # decoders / encoders / sliding      (mvpy/estimators/ridgedecoder.py:244-310,
 #                                     mvpy/estimators/ridgeencoder.py:273-382, sliding.py:575-622)
 # --------------------------------------------------------------------------------------------

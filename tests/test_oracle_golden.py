@@ -214,3 +214,15 @@ def test_receptive_field_reference_cases(golden):
         assert np.array_equal(orc.rf_regulariser(C, W, rt).numpy(), g[f'reg{i}']), (C, W, rt)
     with pytest.raises(ValueError):
         orc.rf_regulariser(2, 3, 'lasso')
+
+
+def test_pairwise_coupling(golden):
+    """Wu-Lin coupling restatement against the reference's routine (classifier.py:573-653) incl. its last-write-wins updates."""
+    g = golden('coupling.npz')
+    for tag, K in (('a', 3), ('b', 5), ('c', 2), ('d', 4), ('e', 7)):
+        p_pair = T(g[f'{tag}_pair'])
+        eps = 5e-3 / K
+        p = orc.pairwise_coupling(p_pair, max(100, K), eps, eps)
+        tol = 1e-12 if p_pair.dtype == torch.float64 else 2e-6
+        np.testing.assert_allclose(p.numpy(), g[f'{tag}_p'], rtol=0, atol=tol, err_msg=tag)
+        np.testing.assert_allclose(p.sum(1).numpy(), 1.0, atol=1e-6)
