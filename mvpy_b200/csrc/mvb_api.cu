@@ -1088,11 +1088,14 @@ int mvb_score(const void* y, const void* yhat, const void* y_b, int64_t R, int64
   const bool vec32 = K % 4 == 0 && (((uintptr_t)y | (uintptr_t)yhat | (uintptr_t)y_b) & 15) == 0;
   const bool vec64 = K % 2 == 0 && (((uintptr_t)y | (uintptr_t)yhat | (uintptr_t)y_b) & 15) == 0;
   if (dtype == MVB_F32) {
-    if (vec32) mvb::score_vec_kernel<float><<<cdiv(K, 128), 128, 0, st>>>((const float*)y, (const float*)yhat, (const float*)y_b, R, K, (float*)r2_out, (float*)pearson_out);
+    // small problems: four interleaved row slices per warp so that there are enough warps to fill the SMs
+    if (vec32 && K / 4 < (int64_t)148 * 2048) mvb::score_vec_kernel<float, 4, 4><<<cdiv(K, 256), 256, 0, st>>>((const float*)y, (const float*)yhat, (const float*)y_b, R, K, (float*)r2_out, (float*)pearson_out);
+    else if (vec32) mvb::score_vec_kernel<float, 1, 4><<<cdiv(K, 1024), 256, 0, st>>>((const float*)y, (const float*)yhat, (const float*)y_b, R, K, (float*)r2_out, (float*)pearson_out);
     else if (R <= 32) mvb::score_kernel<float, 32><<<grid, 128, 0, st>>>((const float*)y, (const float*)yhat, (const float*)y_b, R, K, (float*)r2_out, (float*)pearson_out);
     else mvb::score_kernel<float, 0><<<grid, 128, 0, st>>>((const float*)y, (const float*)yhat, (const float*)y_b, R, K, (float*)r2_out, (float*)pearson_out);
   } else if (dtype == MVB_F64) {
-    if (vec64) mvb::score_vec_kernel<double><<<cdiv(K, 64), 128, 0, st>>>((const double*)y, (const double*)yhat, (const double*)y_b, R, K, (double*)r2_out, (double*)pearson_out);
+    if (vec64 && K / 2 < (int64_t)148 * 2048) mvb::score_vec_kernel<double, 4, 4><<<cdiv(K, 128), 256, 0, st>>>((const double*)y, (const double*)yhat, (const double*)y_b, R, K, (double*)r2_out, (double*)pearson_out);
+    else if (vec64) mvb::score_vec_kernel<double, 1, 4><<<cdiv(K, 512), 256, 0, st>>>((const double*)y, (const double*)yhat, (const double*)y_b, R, K, (double*)r2_out, (double*)pearson_out);
     else if (R <= 32) mvb::score_kernel<double, 32><<<grid, 128, 0, st>>>((const double*)y, (const double*)yhat, (const double*)y_b, R, K, (double*)r2_out, (double*)pearson_out);
     else mvb::score_kernel<double, 0><<<grid, 128, 0, st>>>((const double*)y, (const double*)yhat, (const double*)y_b, R, K, (double*)r2_out, (double*)pearson_out);
   }

@@ -637,51 +637,46 @@ __global__ void score_kernel(const T* __restrict__ y, const T* __restrict__ yh, 
 
 
 // ---- fused r2 + pearson, vectorised and warp-shuffle-reduced (math/r2.py:57-101, math/pearsonr.py:35-56) -----------------
-// y, yh: [R][K] with the reduced samples as the slow axis.  A warp owns 32 / 16 consecutive cells (128 contiguous bytes
-// per row): lane = (row slice rs = lane / 8) x (16-byte column group cg = lane % 8), so one load instruction covers four rows
-// with every 32-byte sector fully used; each lane walks rows rs, rs + 4, ... (unrolled by 3: six 16-byte loads in flight
-// per lane), accumulates the moments about a pivot (the first sample of the cell, so that a constant series has exactly zero
-// variance and scores NaN like the reference's 0 / 0) in fp64 -- one pass for any R: the centred sums follow as
-// S_xy - S_x S_y / R -- and the four row slices are combined with two xor-shuffles.  Each input byte is read from HBM once.
+// y, yh: [R][K] with the reduced samples as the slow axis.  A lane owns one 16-byte group of cells and walks the rows; RS
+// lanes-groups of a warp take interleaved rows (RS = 1: a warp reads 512 contiguous bytes per row; RS = 4: 128 bytes of four
+// rows, for small problems that would otherwise leave the SMs empty) and are combined with xor-shuffles at the end.  Rows are
+// unrolled by four: eight independent 16-byte loads in flight per lane, from at most 8 RS different rows -- measured with ncu
+// (profiles/r02_notes.md): what bounds this kernel is memory latency, and that latency explodes once a warp has loads to more
+// than a few dozen different 2 MB pages in flight (the rows of one cell group are K * 4 bytes apart), so the row unroll is
+// kept short and the occupancy high instead.  Moments are taken about a pivot (the first sample of the cell: a constant
+// series then has exactly zero variance and scores NaN like the reference's 0 / 0), summed in T over blocks of 32 rows and
+// folded into a second set of accumulators; the centred sums follow in fp64 as S_xy - S_x S_y / R.  One pass, each input byte
+// read from HBM once.
 template <typename T> struct ScoreVec;
 template <> struct ScoreVec<float> { using V = float4; static constexpr int W = 4; };
 template <> struct ScoreVec<double> { using V = double2; static constexpr int W = 2; };
 __device__ __forceinline__ void vec_get(const float4& v, float (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
 __device__ __forceinline__ void vec_get(const double2& v, double (&o)[2]) { o[0] = v.x; o[1] = v.y; }
 
-template <typename T>
-__global__ void __launch_bounds__(128) score_vec_kernel(const T* __restrict__ y, const T* __restrict__ yh, const T* __restrict__ yb,
+template <typename T, int RS, int U>
+__global__ void __launch_bounds__(256, U == 2 ? 3 : 2) score_vec_kernel(const T* __restrict__ y, const T* __restrict__ yh, const T* __restrict__ yb,
                                                         int64_t R, int64_t K, T* __restrict__ r2, T* __restrict__ pr) {
   using V = typename ScoreVec<T>::V;
   constexpr int W = ScoreVec<T>::W;
-  const int lane = threadIdx.x & 31, cg = lane & 7, rs = lane >> 3;
+  constexpr int CGW = 32 / RS;                                 // column groups per warp
+  const int lane = threadIdx.x & 31, cg = lane % CGW, rs = lane / CGW;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t k0 = (warp * 8 + cg) * W;                      // first cell of this lane (K % W == 0)
+  const int64_t k0 = (warp * CGW + cg) * W;                    // first cell of this lane (K % W == 0)
   const bool ok = k0 < K;
-  double sy[W], sh[W], syy[W], shh[W], syh[W], see[W], sgg[W];
   T base[W], py0[W], ph0[W];
+  T ty[W], th[W], tyy[W], thh[W], tyh[W], tee[W], tgg[W];      // current block of rows
+  T sy[W], sh[W], syy[W], shh[W], syh[W], see[W], sgg[W];      // folded blocks
 #pragma unroll
-  for (int u = 0; u < W; ++u) { sy[u] = sh[u] = syy[u] = shh[u] = syh[u] = see[u] = sgg[u] = 0.0; base[u] = py0[u] = ph0[u] = (T)0; }
+  for (int u = 0; u < W; ++u) {
+    base[u] = py0[u] = ph0[u] = (T)0;
+    ty[u] = th[u] = tyy[u] = thh[u] = tyh[u] = tee[u] = tgg[u] = (T)0;
+    sy[u] = sh[u] = syy[u] = shh[u] = syh[u] = see[u] = sgg[u] = (T)0;
+  }
   if (ok) {
     if (yb) vec_get(__ldg(reinterpret_cast<const V*>(yb + k0)), base);
-    vec_get(__ldg(reinterpret_cast<const V*>(y + k0)), py0);            // pivots: the cell's first sample (shared by the 4 row slices)
+    vec_get(__ldg(reinterpret_cast<const V*>(y + k0)), py0);            // pivots: the cell's first sample
     vec_get(__ldg(reinterpret_cast<const V*>(yh + k0)), ph0);
   }
-  // Moments of up to CH rows per lane are summed in T (pivot-shifted values, a dozen terms: 1e-7 relative) and then folded
-  // into the fp64 accumulators: fp64 conversions / adds per element would otherwise, not HBM, bound the kernel.
-  T ty[W], th[W], tyy[W], thh[W], tyh[W], tee[W], tgg[W];
-  auto clear = [&]() {
-#pragma unroll
-    for (int u = 0; u < W; ++u) ty[u] = th[u] = tyy[u] = thh[u] = tyh[u] = tee[u] = tgg[u] = (T)0;
-  };
-  auto flush = [&]() {
-#pragma unroll
-    for (int u = 0; u < W; ++u) {
-      sy[u] += (double)ty[u]; sh[u] += (double)th[u]; syy[u] += (double)tyy[u]; shh[u] += (double)thh[u];
-      syh[u] += (double)tyh[u]; see[u] += (double)tee[u]; sgg[u] += (double)tgg[u];
-    }
-    clear();
-  };
   auto add = [&](const V& av, const V& bv) {
     T a[W], b[W];
     vec_get(av, a); vec_get(bv, b);
@@ -693,25 +688,32 @@ __global__ void __launch_bounds__(128) score_vec_kernel(const T* __restrict__ y,
       tee[u] = fma(e, e, tee[u]); tgg[u] = fma(g, g, tgg[u]);
     }
   };
-  clear();
+  auto fold = [&]() {
+#pragma unroll
+    for (int u = 0; u < W; ++u) {
+      sy[u] += ty[u]; sh[u] += th[u]; syy[u] += tyy[u]; shh[u] += thh[u]; syh[u] += tyh[u]; see[u] += tee[u]; sgg[u] += tgg[u];
+      ty[u] = th[u] = tyy[u] = thh[u] = tyh[u] = tee[u] = tgg[u] = (T)0;
+    }
+  };
   if (ok) {
     const V* py = reinterpret_cast<const V*>(y + k0);
     const V* ph = reinterpret_cast<const V*>(yh + k0);
     const int64_t stride = K / W;                              // row pitch in vectors
     int64_t r = rs;
-    int pending = 0;
-    for (; r + 8 < R; r += 12) {
-      const V a0 = __ldg(py + r * stride), b0 = __ldg(ph + r * stride);
-      const V a1 = __ldg(py + (r + 4) * stride), b1 = __ldg(ph + (r + 4) * stride);
-      const V a2 = __ldg(py + (r + 8) * stride), b2 = __ldg(ph + (r + 8) * stride);
-      add(a0, b0); add(a1, b1); add(a2, b2);
-      if (++pending == 4) { flush(); pending = 0; }            // 12 rows per lane between folds
+    int blk = 0;
+    for (; r + (U - 1) * RS < R; r += U * RS) {
+      V a[U], b[U];
+#pragma unroll
+      for (int i = 0; i < U; ++i) { a[i] = __ldg(py + (r + i * RS) * stride); b[i] = __ldg(ph + (r + i * RS) * stride); }
+#pragma unroll
+      for (int i = 0; i < U; ++i) add(a[i], b[i]);
+      if (++blk == 32 / U) { fold(); blk = 0; }
     }
-    for (; r < R; r += 4) add(__ldg(py + r * stride), __ldg(ph + r * stride));
-    flush();
+    for (; r < R; r += RS) add(__ldg(py + r * stride), __ldg(ph + r * stride));
+    fold();
   }
 #pragma unroll
-  for (int o = 8; o <= 16; o <<= 1)
+  for (int o = CGW; o < 32; o <<= 1)
 #pragma unroll
     for (int u = 0; u < W; ++u) {
       sy[u] += __shfl_xor_sync(0xffffffffu, sy[u], o); sh[u] += __shfl_xor_sync(0xffffffffu, sh[u], o);
@@ -723,15 +725,15 @@ __global__ void __launch_bounds__(128) score_vec_kernel(const T* __restrict__ y,
     const double inv = 1.0 / (double)R;
 #pragma unroll
     for (int u = 0; u < W; ++u) {
-      const double cxx = syy[u] - sy[u] * sy[u] * inv, chh = shh[u] - sh[u] * sh[u] * inv, cxy = syh[u] - sy[u] * sh[u] * inv;
-      const double den = yb ? sgg[u] : cxx;                    // without a baseline: the mean of y (r2.py:80-81)
+      const double dsy = sy[u], dsh = sh[u];
+      const double cxx = (double)syy[u] - dsy * dsy * inv, chh = (double)shh[u] - dsh * dsh * inv, cxy = (double)syh[u] - dsy * dsh * inv;
+      const double den = yb ? (double)sgg[u] : cxx;            // without a baseline: the mean of y (r2.py:80-81)
       if (r2) r2[k0 + u] = ((T)den > (T)0) ? (T)1 - (T)see[u] / (T)den : (T)0;
       // a constant series has all pivot moments exactly zero: 0 / 0 = NaN as in the reference (pearsonr.py:55-56, no guard)
       if (pr) pr[k0 + u] = (T)cxy / (T)sqrt((double)((T)fmax(cxx, 0.0) * (T)fmax(chh, 0.0)));
     }
   }
 }
-
 
 // ---- Wu-Lin pairwise coupling of one-versus-one probabilities (estimators/classifier.py:527-653) ----------------------
 // One thread per sample, K <= COUPLING_MAX_K classes, double arithmetic.  The reference builds Q and r with in-place adds

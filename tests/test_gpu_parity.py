@@ -694,8 +694,7 @@ def test_ridge_classifier_golden(golden):
     assert len(ovo.estimators_) == 4 and ovo.coef_.shape == (4, 2, 10) and np.array_equal(ovo.predict(X).cpu().numpy(), g['ovo_pred'])
     np.testing.assert_allclose(ovo.coef_.cpu().numpy(), g['ovo_coef'], rtol=1e-3, atol=1e-5)
     assert ovo.decision_function(X).shape == (4, 150, 2)
-    with pytest.raises(NotImplementedError):
-        ovo.predict_proba(X)
+    assert ovo.predict_proba(X).shape == (150, 5)                 # values: test_pairwise_coupling_and_ovo_predict_proba
     _, sc = mv.crossvalidation.cross_val_score(mv.estimators.RidgeClassifier(alphas=al), X, y, cv=mv.crossvalidation.StratifiedKFold(n_splits=3))
     assert sc.shape == (3, 2) and float(sc.min()) > 0.6
     # decoding over time: one classifier per time slice

@@ -39,7 +39,13 @@ beta_mixed = torch.linalg.solve(G.double() + a * eye, XtY.double())
 print('coef: fp64 solve on OUR fp32 G / XtY vs oracle', ((beta_mixed.T - fit['coef']).norm() / fit['coef'].norm()).item(),
       '; ours vs that', ((ours - beta_mixed.T).norm() / beta_mixed.norm()).item())
 if len(sys.argv) > 3:
+    _lib.band_reduce(G.clone())
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
     Qt, Td, Ts, cnt = _lib.band_reduce(G.clone(), counters=True)
+    e1.record(); torch.cuda.synchronize()
+    print('band reduce ms', e0.elapsed_time(e1))
     P = Qt.shape[0]
     Q64 = Qt.double()
     print('orth', (Q64 @ Q64.T - torch.eye(P, dtype=torch.float64, device='cuda')).abs().max().item(), 'fallbacks', cnt)
