@@ -447,15 +447,24 @@ def main():
     # compared on rank 0 with the same call computed without sharding
     sharded = None
     if args.workload == 'cfg2' and not args.no_sharded_api:
+        peak_alg = float(peaks['bf16_tflops_sustained']) / 6.0 if peaks.get('bf16_tflops_sustained') else tf32_peak / 3.0
+
         def timed(fn):
+            """seconds (max over ranks), result, and this rank's tensor-core roofline over the call (library CUDA-event hook)"""
             barrier()
+            _lib.profile_reset()
             t0 = time.perf_counter()
             out = fn()
             barrier()
             t = torch.tensor([time.perf_counter() - t0], device=dev)
+            pr = _lib.profile_read()
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item()), out
+            ms_k, fl = sum(v['ms'] for v in pr.values()), sum(v['flops'] for v in pr.values())
+            tf = fl / (ms_k * 1e-3) * 1e-12 if ms_k > 0 else 0.0
+            roof = dict(bound='tensor', achieved=tf, peak=peak_alg, unit='TFLOP/s', frac=tf / peak_alg,
+                        share_of_call=ms_k * 1e-3 / float(t.item()), note='rank 0, all contraction launches of the call')
+            return float(t.item()), out, roof
 
         def run_h():
             return mv.model_selection.hierarchical_score(pipe, X.to(dev), y.to(dev), groups=groups3.to(dev), cv=N_FOLDS)[1]
@@ -465,12 +474,13 @@ def main():
             return mv.model_selection.shapley_score(pipe, X, y, groups=groups, cv=N_FOLDS, n_permutations=2 * world,
                                                     return_shapley=True)[1]
         run_h()                                                       # warm-up (allocator, lazy module loads)
-        t_h, sc_hier = timed(run_h)
-        t_s, sc_shap = timed(run_s)
+        t_h, sc_hier, roof_h = timed(run_h)
+        t_s, sc_shap, roof_s = timed(run_s)
         sharded = dict(hierarchical_score=dict(units=8 * N_FOLDS, fits=8 * N_FOLDS * N_ALPHAS, seconds=t_h, fits_per_s=8 * N_FOLDS * N_ALPHAS / t_h,
-                                               scaling='strong', unit_of_sharding='(set, fold), longest first'),
+                                               scaling='strong', unit_of_sharding='(set, fold), longest first', roofline=roof_h),
                        shapley_score=dict(permutations=2 * world, units=2 * world, fits=2 * world * 8 * N_FOLDS * N_ALPHAS, seconds=t_s,
-                                          fits_per_s=2 * world * 8 * N_FOLDS * N_ALPHAS / t_s, scaling='weak', unit_of_sharding='permutation'),
+                                          fits_per_s=2 * world * 8 * N_FOLDS * N_ALPHAS / t_s, scaling='weak', unit_of_sharding='permutation',
+                                          roofline=roof_s),
                        n_gpus=world)
         if world > 1 and rank == 0 and args.check_sharded:
             # the unsharded answer on rank 0 alone (other ranks wait at the barrier below): identical tensors expected
