@@ -111,6 +111,13 @@ size_t mvb_trf_stats_workspace_bytes(const mvb_design* d, int n_targets);
 int mvb_trf_stats(const mvb_design* d, const void* y, int n_targets, int fit_intercept,
                   void* G, void* XtY, void* mu, void* ybar, void* ws, size_t ws_bytes, void* stream);
 
+/* mvb_gather_stats: statistics of a predictor subset (features feat_idx, all n_lag lags each) as the principal sub-block
+ * of the full-predictor statistics of the same fold -- what lets hierarchical_score / shapley_score (hierarchical.py:150-207,
+ * shapley.py:64-182: one full refit per predictor set) build X^T X once per fold.  G [p_full][p_full], XtY [p_full][F],
+ * mu [p_full] -> G_sub [ps][ps], XtY_sub [ps][F], mu_sub [ps], ps = n_feat * n_lag.                                    */
+int mvb_gather_stats(const void* G, const void* XtY, const void* mu, int64_t p_full, int n_targets, const int32_t* feat_idx, int n_feat,
+                     int n_lag, int dtype, void* G_sub, void* XtY_sub, void* mu_sub, void* stream);
+
 /* ---- batched symmetric eigensolver ---------------------------------------------------------------
  * replaces torch.linalg.svd / eigh in ridgecv.py:144,218.  A: batch x p x p symmetric (destroyed),
  * Vt: batch x p x p, row k = k-th eigenvector; lam: batch x p (unsorted, >= 0 enforced).        */

@@ -58,6 +58,8 @@ _SIGNATURES = {
     'mvb_trf_stats_workspace_bytes': (c_size_t, [POINTER(mvb_design), c_int]),
     'mvb_trf_stats': (c_int, [POINTER(mvb_design), c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_size_t, c_void_p]),
+    'mvb_gather_stats': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_void_p]),
     'mvb_eigh_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'mvb_eigh': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     'mvb_ridge_solve_workspace_bytes': (c_size_t, [POINTER(mvb_design), c_int, c_int]),
@@ -294,6 +296,18 @@ def trf_stats(design: Design, y: torch.Tensor, fit_intercept: bool = True):
     check(lib.mvb_trf_stats(ctypes.byref(cs), _ptr(y), F, int(fit_intercept), _ptr(G), _ptr(XtY), _ptr(mu), _ptr(ybar),
                             _ptr(ws), ws.numel(), _stream(y)), 'mvb_trf_stats')
     return G, XtY, mu, ybar
+
+
+def gather_stats(G: torch.Tensor, XtY: torch.Tensor, mu: torch.Tensor, feat_idx: torch.Tensor, n_lag: int):
+    """(G, XtY, mu) of the predictor subset ``feat_idx`` sliced out of the full-predictor statistics (one kernel)."""
+    fi = feat_idx.to(device=G.device, dtype=torch.int32).contiguous()
+    ps, F = int(fi.numel()) * n_lag, XtY.shape[1]
+    Gs = torch.empty((ps, ps), dtype=G.dtype, device=G.device)
+    Bs = torch.empty((ps, F), dtype=G.dtype, device=G.device)
+    ms = torch.empty(ps, dtype=G.dtype, device=G.device)
+    check(load().mvb_gather_stats(_ptr(G), _ptr(XtY), _ptr(mu), G.shape[0], F, _ptr(fi), int(fi.numel()), n_lag, dtype_code(G), _ptr(Gs),
+                                  _ptr(Bs), _ptr(ms), _stream(G)), 'mvb_gather_stats')
+    return Gs, Bs, ms
 
 
 def ridge_solve(design: Design, y: torch.Tensor, G, XtY, mu, ybar, alphas: torch.Tensor, fit_intercept: bool,

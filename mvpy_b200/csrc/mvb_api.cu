@@ -988,6 +988,20 @@ int mvb_trf_stats(const mvb_design* d, const void* y, int n_targets, int fit_int
   return trf_stats_impl<double>(d, (const double*)y, n_targets, fit_intercept, (double*)G, (double*)XtY, (double*)mu, (double*)ybar, ws, ws_bytes, st);
 }
 
+int mvb_gather_stats(const void* G, const void* XtY, const void* mu, int64_t p_full, int n_targets, const int32_t* feat_idx, int n_feat,
+                     int n_lag, int dtype, void* G_sub, void* XtY_sub, void* mu_sub, void* stream) {
+  if (!G || !XtY || !mu || !feat_idx || !G_sub || !XtY_sub || !mu_sub || p_full < 1 || n_targets < 1 || n_feat < 1 || n_lag < 1)
+    return fail(MVB_E_ARG, "gather_stats: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t ps = (int64_t)n_feat * n_lag;
+  const int grid = grid_for(ps * ps + ps * n_targets + ps);
+  if (dtype == MVB_F32) mvb::gather_stats_kernel<float><<<grid, 256, 0, st>>>((const float*)G, (const float*)XtY, (const float*)mu, p_full, n_targets, feat_idx, n_feat, n_lag, (float*)G_sub, (float*)XtY_sub, (float*)mu_sub);
+  else if (dtype == MVB_F64) mvb::gather_stats_kernel<double><<<grid, 256, 0, st>>>((const double*)G, (const double*)XtY, (const double*)mu, p_full, n_targets, feat_idx, n_feat, n_lag, (double*)G_sub, (double*)XtY_sub, (double*)mu_sub);
+  else return fail(MVB_E_UNSUPPORTED, "gather_stats: dtype %d", dtype);
+  MVB_LAUNCHED();
+  return MVB_OK;
+}
+
 size_t mvb_eigh_workspace_bytes(int batch, int p, int dtype) { return eigh_ws_bytes(batch, p, dtype); }
 
 int mvb_eigh(void* A, void* Vt, void* lam, int batch, int p, int dtype, void* ws, size_t ws_bytes, void* stream) {

@@ -819,4 +819,31 @@ __global__ void coupling_finish_kernel(const double* __restrict__ buf0, const do
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) out[e] = (T)src[e];
 }
 
+
+// ---- statistics of a predictor subset as a slice of the full-predictor statistics --------------------------------------
+// Columns of the lag-expanded design are (feature, lag): the subset `feat_idx` of the features selects
+// cols[c * W + w] = feat_idx[c] * W + w.  G_sub = G[cols][:, cols], XtY_sub = XtY[cols], mu_sub = mu[cols]
+// (hierarchical.py / shapley.py refit every predictor set from scratch; SURVEY 8 a-note: the subset's Gram is a principal
+// sub-block of the fold's full Gram).  One pass: each output element is read once and written once.
+template <typename T>
+__global__ void gather_stats_kernel(const T* __restrict__ G, const T* __restrict__ XtY, const T* __restrict__ mu, int64_t p_full, int F,
+                                    const int32_t* __restrict__ feat_idx, int n_feat, int W, T* __restrict__ Gs, T* __restrict__ XtYs,
+                                    T* __restrict__ mus) {
+  const int64_t ps = (int64_t)n_feat * W;
+  const int64_t total = ps * ps + ps * F + ps;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    if (e < ps * ps) {
+      const int64_t r = e / ps, c = e - r * ps;
+      const int64_t rf = (int64_t)feat_idx[r / W] * W + r % W, cf = (int64_t)feat_idx[c / W] * W + c % W;
+      Gs[e] = G[rf * p_full + cf];
+    } else if (e < ps * ps + ps * F) {
+      const int64_t q = e - ps * ps, r = q / F, f = q - r * F;
+      XtYs[q] = XtY[((int64_t)feat_idx[r / W] * W + r % W) * F + f];
+    } else {
+      const int64_t r = e - ps * ps - ps * F;
+      mus[r] = mu[(int64_t)feat_idx[r / W] * W + r % W];
+    }
+  }
+}
+
 }  // namespace mvb

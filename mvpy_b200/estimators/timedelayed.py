@@ -136,9 +136,8 @@ class _TimeDelayed_torch(sklearn.base.BaseEstimator):
                 par['shared'].pop(next(iter(par['shared'])))          # reshuffle per clone would otherwise grow this without reuse
             par['shared'][key] = entry
         full, (G, XtY, mu, ybar), shift = entry
-        cols = (idx.to(G.device)[:, None] * W + torch.arange(W, device=G.device)[None, :]).reshape(-1)
-        stats = (G[cols][:, cols].contiguous(), XtY[cols].contiguous(), mu[cols].contiguous(), ybar)
-        return full.subset(feat_idx=idx), stats, shift
+        Gs, Bs, ms = _lib.gather_stats(G, XtY, mu, idx, W)
+        return full.subset(feat_idx=idx), (Gs, Bs, ms, ybar), shift
 
     def fit(self, X: torch.Tensor, y: torch.Tensor):
         if (len(X.shape) != 3) | (len(y.shape) != 3):
