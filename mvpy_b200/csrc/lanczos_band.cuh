@@ -24,7 +24,6 @@
 #include <stdlib.h>
 #include <algorithm>
 #include "tc_gemm.cuh"
-#include "tc_gemm_skinny.cuh"   // experimental turned-around skinny product, MVB_LB_SKINNY=1 only
 #include "jacobi_block.cuh"   // small_eig_kernel (128 x 128 symmetric eigensolver in shared memory)
 
 namespace mvb {
@@ -392,33 +391,6 @@ inline bool gemm(Ctx& cx, const GatherOperand& A, const GatherOperand& B, int M,
   const int bn = N > 128 ? 256 : 128;
   int max_splits = (int)std::min<size_t>(64, cx.pl.part_elems / ((size_t)M * N));
   if (max_splits < 1) max_splits = 1;
-  // EXPERIMENT (off unless MVB_LB_SKINNY=1; not measured yet, see tc_gemm_skinny.cuh): the large products of a 128-row block
-  // against a dense row-major matrix run turned around -- the matrix's rows are the MMA's A operand, streamed raw from HBM;
-  // the block is pre-split into 13 MB of planes in the scratch that otherwise holds the Gp planes.
-  static const bool skinny_on = [] { const char* e = getenv("MVB_LB_SKINNY"); return e && atoi(e) != 0; }();
-  if (skinny_on && cx.pl.planes_bytes && M == NB && N % 128 == 0 && K % tc::BK == 0 && (int64_t)N * K >= ((int64_t)1 << 24) &&
-      A.lanes_along_k == 2 && B.lanes_along_k == 2 && A.roff == cx.i64(cx.pl.off_rowP) && B.roff == cx.i64(cx.pl.off_rowP) &&
-      A.koff == cx.i64(cx.pl.off_iota) && B.koff == cx.i64(cx.pl.off_iota)) {
-    const int P = cx.pl.P;
-    uint8_t* scratch = (uint8_t*)(cx.base + cx.pl.off_plG);
-    const int splits = tc_choose_splits(N / 128, K / tc::BK, max_splits, (int64_t)M * N);
-    const bool via_parts = splits > 1 || subtract;
-    float* out = via_parts ? cx.f(cx.pl.off_part) : C;
-    const bool timed = cx.hooks && !skip;
-    const int slot = timed ? cx.hooks->begin(2, 2.0 * M * (double)N * K, cx.st) : -1;
-    cx.err = skinny::presplit128_launch(A.base, P, K, scratch, cx.st, skip);
-    if (cx.err == cudaSuccess)
-      cx.err = skinny::skinny_launch(B.base, P, scratch, out, via_parts ? N : ldc, (int64_t)M * N, N, K, splits, cx.st, skip);
-    if (timed) cx.hooks->end(slot, cx.st);
-    cx.launches += 2;
-    if (cx.err != cudaSuccess) return false;
-    if (via_parts) {
-      const int rgrid = (int)std::min<int64_t>(148 * 4, ((int64_t)M * N + 255) / 256);
-      reduce_parts_kernel<<<rgrid, 256, 0, cx.st>>>(cx.f(cx.pl.off_part), splits, (int64_t)M * N, M, N, C, ldc, skip, subtract ? 1 : 0);
-      ++cx.launches;
-    }
-    return true;
-  }
   const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
   const int splits = tc_choose_splits(tiles, (K + tc::BK - 1) / tc::BK, max_splits, (int64_t)M * N);
   TcGemmParams g = tc_gemm_defaults();
@@ -529,9 +501,7 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
   if (pl.planes_bytes) {
     plG = (uint8_t*)(cx.base + pl.off_plG); plQt = (uint8_t*)(cx.base + pl.off_plQt); plQc = (uint8_t*)(cx.base + pl.off_plQc);
     GatherOperand g_all{Gp, rowP, iota, P, 2};
-    static const bool skinny_env = [] { const char* e = getenv("MVB_LB_SKINNY"); return e && atoi(e) != 0; }();
-    if (skinny_env) plG = nullptr;        // the region is the skinny path's scratch then (gemm())
-    else { LB_CK(tc_presplit_launch(g_all, P, plG, st)); ++cx.launches; }
+    LB_CK(tc_presplit_launch(g_all, P, plG, st)); ++cx.launches;
     LB_CK(cudaMemsetAsync(plQt, 0, pl.planes_bytes, st));       // blocks arrive one per step; rows / stages not yet there read as zero
     LB_CK(cudaMemsetAsync(plQc, 0, pl.planes_bytes, st));
   }

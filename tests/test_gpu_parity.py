@@ -877,7 +877,13 @@ def test_pairwise_coupling_and_ovo_predict_proba(golden):
         if p.dtype == torch.float64:
             assert err.max() < 1e-9, tag
         else:
-            assert err.max() < 5e-3 / K and np.median(err) < 1e-6 and (err > 1e-5).mean() < 0.05, (tag, err.max())
+            # fp32 inputs: the kernel iterates in double; the reference solves its (K+1) x (K+1) KKT systems in fp32, where the
+            # 1e-9 ridge on Q (entries up to 1 / eps^2) is below rounding and single samples land anywhere (observed: 0.57 off
+            # for K = 7 on uniform random pairwise probabilities).  Pin the kernel on the double restatement of the same
+            # iteration, and require agreement with the reference's fp32 output for the bulk of the samples.
+            ref64 = _orc().pairwise_coupling(p_pair.cpu().double(), max(100, K), eps, eps).numpy()
+            assert np.abs(p.cpu().numpy() - ref64).max() < 1e-5, tag
+            assert np.median(err) < 1e-5 and (err.max(axis=1) < 1e-3).mean() > 0.8, (tag, np.median(err), (err.max(axis=1) < 1e-3).mean())
     c = golden('clf.npz')
     X, y, al = T(c['X']).cuda(), T(c['y']).cuda(), T(c['alphas'])
     clf = mv.estimators.RidgeClassifier(alphas=al, method='OvO').fit(X, y)

@@ -24,7 +24,7 @@
 // is unchanged (the transposed store writes the same [split][128][N] layout).  Once measured faster, the Gp / Qt / Q^T plane
 // copies (3 x 1.34 GB and their incremental presplit launches) can go.
 #pragma once
-#include "tc_gemm.cuh"
+#include "../../mvpy_b200/csrc/tc_gemm.cuh"
 
 namespace mvb {
 namespace skinny {

@@ -4,7 +4,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <vector>
-#include "../../mvpy_b200/csrc/tc_gemm_skinny.cuh"
+#include "tc_gemm_skinny.cuh"
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
 static float frand() { return (float)rand() / RAND_MAX * 2.f - 1.f; }
 
