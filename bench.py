@@ -532,10 +532,11 @@ def main():
                     roof['by_kernel'][k]['algorithmic_bytes'] = v['algorithmic_bytes_per_launch']
                     if 'operand_bytes_per_launch' in v:
                         roof['by_kernel'][k]['operand_bytes'] = v['operand_bytes_per_launch']
-            zk = 'Z = X Q^T (leverages)'        # the largest single launch of the step: its ncu dram bytes stand for the kernel
-            if zk in tr and zk in roof['by_kernel']:
-                roof['traffic'] = tr[zk]['dram_bytes_per_launch']
-                roof['traffic_of'] = f'{zk}: one launch, algorithmic bytes {tr[zk]["algorithmic_bytes_per_launch"]}'
+            # roofline.traffic: the dram bytes of the dominant-by-time class, the block-Lanczos reduction (its W = Q_j G launch)
+            lk = 'band reduction (block Lanczos) / eig refresh'
+            if lk in tr and lk in roof['by_kernel']:
+                roof['traffic'] = tr[lk]['dram_bytes_per_launch']
+                roof['traffic_of'] = f'{lk}: one W = Q_j G launch, algorithmic bytes {tr[lk]["algorithmic_bytes_per_launch"]} (ncu, profiles/r02_ncu_full.md)'
         except Exception:
             pass
     # ---- HBM-bound leg of the path: the fused r2 + pearson scoring kernel on one test fold (CUDA events, 50 launches) ----
