@@ -6,7 +6,8 @@
 // That one form covers every contraction on the ridge hot path:
 //   * the implicit lag-expanded design  Xt[(trial,t),(c,w)] = Xpad[trial,c,t+w]
 //     (rows: roff = trial*C*Tp + t, cols: koff = c*Tp + w)  -- the lag expansion
-//     (reference: mvpy/estimators/timedelayed.py:394-431) is never materialised,
+//     (reference: mvpy/estimators/timedelayed.py:394-431) is never materialised (X^T X itself has its own kernel,
+//     toeplitz_gram.cuh, which needs no gather tables at all),
 //   * dense row-major matrices (eigenvector / coefficient operands),
 //   * feature masks and training-trial subsets (just shorter offset tables).
 //

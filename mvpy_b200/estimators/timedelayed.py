@@ -2,8 +2,9 @@
 (mvpy/estimators/timedelayed.py:318-817).
 
 The reference gathers every lag into a (trials*time, channels*lags) matrix and hands it to RidgeCV.
-Here the stimulus is only edge-padded (``mvb_trf_pad``); all contractions (X^T X, X^T y, X V, X beta,
-prediction) read the padded series through offset tables, so the lag expansion never exists in HBM."""
+Here the stimulus is only edge-padded (``mvb_trf_pad``): X^T X is built from windows of the padded series (TMA +
+overlapping UMMA descriptors, ``toeplitz_gram.cuh``), X^T y, X Q^T, X beta and the prediction read it through offset
+tables, so the lag expansion never exists in HBM -- neither as a matrix nor as pre-split operand planes."""
 from __future__ import annotations
 
 import os
