@@ -11,6 +11,7 @@
 #include "mvb_kernels.cuh"
 #include "tc_gemm.cuh"
 #include "toeplitz_gram.cuh"
+#include "gram_recurrence.cuh"
 #include "jacobi_block.cuh"
 #include "lanczos_band.cuh"
 #include "band_loo.cuh"
@@ -218,8 +219,18 @@ struct StatsWs {
   void* contract_ws; size_t contract_bytes;
   void* planes; size_t planes_bytes;      // pre-split TF32 planes of y (the dense B operand of X^T y), large fp32 problems only
   float* pack; size_t pack_bytes;         // TF32 planes of the four shifted copies of the training series (toeplitz_gram.cuh)
+  float* B0; int64_t* lag0_off;           // first block rows G[(c,0),:] and the offsets of the lag-0 columns (gram_recurrence.cuh)
   int parts;
 };
+
+// Default route of the Gram of a lag-expanded fp32 design: its displacement structure (gram_recurrence.cuh), 1 % of the dense
+// contraction's flops.  MVB_GRAM_RECURRENCE=0 takes the dense routes below (the implicit-Toeplitz tensor-core kernel when its shape
+// allows, else the generic gather kernel).
+bool use_gram_recurrence(const mvb_design* d) {
+  const char* e = getenv("MVB_GRAM_RECURRENCE");
+  if (e && atoi(e) == 0) return false;
+  return d->dtype == MVB_F32 && !force_simt() && mvb::gr::usable(d->n_lag);
+}
 
 // The Gram of a lag-expanded design runs on the implicit-Toeplitz kernel (toeplitz_gram.cuh) whenever its shape allows:
 // fp32, tensor cores, whole 8-sample MMA steps per trial, enough tiles to fill the SMs.  MVB_TOEPLITZ_GRAM=0 keeps the
@@ -227,7 +238,7 @@ struct StatsWs {
 bool use_toeplitz_gram(const mvb_design* d) {
   const char* e = getenv("MVB_TOEPLITZ_GRAM");
   const int mode = e ? atoi(e) : 1;
-  if (mode == 0 || d->dtype != MVB_F32 || force_simt()) return false;
+  if (mode == 0 || d->dtype != MVB_F32 || force_simt() || use_gram_recurrence(d)) return false;
   return mvb::tg::usable(d->n_time, d->n_lag, d->n_feat, mode == 2);
 }
 
@@ -243,7 +254,11 @@ size_t carve_stats(Arena& ar, const mvb_design* d, int F, StatsWs& w) {
   w.mu64 = ar.take<double>(p);
   w.ybar64 = ar.take<double>(F);
   constexpr int dt = sizeof(T) == 4 ? MVB_F32 : MVB_F64;
-  size_t cb = std::max(plan_contract((int)p, (int)p, (int)n, dt, 1).ws_elems, plan_contract((int)p, F, (int)n, dt, 0).ws_elems) * sizeof(T);
+  const bool rec = sizeof(T) == 4 && use_gram_recurrence(d);
+  w.B0 = rec ? ar.take<float>((size_t)d->n_feat * p) : nullptr;
+  w.lag0_off = rec ? ar.take<int64_t>(d->n_feat) : nullptr;
+  size_t cb = std::max(rec ? plan_contract(d->n_feat, (int)p, (int)n, dt, 0).ws_elems : plan_contract((int)p, (int)p, (int)n, dt, 1).ws_elems,
+                       plan_contract((int)p, F, (int)n, dt, 0).ws_elems) * sizeof(T);
   w.contract_bytes = cb;
   w.contract_ws = ar.take<char>(cb);
   w.planes_bytes = (sizeof(T) == 4 && p >= 1024 && !force_simt()) ? mvb::tc_planes_bytes(F, (int)n) : 0;
@@ -287,7 +302,18 @@ int trf_stats_impl(const mvb_design* d, const T* y, int F, int fit_intercept, T*
   mvb_operand yc{y, w.ycol_off, w.yrow_off, F, y_vec ? 2 : 1};
   int rc;
   if constexpr (sizeof(T) == 4) {
-    if (w.pack_bytes) {
+    if (w.B0) {
+      // X^T X from its displacement structure: the first row of every (c, c') block by one skinny tensor-core contraction over
+      // the implicit design (the C lag-0 columns against all p columns), the rest of each block by the diagonal recurrence
+      mvb::stride_pick_kernel<<<grid_for(d->n_feat), 256, 0, st>>>(w.col_off, d->n_lag, d->n_feat, w.lag0_off);
+      MVB_LAUNCHED();
+      mvb_operand x0{d->xp, w.lag0_off, w.row_off, d->n_feat, 1};          // rows = lag-0 columns, k = (trial, t) contiguous in t
+      { ProfScope ps(PC_GRAM); rc = run_contract<float>(x0, xc, d->n_feat, (int)p, (int)n, w.B0, p, 0, w.contract_ws, w.contract_bytes, st); }
+      if (rc) return rc;
+      MVB_CUDA(mvb::gr::launch((const float*)d->xp, d->trial_idx, d->n_trials, d->trial_stride, d->feat_idx, d->n_feat, d->feat_stride, d->n_lag,
+                               Tn, w.B0, (float*)G, p, st));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else if (w.pack_bytes) {
       // X^T X straight from the padded stimulus: the training series are split into TF32 planes once (8 shifted / split
       // copies, 130 MB at configs[1]) and the kernel's operands are windows of them -- nothing of the size of the lag
       // expansion (timedelayed.py:415-423: 1.98 GB) exists at any point

@@ -846,4 +846,10 @@ __global__ void gather_stats_kernel(const T* __restrict__ G, const T* __restrict
   }
 }
 
+
+// out[i] = tab[i * stride]
+__global__ void stride_pick_kernel(const int64_t* __restrict__ tab, int stride, int n, int64_t* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = tab[(int64_t)i * stride];
+}
+
 }  // namespace mvb

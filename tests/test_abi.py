@@ -61,10 +61,11 @@ def test_product_does_not_import_oracle():
                 assert not re.search(r'^\s*(from|import)\s+[\w.]*oracle', src, flags=re.M), f'{f} imports the oracle'
 
 
-def test_stats_workspace_never_holds_the_lag_expansion():
+def test_stats_workspace_never_holds_the_lag_expansion(monkeypatch):
     """mvb_trf_stats_workspace_bytes is host-only arithmetic.  The Gram of a lag-expanded design is built from the padded
-    stimulus itself (toeplitz_gram.cuh): the only design-sized scratch is the "pack" -- 2 TF32 planes x 4 shifted copies of
-    the training series, 32 bytes per padded sample -- never anything of the size of the lag expansion
+    stimulus itself: by the displacement-structure recurrence (gram_recurrence.cuh; scratch = the C first block rows) or, with
+    MVB_GRAM_RECURRENCE=0, by the implicit-Toeplitz kernel (toeplitz_gram.cuh; scratch = the "pack": 2 TF32 planes x 4 shifted
+    copies of the training series, 32 bytes per padded sample) -- never anything of the size of the lag expansion
     (n x p x 4 bytes = 1.98 GB at BASELINE configs[1]; timedelayed.py:415-423 materialises exactly that)."""
     from mvpy_b200 import _lib
     lib = _lib.load()
@@ -75,8 +76,12 @@ def test_stats_workspace_never_holds_the_lag_expansion():
         return lib.mvb_trf_stats_workspace_bytes(ctypes.byref(d), F)
 
     # BASELINE configs[1] (96 training trials x 64 features x 400 samples, 201 lags, 306 channels)
-    cfg2 = ws(96, 64, 400, 201, 0, F=306)
     expansion = 96 * 400 * 64 * 201 * 4
+    monkeypatch.setenv('MVB_GRAM_RECURRENCE', '1')
+    rec = ws(96, 64, 400, 201, 0, F=306)
+    assert 64 * 12864 * 4 <= rec < (256 << 20) and rec < expansion // 4, (rec, expansion)
+    monkeypatch.setenv('MVB_GRAM_RECURRENCE', '0')
+    cfg2 = ws(96, 64, 400, 201, 0, F=306)
     pitch = -(-(400 + 200 + 64) // 4) * 4
     pack = 96 * 64 * pitch * 8 * 4
     assert pack <= cfg2 < (1 << 30) and cfg2 < expansion // 2, (cfg2, pack, expansion)

@@ -745,13 +745,16 @@ def test_predictor_sets_share_fold_statistics(monkeypatch):
 @pytest.mark.parametrize('shape', [(6, 20, 400, -1.0, 200, None, None),          # 201 lags: 7 blocks per feature, 9 rows in the last
                                    (5, 40, 152, -0.315, 200, [4, 0, 2], None),      # 64 lags, two unequal K chunks, a training subset
                                    (4, 24, 256, -0.5, 200, None, [0, 3, 4, 7, 8, 11, 12, 15, 16, 19, 20, 21, 22, 23, 1, 2, 5, 6, 9, 10])])
-def test_stats_toeplitz_gram_vs_fp64(shape, monkeypatch):
-    """Designs large enough that mvb_trf_stats builds X^T X on the implicit-Toeplitz kernel (toeplitz_gram.cuh: windows of
-    the padded stimulus by TMA, overlapping UMMA descriptors, lower tiles + mirror): against the same entry point in fp64
-    (CUDA-core contraction over offset tables) and against a materialised lag expansion (reference: timedelayed.py:394-431 +
-    ridgecv.py:59-94); with trial and feature subsets."""
+@pytest.mark.parametrize('route', ['recurrence', 'toeplitz'])
+def test_stats_toeplitz_gram_vs_fp64(shape, route, monkeypatch):
+    """The two structured routes of X^T X for a lag-expanded fp32 design -- the displacement-structure recurrence
+    (gram_recurrence.cuh: first block rows by one skinny contraction, the rest along the diagonals; the default) and the
+    implicit-Toeplitz tensor-core kernel (toeplitz_gram.cuh: windows of the padded stimulus by TMA, overlapping UMMA descriptors,
+    lower tiles + mirror) -- against the same entry point in fp64 (CUDA-core contraction over offset tables) and against a
+    materialised lag expansion (reference: timedelayed.py:394-431 + ridgecv.py:59-94); with trial and feature subsets."""
     mv = _mv()
     from mvpy_b200 import _lib
+    monkeypatch.setenv('MVB_GRAM_RECURRENCE', '1' if route == 'recurrence' else '0')
     monkeypatch.setenv('MVB_TOEPLITZ_GRAM', '2')           # also for designs too small to fill the SMs without split-K
     N, C, Tn, t_min, fs, trials, feats = shape
     g = torch.Generator().manual_seed(5)
