@@ -49,8 +49,8 @@ int fail(int code, const char* fmt, ...) {
 // ---- measurement hook (include/mvb.h) ------------------------------------------------------------------
 enum ProfClass { PC_GRAM = 0, PC_XTY, PC_SMALL, PC_LEVERAGE_Z, PC_RESIDUAL, PC_PREDICT, PC_EIG_GRAM, PC_EIG_APPLY,
                  PC_EIG_REFRESH, PC_OTHER, PC_COUNT };
-const char* kProfNames[PC_COUNT] = {"gram X^T X (implicit Toeplitz)", "X^T y", "Q b and beta = Q^T x (dense)", "Z = X Q^T (leverages)",
-                                    "R = X beta (LOO residuals)", "predict X coef", "eig: pair Gram", "eig: rotate rows",
+const char* kProfNames[PC_COUNT] = {"gram X^T X (tensor-core part: first block rows, or the dense Toeplitz kernel)", "X^T y", "Q b and coef = Q^T x (dense)", "Z = X Q^T (leverages)",
+                                    "R = Z S^T (LOO fitted values, reduced basis)", "predict X coef", "eig: pair Gram", "eig: rotate rows",
                                     "band reduction (block Lanczos) / eig refresh", "block substitution sweep (forward / backward)"};
 constexpr int kProfMaxTimed = 32768;   // per class: enough to time every contraction launch of a multi-step bench run
 struct ProfState {
@@ -460,7 +460,8 @@ int band_min_p() {
 inline bool use_band(int64_t p, int dtype) { return dtype == MVB_F32 && p >= band_min_p() && !force_simt(); }
 
 struct BandWs {
-  int64_t *row_off, *col_off, *yrow_off, *iota, *rowP, *tab128, *tab256, *kofs, *rowUb, *iota_F, *iota_p;
+  int64_t *row_off, *col_off, *yrow_off, *iota, *rowP, *tab128, *tab256, *kofs, *rowUb, *iota_F, *iota_p, *zkoff;
+  float *R, *Ssel;             // fitted values of all (alpha, target) pairs, n x AF; substitution result of the selected alpha(s), F x P
   float *Qt, *Tdiag, *Tsub, *Minv, *Nmat, *Pb, *MN, *Z, *h, *U0, *U1, *C1, *C2, *Ct, *Ub, *Xb, *beta, *dd;
   double *mu64, *ybar64, *cz, *mb, *loss_partial, *loss64;
   void* lanczos_ws; void* contract_ws; size_t contract_bytes;
@@ -494,7 +495,10 @@ void carve_band(Arena& ar, const mvb_design* d, int F, int A, BandWs& w) {
   w.Nmat = ar.take<float>((int64_t)A * nb * 128 * 128);
   w.Pb = ar.take<float>((int64_t)A * nb * 128 * 128);
   w.MN = ar.take<float>((int64_t)A * nb * 128 * 256);
-  w.Z = ar.take<float>(n * std::max<int64_t>(P, AF));        // column-blocked [nb][n][128] for the sweep, later R (n x AF)
+  w.Z = ar.take<float>(n * P);                               // column-blocked [nb][n][128], centred: the sweep's and the fitted values' operand
+  w.R = ar.take<float>(n * AF);
+  w.Ssel = ar.take<float>((int64_t)F * P);
+  w.zkoff = ar.take<int64_t>(P);
   w.h = ar.take<float>((int64_t)mvb::TC_ROWSQ_PARTS * A * n);   // column parts of sum_j |u_j|^2
   w.U0 = ar.take<float>((int64_t)A * n * 128);
   w.U1 = ar.take<float>((int64_t)A * n * 128);
@@ -503,7 +507,6 @@ void carve_band(Arena& ar, const mvb_design* d, int F, int A, BandWs& w) {
   w.Ct = ar.take<float>((int64_t)F * P);
   w.Ub = ar.take<float>(AF * P);
   w.Xb = ar.take<float>(AF * P);
-  w.beta = ar.take<float>(AF * p);
   w.dd = ar.take<float>(n * A);
   w.mu64 = ar.take<double>(P);
   w.ybar64 = ar.take<double>(F);
@@ -516,11 +519,12 @@ void carve_band(Arena& ar, const mvb_design* d, int F, int A, BandWs& w) {
   cb = std::max(cb, plan_contract((int)F, (int)P, (int)p, MVB_F32, 0).ws_elems);
   cb = std::max(cb, plan_contract((int)AF, (int)p, (int)P, MVB_F32, 0).ws_elems);
   cb = std::max(cb, plan_contract((int)n, (int)P, (int)p, MVB_F32, 0).ws_elems);
-  cb = std::max(cb, plan_contract((int)n, (int)AF, (int)p, MVB_F32, 0).ws_elems);
+  cb = std::max(cb, plan_contract((int)n, (int)AF, (int)P, MVB_F32, 0).ws_elems);
+  cb = std::max(cb, plan_contract(F, (int)p, (int)P, MVB_F32, 0).ws_elems);
   w.contract_bytes = cb * 4;
   w.contract_ws = ar.take<char>(w.contract_bytes);
   w.planes_bytes = std::max(std::max(mvb::tc_planes_bytes((int)P, (int)p), mvb::tc_planes_bytes((int)p, (int)P)),
-                            mvb::tc_planes_bytes((int)AF, (int)p));
+                            mvb::tc_planes_bytes((int)AF, (int)P));
   w.planes = ar.take<char>(w.planes_bytes);
 }
 
@@ -557,6 +561,26 @@ __global__ void leverage_to_d_kernel(const float* __restrict__ h, int64_t n, int
     for (int part = 0; part < halves; ++part) hv += h[((int64_t)part * A + a) * n + i];
     d[e] = 1.f - c0 - hv;
   }
+}
+
+// k offsets of the column-blocked Z ([P / 128][n][128]) as a contraction operand: k -> (k / 128) * n * 128 + k % 128
+__global__ void zblock_koff_kernel(int64_t* __restrict__ koff, int64_t P, int64_t n) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < P; k += (int64_t)gridDim.x * blockDim.x)
+    koff[k] = (k >> 7) * n * 128 + (k & 127);
+}
+// out[f][:] = X[(best_f, f)][:]   (X: [A][F][P])
+__global__ void gather_rows_kernel(const float* __restrict__ X, int F, int64_t P, const int32_t* __restrict__ best, int per_target,
+                                   float* __restrict__ out) {
+  const int64_t total = (int64_t)F * P;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(e / P);
+    const int a = per_target ? best[f] : best[0];
+    out[e] = X[((int64_t)a * F + f) * P + (e - (int64_t)f * P)];
+  }
+}
+__global__ void intercept_kernel(const double* __restrict__ ybar, const double* __restrict__ mb, int F, int fit_intercept, float* intercept) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < F) intercept[f] = fit_intercept ? (float)(ybar[f] - mb[f]) : 0.f;
 }
 
 // helper stream for work that is independent of the caller's stream for a while (forked / joined with events): one per
@@ -742,28 +766,36 @@ int ridge_solve_band(const mvb_design* d, const float* y, int F, float* G, const
       mvb::bl::recur_update_kernel<<<cdiv(AF * 32, 256), 256, 0, st>>>(w.C1, j < nb - 1 ? w.C2 : nullptr, AF, w.Xb + (int64_t)j * 128, P, nullptr);
       MVB_LAUNCHED();
     }
-    // beta_all[(a,f)][jj] = sum_k Xb[(a,f)][k] Qt[k][jj]
+  }
+  // 6. fitted values for every (alpha, target) in the reduced basis:  X_c beta_a = Z_c (T + a I)^-1 Q b = Z_c Xb_a^T.  Z is already
+  //    there (centred, column-blocked), so the coefficients beta = Q^T x are only formed for the selected alpha(s) afterwards
+  //    (r01 built beta for the whole grid -- an (A F) x p x P product -- and contracted the implicit design with it).
+  zblock_koff_kernel<<<grid_for(P), 256, 0, st>>>(w.zkoff, P, n);                                    MVB_LAUNCHED();
+  {
+    mvb_operand opZ{w.Z, w.tab128, w.zkoff, (int)n, 2};          // row i at i * 128 inside a column block, k -> block * n * 128 + k % 128
     mvb_operand opX{w.Xb, w.rowP, w.iota, (int)AF, 2};
-    const float* Qc = (const float*)((const char*)w.lanczos_ws + mvb::lb::make_plan((int)p).off_Qc);   // Q^T from the reduction
-    mvb_operand opQc{Qc, w.rowP, w.iota, (int)p, 2};          // rows jj of Q^T, contraction k contiguous
-    { ProfScope ps(PC_SMALL); rc = run_contract<float>(opX, opQc, (int)AF, (int)p, (int)P, w.beta, p, 0, w.contract_ws, w.contract_bytes, st, 0, 0, w.planes, w.planes_bytes); }
+    { ProfScope ps(PC_RESIDUAL); rc = run_contract<float>(opZ, opX, (int)n, (int)AF, (int)P, w.R, AF, 0, w.contract_ws, w.contract_bytes, st, 0, 0, w.planes, w.planes_bytes); }
     if (rc) return rc;
   }
-  mvb::matvec_rows_kernel<float><<<cdiv(AF * 32, 256), 256, 0, st>>>(w.beta, AF, p, w.mu64, w.mb);   MVB_LAUNCHED();
-  // 6. fitted values for every (alpha, target): R = X_t beta_all^T, LOO losses, selection, coefficients
-  mvb_operand opBeta{w.beta, w.iota_p, w.iota, (int)AF, dense_mode(p, (int)p, w.beta, 4)};
-  { ProfScope ps(PC_RESIDUAL); rc = run_contract<float>(opRows, opBeta, (int)n, (int)AF, (int)p, w.Z, AF, 0, w.contract_ws, w.contract_bytes, st, 0, 0, w.planes, w.planes_bytes); }
-  if (rc) return rc;
+  MVB_CUDA(cudaMemsetAsync(w.mb, 0, (size_t)AF * sizeof(double), st));        // Z is centred: no <beta, mu> term in the residuals
   {
     dim3 grid(cdiv(AF, 128), w.slabs);
-    mvb::loo_loss_kernel<float><<<grid, 128, 0, st>>>(w.Z, n, A, F, AF, y, w.yrow_off, (int64_t)Tn, w.ybar64, w.mb, w.dd, w.loss_partial);
+    mvb::loo_loss_kernel<float><<<grid, 128, 0, st>>>(w.R, n, A, F, AF, y, w.yrow_off, (int64_t)Tn, w.ybar64, w.mb, w.dd, w.loss_partial);
     MVB_LAUNCHED();
     mvb::select_alpha_kernel<float><<<1, 256, 0, st>>>(w.loss_partial, w.slabs, A, F, 1.0 / (double)n, alphas, per_target, loss, best,
                                                        alpha_out, w.loss64);
     MVB_LAUNCHED();
-    mvb::gather_coef_kernel<float><<<grid_for((int64_t)F * p), 256, 0, st>>>(w.beta, F, p, best, per_target, w.ybar64, w.mb, fit_intercept,
-                                                                              coef, intercept);
-    MVB_LAUNCHED();
+  }
+  // 7. coefficients of the chosen alpha(s): coef[f] = Q^T Xb[(best_f, f)], intercept = ybar - <coef, mu>
+  {
+    gather_rows_kernel<<<grid_for((int64_t)F * P), 256, 0, st>>>(w.Xb, F, P, best, per_target, w.Ssel);   MVB_LAUNCHED();
+    mvb_operand opS{w.Ssel, w.rowP, w.iota, F, 2};
+    const float* Qc = (const float*)((const char*)w.lanczos_ws + mvb::lb::make_plan((int)p).off_Qc);   // Q^T from the reduction
+    mvb_operand opQc{Qc, w.rowP, w.iota, (int)p, 2};          // rows jj of Q^T, contraction k contiguous
+    { ProfScope ps(PC_SMALL); rc = run_contract<float>(opS, opQc, F, (int)p, (int)P, coef, p, 0, w.contract_ws, w.contract_bytes, st); }
+    if (rc) return rc;
+    mvb::matvec_rows_kernel<float><<<cdiv((int64_t)F * 32, 256), 256, 0, st>>>(coef, F, p, w.mu64, w.mb);   MVB_LAUNCHED();
+    intercept_kernel<<<cdiv(F, 256), 256, 0, st>>>(w.ybar64, w.mb, F, fit_intercept, intercept);            MVB_LAUNCHED();
   }
   return MVB_OK;
 }
