@@ -146,6 +146,7 @@ class _FoldContext(threading.local):
     parent = None       # dict(X=..., dim=..., idx=..., shared={...}) set by fit_validator_
     train = None        # training indices of the current fold, set by fit_model_
     model = None        # the model clone being fitted in the current fold, set by fit_model_
+    train_key = None    # host-side identity of ``train`` (validator.fold_key), set by fit_model_ when the driver computed one
 
 
 fold_ctx = _FoldContext()

@@ -20,7 +20,7 @@ import sklearn.base
 import torch
 from sklearn.pipeline import Pipeline
 
-from .. import _dist, _lib
+from .. import _dist, _lib, _streams
 from ..metrics import Metric, score
 from .kfold import KFold
 
@@ -67,8 +67,22 @@ def _resolve_metric(model, metric):
     return getattr(model, 'metric_', None)
 
 
+def _lanes_ok(model) -> bool:
+    """Folds may run on concurrent stream lanes when the fit is one of the large launch chains that profit (``TimeDelayed``
+    / ``RidgeCV`` behind per-feature preprocessing); estimators that manage streams or CUDA graphs themselves (``Sliding``)
+    and user-supplied models keep the caller's stream."""
+    last = model[-1] if isinstance(model, Pipeline) else model
+    return bool(getattr(last, '_mvb_fold_lanes', False))
+
+
+def fold_key(train: torch.Tensor):
+    """Host-side identity of a training set (key of the predictor-set drivers' per-fold statistics cache); computed by the
+    driver's own thread before the fold is enqueued, so that no fit has to read its indices back from the device."""
+    return hash(train.detach().cpu().numpy().tobytes())
+
+
 def fit_model_(model, train: torch.Tensor, test: torch.Tensor, X: torch.Tensor, y: Optional[torch.Tensor] = None,
-               metric: Optional[Union[Metric, Tuple[Metric]]] = None) -> Dict:
+               metric: Optional[Union[Metric, Tuple[Metric]]] = None, train_key=None) -> Dict:
     """One fold (validator.py:20-115)."""
     model = model.clone() if hasattr(model, 'clone') else deepcopy(model)
     metric = deepcopy(_resolve_metric(model, metric))
@@ -76,11 +90,11 @@ def fit_model_(model, train: torch.Tensor, test: torch.Tensor, X: torch.Tensor, 
     if y is not None and metric is not None:
         for m in (metric if many else (metric,)):
             m.grant({'y_b': y[train].mean(m.reduce, keepdim=True)})
-    _lib.fold_ctx.train, _lib.fold_ctx.model = train, model        # lets TimeDelayed share per-fold statistics across predictor sets
+    _lib.fold_ctx.train, _lib.fold_ctx.model, _lib.fold_ctx.train_key = train, model, train_key    # lets TimeDelayed share per-fold statistics across predictor sets
     try:
         model.fit(*((X[train], y[train]) if y is not None else (X[train],)))
     finally:
-        _lib.fold_ctx.train = _lib.fold_ctx.model = None
+        _lib.fold_ctx.train = _lib.fold_ctx.model = _lib.fold_ctx.train_key = None
     args = (X[test], y[test]) if y is not None else (X[test],)
     score_i = score(model, metric, *args) if metric is not None else model.score(*args)
     if many and len(metric) > 1:
@@ -136,17 +150,30 @@ class Validator(sklearn.base.BaseEstimator):
         shard = _dist.sharding_active()
         mine = set(_dist.my_units(len(folds))) if shard else set(range(len(folds)))
         local_scores: Dict[int, Any] = {}
-        with _dist.sharded_region():
-            for k, (train, test) in enumerate(folds):
-                self.test_.append(test)
-                if k not in mine:
-                    self.model_.append(None)
-                    self.metric_.append(None)
-                    continue
-                r = fit_model_(self.model, train.to(Xd.device), test.to(Xd.device), Xd, y=yd, metric=self.metric)
-                local_scores[k] = r['score_']
-                self.model_.append(_move_tensors(r['model'], out_dev))
-                self.metric_.append(_move_tensors(r['metric'], out_dev))
+        todo = [k for k in range(len(folds)) if k in mine]
+
+        keys = {k: fold_key(folds[k][0]) for k in todo} if _lib.fold_ctx.parent is not None else {}
+
+        def one(k: int):
+            train, test = folds[k]
+            return fit_model_(self.model, train.to(Xd.device), test.to(Xd.device), Xd, y=yd, metric=self.metric, train_key=keys.get(k))
+        with _dist.sharded_region():           # process-wide depth counter: held by this thread while the lanes work
+            # large fits leave SMs idle inside their launch chains: folds go to a few stream lanes (fold k always on lane k mod n)
+            if Xd.is_cuda and _lanes_ok(self.model):
+                done = _streams.run_on_lanes([(lambda k=k: one(k)) for k in todo], Xd.device, lane_keys=todo)
+            else:
+                done = [one(k) for k in todo]
+        fitted = dict(zip(todo, done))
+        for k, (train, test) in enumerate(folds):
+            self.test_.append(test)
+            r = fitted.get(k)
+            if r is None:
+                self.model_.append(None)
+                self.metric_.append(None)
+                continue
+            local_scores[k] = r['score_']
+            self.model_.append(_move_tensors(r['model'], out_dev))
+            self.metric_.append(_move_tensors(r['metric'], out_dev))
         if self._multi():
             self.score_ = {}
             for m in self.metric:

@@ -8,6 +8,7 @@ tables, so the lag expansion never exists in HBM -- neither as a matrix nor as p
 from __future__ import annotations
 
 import os
+import threading
 from typing import Dict, Optional, Tuple, Union
 
 import numpy as np
@@ -19,6 +20,7 @@ from .ridgecv import _RidgeCV_torch, solve_design
 
 
 SHARED_FOLD_ENTRIES = 8      # per-driver cache of per-fold full-predictor statistics (p x p Gram each): bounded
+_SHARED_LOCK = threading.Lock()
 
 
 def lag_window(t_min: float, t_max: float, fs: float) -> np.ndarray:
@@ -33,6 +35,8 @@ class _TimeDelayed_torch(sklearn.base.BaseEstimator):
     """Attributes: ``alphas, kwargs, patterns, t_min, t_max, fs, window`` (int32 lags), ``estimator`` (the
     inner RidgeCV holding ``alpha_``, flat ``coef_`` (f, c*w), ``intercept_``), ``f_, c_, w_``,
     ``intercept_`` (1, f), ``coef_`` (f, c, w) stored lag-reversed, ``pattern_``, ``metric_``."""
+
+    _mvb_fold_lanes = True       # a Validator may enqueue this estimator's folds on concurrent stream lanes (_streams.py)
 
     def __init__(self, t_min: float, t_max: float, fs: int, alphas: torch.Tensor = torch.tensor([1]), patterns: bool = False,
                  **kwargs):
@@ -123,7 +127,8 @@ class _TimeDelayed_torch(sklearn.base.BaseEstimator):
         n_tr, W = int(train.numel()), self.window.shape[0]
         if Xd.shape != (n_tr, int(idx.numel()), X_all.shape[2]) or n_tr * X_all.shape[2] <= X_all.shape[1] * W + 1:
             return None
-        key = (tuple(train.tolist()), W, self._lag_min, bool(self.estimator.fit_intercept))
+        tkey = ctx.train_key if ctx.train_key is not None else tuple(train.tolist())     # the latter reads the indices back (sync)
+        key = (tkey, W, self._lag_min, bool(self.estimator.fit_intercept))
         entry = par['shared'].get(key)
         if entry is None:
             X_tr = X_all[train.to(X_all.device)]
@@ -133,9 +138,10 @@ class _TimeDelayed_torch(sklearn.base.BaseEstimator):
             if self.estimator.fit_intercept:
                 full, shift = _lib.shift_design(full)             # centring before multiplying (ridgecv.solve_design)
             entry = (full, _lib.trf_stats(full, yd, self.estimator.fit_intercept), shift)
-            while len(par['shared']) >= SHARED_FOLD_ENTRIES:          # oldest first (dicts keep insertion order): splitters that
-                par['shared'].pop(next(iter(par['shared'])))          # reshuffle per clone would otherwise grow this without reuse
-            par['shared'][key] = entry
+            with _SHARED_LOCK:                                        # folds of one driver may be fitted from several lane threads
+                while len(par['shared']) >= SHARED_FOLD_ENTRIES:      # oldest first (dicts keep insertion order): splitters that
+                    par['shared'].pop(next(iter(par['shared'])))      # reshuffle per clone would otherwise grow this without reuse
+                par['shared'][key] = entry
         full, (G, XtY, mu, ybar), shift = entry
         Gs, Bs, ms = _lib.gather_stats(G, XtY, mu, idx, W)
         return full.subset(feat_idx=idx), (Gs, Bs, ms, ybar), shift

@@ -153,23 +153,32 @@ class Hierarchical:
         vals = [base.clone() for _ in range(n_sets)]
         for v in vals:
             v.model_, v.metric_, v.test_ = [None] * K, [None] * K, [te for _, te in folds]
-        local, shared, cur_fold = {}, {}, None
+        from ..crossvalidation.validator import fold_key, _lanes_ok
+        from .. import _streams
+        local, shared = {}, {}                                        # `shared` is bounded by the estimator (oldest fold evicted)
         idxs = [torch.nonzero(m.to(Xd.device), as_tuple=False).squeeze(-1) for m in masks]
+        keys = [fold_key(tr) for tr, _ in folds]
+
+        def one(u: int):
+            i, k = u // K, u % K
+            X_i = torch.index_select(Xd, dim=dim, index=idxs[i])
+            _lib.fold_ctx.parent = dict(X=Xd, dim=dim, idx=idxs[i], shared=shared)
+            try:
+                return fit_model_(base.model, folds[k][0].to(Xd.device), folds[k][1].to(Xd.device), X_i, y=yd, metric=base.metric,
+                                  train_key=keys[k])
+            finally:
+                _lib.fold_ctx.parent = None
         with _dist.sharded_region():
-            for u in mine:
-                i, k = u // K, u % K
-                if k != cur_fold:
-                    shared.clear()
-                    cur_fold = k
-                X_i = torch.index_select(Xd, dim=dim, index=idxs[i])
-                _lib.fold_ctx.parent = dict(X=Xd, dim=dim, idx=idxs[i], shared=shared)
-                try:
-                    r = fit_model_(base.model, folds[k][0].to(Xd.device), folds[k][1].to(Xd.device), X_i, y=yd, metric=base.metric)
-                finally:
-                    _lib.fold_ctx.parent = None
-                local[u] = r['score_']
-                vals[i].model_[k] = _move_tensors(r['model'], out_dev)
-                vals[i].metric_[k] = _move_tensors(r['metric'], out_dev)
+            # units of one fold share its statistics and stay on one stream lane, in order; different folds overlap
+            if Xd.is_cuda and _lanes_ok(base.model):
+                done = _streams.run_on_lanes([(lambda u=u: one(u)) for u in mine], Xd.device, lane_keys=[u % K for u in mine])
+            else:
+                done = [one(u) for u in mine]
+        for u, r in zip(mine, done):
+            i, k = u // K, u % K
+            local[u] = r['score_']
+            vals[i].model_[k] = _move_tensors(r['model'], out_dev)
+            vals[i].metric_[k] = _move_tensors(r['metric'], out_dev)
         names = multi if multi is not None else [None]
         scores = {}
         for name in names:

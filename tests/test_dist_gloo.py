@@ -52,7 +52,7 @@ def _stub_fit_validator(validator, X, y, mask, dim, shared=None, split_like=None
     return _StubValidator(_base_score(X, (m * w).sum()) + _FOLD_TABLE)
 
 
-def _stub_fit_model(model, train, test, X, y=None, metric=None):
+def _stub_fit_model(model, train, test, X, y=None, metric=None, train_key=None):
     """One (set, fold) unit of the sharded Hierarchical: the same numbers as fold k of _stub_fit_validator, rebuilt from the
     context the driver hands to the estimators (parent array + selected feature indices)."""
     from mvpy_b200 import _lib

@@ -742,6 +742,36 @@ def test_predictor_sets_share_fold_statistics(monkeypatch):
         np.testing.assert_allclose(out['1'][1].cpu().numpy(), out['0'][1].cpu().numpy(), rtol=0, atol=4e-5)
 
 
+def test_fold_lanes_give_the_serial_numbers():
+    """Folds enqueued on concurrent stream lanes (mvpy_b200/_streams.py; the reference's joblib site validator.py:365-380)
+    run the same kernels in the same per-fold order: scores, alphas and coefficients are bit-identical to the serial run,
+    for cross_val_score (band route, p = 6 x 51 = 306) and for hierarchical_score with shared per-fold statistics; host
+    inputs included."""
+    from mvpy_b200 import _streams
+    mv = _mv()
+    torch.manual_seed(5)
+    X, y = mv.dataset.make_meeg_continuous(fs=50, n_trials=60, n_channels=12, n_features=6)
+    al = torch.logspace(-3, 3, 9)
+    groups = torch.tensor([[1, 1, 0, 0, 0, 0], [0, 0, 1, 1, 0, 0], [0, 0, 0, 0, 1, 1]])
+    out = {}
+    try:
+        for lanes in (1, 2, 3):
+            _streams.set_fold_streams(lanes)
+            pipe = make_pipeline(mv.preprocessing.Scaler().to_torch(), mv.estimators.TimeDelayed(-1.0, 0.0, 50, alphas=al))
+            v, sc = mv.crossvalidation.cross_val_score(pipe, X.cuda(), y.cuda(), cv=5)
+            vh, sch = mv.crossvalidation.cross_val_score(pipe, X, y, cv=5)                      # host tensors
+            h, hs = mv.model_selection.hierarchical_score(pipe, X.cuda(), y.cuda(), groups=groups, cv=4)
+            coef = torch.stack([m[-1].coef_ for m in v.model_])
+            alpha = torch.stack([m[-1].estimator.alpha_ for m in v.model_])
+            out[lanes] = (sc, sch, hs, coef, alpha)
+            assert sch.device.type == 'cpu' and vh.model_[0][-1].coef_.device.type == 'cpu'
+    finally:
+        _streams.set_fold_streams(None)
+    for lanes in (2, 3):
+        for a, b in zip(out[1], out[lanes]):
+            assert torch.equal(a, b), lanes
+
+
 @pytest.mark.parametrize('shape', [(6, 20, 400, -1.0, 200, None, None),          # 201 lags: 7 blocks per feature, 9 rows in the last
                                    (5, 40, 152, -0.315, 200, [4, 0, 2], None),      # 64 lags, two unequal K chunks, a training subset
                                    (4, 24, 256, -0.5, 200, None, [0, 3, 4, 7, 8, 11, 12, 15, 16, 19, 20, 21, 22, 23, 1, 2, 5, 6, 9, 10])])
