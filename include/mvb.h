@@ -147,6 +147,30 @@ int mvb_ridge_solve(const mvb_design* d, const void* y, int n_targets, void* G, 
                     void* coef, void* intercept, void* alpha_out, int32_t* best, void* loss,
                     void* ws, size_t ws_bytes, void* stream);
 
+/* ---- batched small dense LOO ridge (mvb_dense_ridge_batched) -------------------------------------------------
+ * replaces the per-slice estimator loop of _Sliding_torch.fit (estimators/sliding.py:575-622) around _RidgeCV_torch.fit
+ * (estimators/ridgecv.py:96-303) -- per-timepoint decoding fits one small ridge per time slice -- and the same loop over any
+ * stack of equally shaped dense problems.  Problem b of `batch`:  X_b[i][c] = X.base[b * batch_stride + s(i) * sample_stride +
+ * c * col_stride], s(i) = sample_idx[i] (NULL = i), likewise Y_b[i][f]; a Sliding view of an (N, C, T) array has
+ * sample_stride = C * T, col_stride = T, batch_stride = 1.  Outputs, per problem: coef [batch][F][p], intercept [batch][F],
+ * alpha_out / best [batch][F] (alpha_per_target) or [batch], loss [batch][A][F] (may be NULL), gram [batch][p][p] = centred
+ * X^T X (may be NULL; RidgeDecoder's patterns, ridgedecoder.py:267-285).  status[b] != 0: problem b met a pivot below
+ * 1e-4 x its largest diagonal entry in some (G + alpha I) -- its outputs are not to be trusted and the caller refits it on the
+ * general route (mvb_trf_stats + mvb_ridge_solve).  float32, 1 <= p <= mvb_dense_ridge_batched_max_cols(), n > p + 1.       */
+typedef struct { const void* base; int64_t sample_stride, col_stride, batch_stride; } mvb_strided;
+int mvb_dense_ridge_batched_max_cols(void);
+size_t mvb_dense_ridge_batched_workspace_bytes(int batch, int n_samples, int n_cols, int n_targets, int n_alphas);
+int mvb_dense_ridge_batched(const mvb_strided* X, const mvb_strided* Y, const int32_t* sample_idx, int n_samples, int n_cols,
+                            int n_targets, int batch, const void* alphas, int n_alphas, int fit_intercept, int alpha_per_target,
+                            int dtype, void* coef, void* intercept, void* alpha_out, int32_t* best, void* loss, void* gram,
+                            int32_t* status, void* ws, size_t ws_bytes, void* stream);
+/* the matching prediction, replaces the per-slice loop of _Sliding_torch.predict (estimators/sliding.py:770-831) over
+ * _RidgeCV_torch.predict (ridgecv.py:305-323): yhat_b[i][f] = X_b[i] . coef[b][f] + intercept[b][f] (intercept may be NULL),
+ * written at yhat[i * out_sample_stride + f * out_target_stride + b * out_batch_stride].                                   */
+int mvb_dense_predict_batched(const mvb_strided* X, int n_samples, int n_cols, int batch, const void* coef, const void* intercept,
+                              int n_targets, int dtype, void* yhat, int64_t out_sample_stride, int64_t out_target_stride,
+                              int64_t out_batch_stride, void* stream);
+
 /* ---- prediction -------------------------------------------------------------------------------------
  * replaces _TimeDelayed_torch.predict / _RidgeCV_torch.predict (timedelayed.py:522-533,
  * ridgecv.py:323): yhat[(s*F + f)*T + t] = sum_j X_t[(s,t), j] coef[f, j] + intercept[f].      */

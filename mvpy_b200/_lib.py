@@ -31,6 +31,10 @@ class mvb_design(ctypes.Structure):
                 ('n_feat', c_int), ('dtype', c_int)]
 
 
+class mvb_strided(ctypes.Structure):
+    _fields_ = [('base', c_void_p), ('sample_stride', c_int64), ('col_stride', c_int64), ('batch_stride', c_int64)]
+
+
 class mvb_operand(ctypes.Structure):
     _fields_ = [('base', c_void_p), ('roff', c_void_p), ('koff', c_void_p), ('rows', c_int), ('contig', c_int)]
 
@@ -82,6 +86,13 @@ _SIGNATURES = {
     'mvb_sum_slabs': (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'mvb_penalised_solve': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'mvb_score': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    'mvb_dense_ridge_batched_max_cols': (c_int, []),
+    'mvb_dense_ridge_batched_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    'mvb_dense_ridge_batched': (c_int, [POINTER(mvb_strided), POINTER(mvb_strided), c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                        c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_size_t, c_void_p]),
+    'mvb_dense_predict_batched': (c_int, [POINTER(mvb_strided), c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64,
+                                          c_int64, c_int64, c_void_p]),
 }
 
 _lib = None
@@ -490,3 +501,68 @@ def contract(a_base, a_roff, a_koff, a_contig, b_base, b_roff, b_koff, b_contig,
     check(lib.mvb_contract(ctypes.byref(A), ctypes.byref(B), M, N, K, dtype_code(a_base), _ptr(C), N, int(symmetric), _ptr(ws),
                            ws.numel(), _stream(a_base)), 'mvb_contract')
     return C
+
+
+DENSE_BATCH_WS_LIMIT = 12 << 30      # bytes of scratch per mvb_dense_ridge_batched call; larger stacks are fitted in chunks
+
+
+def _strided(t3: torch.Tensor) -> mvb_strided:
+    return mvb_strided(t3.data_ptr(), t3.stride(0), t3.stride(1), t3.stride(2))
+
+
+def dense_ridge_batched_ok(n: int, p: int, F: int, A: int, dtype) -> bool:
+    """Shapes the batched small-problem route takes (float32, p <= 320, more samples than columns)."""
+    if dtype != torch.float32:
+        return False
+    return p <= load().mvb_dense_ridge_batched_max_cols() and n > p + 1 and A * F <= 4096
+
+
+def dense_ridge_batched(X3: torch.Tensor, Y3: torch.Tensor, sample_idx: Optional[torch.Tensor], alphas: torch.Tensor, fit_intercept: bool,
+                        alpha_per_target: bool, want_loss: bool = True, want_gram: bool = False):
+    """B independent LOO ridge fits in one call (``mvb_dense_ridge_batched``).  X3: (N, p, B) and Y3: (N, F, B) float32 CUDA
+    tensors of ANY strides (problem b is X3[sample_idx, :, b] -> Y3[sample_idx, :, b]; nothing is copied here).
+    Returns dict(coef (B, F, p), intercept (B, F), alpha (B, F) or (B,), best, loss (B, A, F) | None, gram (B, p, p) | None,
+    status (B,) int32: non-zero = refit that problem on the general route)."""
+    N, p, B = X3.shape
+    F = Y3.shape[1]
+    A = int(alphas.numel())
+    dev = X3.device
+    si = None if sample_idx is None else sample_idx.to(device=dev, dtype=torch.int32).contiguous()
+    n = N if si is None else int(si.numel())
+    lib = load()
+    nb = B if alpha_per_target else 1
+    coef = torch.empty((B, F, p), dtype=torch.float32, device=dev)
+    icpt = torch.empty((B, F), dtype=torch.float32, device=dev)
+    alpha = torch.empty((B, F) if alpha_per_target else (B,), dtype=torch.float32, device=dev)
+    best = torch.empty((B, F) if alpha_per_target else (B,), dtype=torch.int32, device=dev)
+    loss = torch.empty((B, A, F), dtype=torch.float32, device=dev) if want_loss else None
+    gram = torch.empty((B, p, p), dtype=torch.float32, device=dev) if want_gram else None
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    al = alphas.to(device=dev, dtype=torch.float32).contiguous()
+    per = lib.mvb_dense_ridge_batched_workspace_bytes(1, n, p, F, A)
+    if per == 0:
+        raise MvbError(f'mvb_dense_ridge_batched does not take n = {n}, p = {p}, F = {F}, A = {A}')
+    chunk = max(1, min(B, 65535, int(DENSE_BATCH_WS_LIMIT // per)))
+    ws = _workspace(lib.mvb_dense_ridge_batched_workspace_bytes(chunk, n, p, F, A), dev)
+    st = _stream(X3)
+    for b0 in range(0, B, chunk):
+        bc = min(chunk, B - b0)
+        xs, ys = _strided(X3[:, :, b0:b0 + bc]), _strided(Y3[:, :, b0:b0 + bc])
+        check(lib.mvb_dense_ridge_batched(ctypes.byref(xs), ctypes.byref(ys), _ptr(si), n, p, F, bc, _ptr(al), A, int(fit_intercept),
+                                          int(alpha_per_target), F32, _ptr(coef[b0:]), _ptr(icpt[b0:]), _ptr(alpha[b0:]), _ptr(best[b0:]),
+                                          _ptr(loss[b0:]) if want_loss else None, _ptr(gram[b0:]) if want_gram else None,
+                                          _ptr(status[b0:]), _ptr(ws), ws.numel(), st), 'mvb_dense_ridge_batched')
+    return dict(coef=coef, intercept=icpt, alpha=alpha, best=best, loss=loss, gram=gram, status=status)
+
+
+def dense_predict_batched(X3: torch.Tensor, coef: torch.Tensor, intercept: Optional[torch.Tensor]) -> torch.Tensor:
+    """X3 (N, p, B) any strides, coef (B, F, p), intercept (B, F) | None -> predictions (N, F, B) (``mvb_dense_predict_batched``)."""
+    N, p, B = X3.shape
+    F = coef.shape[1]
+    out = torch.empty((N, F, B), dtype=torch.float32, device=X3.device)
+    xs = _strided(X3)
+    coef = coef.contiguous()
+    icpt = None if intercept is None else intercept.contiguous()
+    check(load().mvb_dense_predict_batched(ctypes.byref(xs), N, p, B, _ptr(coef), _ptr(icpt), F, F32, _ptr(out), out.stride(0), out.stride(1),
+                                           out.stride(2), _stream(X3)), 'mvb_dense_predict_batched')
+    return out

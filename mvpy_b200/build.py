@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'mvb_api.cu')
 DEPS = [SRC, os.path.join(HERE, 'csrc', 'mvb_kernels.cuh'), os.path.join(HERE, 'csrc', 'tc_gemm.cuh'), os.path.join(HERE, 'csrc', 'jacobi_block.cuh'), os.path.join(HERE, 'csrc', 'lanczos_band.cuh'), os.path.join(HERE, 'csrc', 'toeplitz_gram.cuh'), os.path.join(HERE, 'csrc', 'gram_recurrence.cuh'),
-        os.path.join(HERE, 'csrc', 'band_loo.cuh'), os.path.join(HERE, 'csrc', 'sweep_chain.cuh'), os.path.join(HERE, 'csrc', 'rf_kernels.cuh'),
+        os.path.join(HERE, 'csrc', 'band_loo.cuh'), os.path.join(HERE, 'csrc', 'sweep_chain.cuh'), os.path.join(HERE, 'csrc', 'rf_kernels.cuh'), os.path.join(HERE, 'csrc', 'dense_batched.cuh'),
         os.path.join(HERE, '..', 'include', 'mvb.h')]
 OUT = os.path.join(HERE, 'libmvb.so')
 

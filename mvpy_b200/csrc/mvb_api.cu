@@ -17,6 +17,7 @@
 #include "band_loo.cuh"
 #include "sweep_chain.cuh"
 #include "rf_kernels.cuh"
+#include "dense_batched.cuh"
 
 namespace {
 
@@ -918,6 +919,145 @@ int predict_impl(const mvb_design* d, const T* coef, const T* intercept, int F, 
   return MVB_OK;
 }
 
+
+// ---- batched small dense LOO ridge (dense_batched.cuh) ------------------------------------------------------
+struct DenseWs {
+  float *Xc, *Yc, *mu, *ybar, *G, *XtY, *Li, *rowsq, *beta, *R, *d;
+  double* partial;
+  int64_t *roffX, *roffXt, *koffN, *iota, *roffLi, *roffBeta;
+  int Pp, tri_rows, tiles_per_alpha, slabs;
+};
+
+void carve_dense(Arena& ar, int B, int n, int p, int F, int A, DenseWs& w) {
+  const int Pp = (p + mvb::db::NB - 1) / mvb::db::NB * mvb::db::NB;
+  const int tri_rows = (Pp + mvb::db::TRI_TILE - 1) / mvb::db::TRI_TILE * mvb::db::TRI_TILE;
+  w.Pp = Pp; w.tri_rows = tri_rows; w.tiles_per_alpha = tri_rows / mvb::db::TRI_TILE;
+  w.slabs = 8;
+  const int64_t AF = (int64_t)A * F;
+  w.Xc = ar.take<float>((int64_t)B * n * Pp);
+  w.Yc = ar.take<float>((int64_t)B * n * F);
+  w.mu = ar.take<float>((int64_t)B * Pp);
+  w.ybar = ar.take<float>((int64_t)B * F);
+  w.G = ar.take<float>((int64_t)B * Pp * Pp);
+  w.XtY = ar.take<float>((int64_t)B * Pp * F);
+  w.Li = ar.take<float>((int64_t)B * A * tri_rows * Pp);
+  w.rowsq = ar.take<float>((int64_t)A * w.tiles_per_alpha * mvb::TC_ROWSQ_PARTS * B * n);
+  w.beta = ar.take<float>((int64_t)B * AF * Pp);
+  w.R = ar.take<float>((int64_t)B * n * AF);
+  w.d = ar.take<float>((int64_t)B * A * n);
+  w.partial = ar.take<double>((int64_t)B * w.slabs * AF);
+  w.roffX = ar.take<int64_t>((int64_t)B * n);
+  w.roffXt = ar.take<int64_t>((int64_t)B * Pp);
+  w.koffN = ar.take<int64_t>(n);
+  w.iota = ar.take<int64_t>(std::max(n, Pp));
+  w.roffLi = ar.take<int64_t>((int64_t)B * A * tri_rows);
+  w.roffBeta = ar.take<int64_t>((int64_t)B * AF);
+}
+
+bool dense_batched_ok(int B, int n, int p, int F, int A) {
+  return B >= 1 && p >= 1 && p <= mvb::db::MAX_COLS && F >= 1 && A >= 1 && n > p + 1 && (int64_t)A * F <= 4096 &&
+         (int64_t)A * ((p + 127) / 128) * 128 <= 65535 * 128LL && n <= 65535 * 4;
+}
+
+int dense_batched_launch(mvb::TcGemmParams& g, int bn, int cls, double flops, cudaStream_t st) {
+  g_prof_class = cls;
+  const int slot = prof_begin(flops, st);
+  cudaError_t e = mvb::tc_gemm_launch(g, 1, bn, st);
+  prof_end(slot, st);
+  g_prof_class = PC_OTHER;
+  if (e != cudaSuccess) return fail(MVB_E_CUDA, "dense_ridge_batched: contraction launch failed: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return MVB_OK;
+}
+
+int dense_ridge_batched_impl(const mvb_strided* X, const mvb_strided* Y, const int32_t* sample_idx, int n, int p, int F, int B,
+                             const float* alphas, int A, int fit_intercept, int per_target, float* coef, float* intercept,
+                             float* alpha_out, int32_t* best, float* loss, float* gram, int32_t* status, void* ws, size_t ws_bytes,
+                             cudaStream_t st) {
+  namespace db = mvb::db;
+  Arena ar(ws, ws_bytes);
+  DenseWs w;
+  carve_dense(ar, B, n, p, F, A, w);
+  if (!ar.ok()) return fail(MVB_E_WORKSPACE, "dense_ridge_batched: workspace %zu < %zu", ws_bytes, ar.off);
+  const int Pp = w.Pp, AF = A * F;
+  const db::View xv{(const float*)X->base, X->sample_stride, X->col_stride, X->batch_stride};
+  const db::View yv{(const float*)Y->base, Y->sample_stride, Y->col_stride, Y->batch_stride};
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(db::chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)db::chol_inv_smem(db::MAX_COLS));
+  });
+  MVB_CUDA(attr_err);
+  MVB_CUDA(cudaMemsetAsync(status, 0, (size_t)B * sizeof(int32_t), st));
+  MVB_CUDA(cudaMemsetAsync(w.mu, 0, (size_t)B * Pp * sizeof(float), st));            // padding columns read as mean 0
+  db::tables_kernel<<<grid_for((int64_t)B * (n + Pp + (int64_t)A * w.tri_rows + AF)), 256, 0, st>>>(B, n, Pp, AF, A, w.tri_rows, w.roffX, w.roffXt,
+                                                                                                     w.koffN, w.iota, w.roffLi, w.roffBeta);
+  MVB_LAUNCHED();
+  // 1. centring before multiplying (ridgecv.py:59-94) + slice-major packing
+  db::means_kernel<<<grid_for((int64_t)p * B), 256, 0, st>>>(xv, sample_idx, n, p, B, fit_intercept, w.mu, Pp);
+  MVB_LAUNCHED();
+  db::means_kernel<<<grid_for((int64_t)F * B), 256, 0, st>>>(yv, sample_idx, n, F, B, fit_intercept, w.ybar, F);
+  MVB_LAUNCHED();
+  db::pack_kernel<<<dim3(cdiv(Pp, 32), cdiv(B, 32), n), dim3(32, 8), 0, st>>>(xv, sample_idx, n, p, B, w.mu, Pp, w.Xc, Pp);
+  MVB_LAUNCHED();
+  db::pack_kernel<<<dim3(cdiv(F, 32), cdiv(B, 32), n), dim3(32, 8), 0, st>>>(yv, sample_idx, n, F, B, w.ybar, F, w.Yc, F);
+  MVB_LAUNCHED();
+  // 2. G_b = Xc_b^T Xc_b (rows = columns of the slice, contraction over its samples), X^T y
+  {
+    mvb::TcGemmParams g = mvb::tc_gemm_defaults();
+    g.A = {w.Xc, w.roffXt, w.koffN, Pp, 0};
+    g.B = g.A;
+    g.M = Pp; g.N = Pp; g.K = n; g.C = w.G; g.ldc = Pp; g.batch = B;
+    g.a_roff_batch = Pp; g.b_roff_batch = Pp; g.c_batch_stride = (int64_t)Pp * Pp;
+    int rc = dense_batched_launch(g, Pp > 128 ? 256 : 128, PC_GRAM, 2.0 * Pp * (double)Pp * n * B, st);
+    if (rc) return rc;
+  }
+  db::xty_kernel<<<dim3(cdiv(Pp, 128), B, cdiv(F, 8)), 128, 0, st>>>(w.Xc, w.Yc, n, Pp, F, w.XtY);
+  MVB_LAUNCHED();
+  if (gram) {
+    db::copy_gram_kernel<<<grid_for((int64_t)B * p * p), 256, 0, st>>>(w.G, B, p, Pp, gram);
+    MVB_LAUNCHED();
+  }
+  // 3. per (slice, alpha): Cholesky factor and its inverse
+  db::chol_inv_kernel<<<B * A, db::CI_THREADS, db::chol_inv_smem(Pp), st>>>(w.G, p, Pp, alphas, A, 1e-4f, w.Li, w.tri_rows, status);
+  MVB_LAUNCHED();
+  // 4. leverages: row squares of Xc_b [L_a^-1]^T for the stack of all alphas (nothing but the squares is stored)
+  MVB_CUDA(cudaMemsetAsync(w.rowsq, 0, (size_t)A * w.tiles_per_alpha * mvb::TC_ROWSQ_PARTS * B * n * sizeof(float), st));
+  {
+    mvb::TcGemmParams g = mvb::tc_gemm_defaults();
+    g.A = {w.Xc, w.roffX, w.iota, n, 2};
+    g.B = {w.Li, w.roffLi, w.iota, A * w.tri_rows, 2};
+    g.M = n; g.N = A * w.tri_rows; g.K = Pp; g.C = nullptr; g.ldc = 0; g.batch = B;
+    g.a_roff_batch = n; g.b_roff_batch = (int64_t)A * w.tri_rows;
+    g.rowsq = w.rowsq; g.b_tri_period = w.tiles_per_alpha;
+    // flops counted for the triangular half actually contracted
+    double kk = 0;
+    for (int t = 0; t < w.tiles_per_alpha; ++t) kk += std::min(Pp, (t + 1) * db::TRI_TILE);
+    int rc = dense_batched_launch(g, db::TRI_TILE, PC_LEVERAGE_Z, 2.0 * n * (double)db::TRI_TILE * kk * A * B, st);
+    if (rc) return rc;
+  }
+  db::leverage_d_kernel<<<grid_for((int64_t)B * A * n), 256, 0, st>>>(w.rowsq, B, A, n, w.tiles_per_alpha, fit_intercept ? 1.f / (float)n : 0.f, w.d);
+  MVB_LAUNCHED();
+  // 5. coefficients of every alpha, fitted values, LOO losses, selection
+  db::beta_kernel<<<B * A, 256, 0, st>>>(w.Li, w.tri_rows, Pp, w.XtY, F, A, w.beta);
+  MVB_LAUNCHED();
+  {
+    mvb::TcGemmParams g = mvb::tc_gemm_defaults();
+    g.A = {w.Xc, w.roffX, w.iota, n, 2};
+    g.B = {w.beta, w.roffBeta, w.iota, AF, 2};
+    g.M = n; g.N = AF; g.K = Pp; g.C = w.R; g.ldc = AF; g.batch = B;
+    g.a_roff_batch = n; g.b_roff_batch = AF; g.c_batch_stride = (int64_t)n * AF;
+    int rc = dense_batched_launch(g, AF > 128 ? 256 : 128, PC_RESIDUAL, 2.0 * n * (double)AF * Pp * B, st);
+    if (rc) return rc;
+  }
+  db::loss_kernel<<<dim3(B, w.slabs), 128, 0, st>>>(w.R, w.Yc, w.d, n, A, F, w.slabs, w.partial);
+  MVB_LAUNCHED();
+  db::select_kernel<<<B, 256, (size_t)(AF + F) * 4, st>>>(w.partial, w.slabs, n, A, F, p, Pp, alphas, per_target, fit_intercept, w.beta, w.mu,
+                                                         w.ybar, loss, best, alpha_out, coef, intercept);
+  MVB_LAUNCHED();
+  return MVB_OK;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -1134,6 +1274,47 @@ int mvb_trf_predict(const mvb_design* d, const void* coef, const void* intercept
   cudaStream_t st = (cudaStream_t)stream;
   if (d->dtype == MVB_F32) return predict_impl<float>(d, (const float*)coef, (const float*)intercept, n_targets, (float*)yhat, ws, ws_bytes, st);
   return predict_impl<double>(d, (const double*)coef, (const double*)intercept, n_targets, (double*)yhat, ws, ws_bytes, st);
+}
+
+int mvb_dense_ridge_batched_max_cols(void) { return mvb::db::MAX_COLS; }
+
+size_t mvb_dense_ridge_batched_workspace_bytes(int batch, int n_samples, int n_cols, int n_targets, int n_alphas) {
+  if (!dense_batched_ok(batch, n_samples, n_cols, n_targets, n_alphas) || batch > 65535) return 0;
+  Arena ar(nullptr, 0);
+  DenseWs w;
+  carve_dense(ar, batch, n_samples, n_cols, n_targets, n_alphas, w);
+  return ar.off + 256;
+}
+
+int mvb_dense_ridge_batched(const mvb_strided* X, const mvb_strided* Y, const int32_t* sample_idx, int n_samples, int n_cols,
+                            int n_targets, int batch, const void* alphas, int n_alphas, int fit_intercept, int alpha_per_target,
+                            int dtype, void* coef, void* intercept, void* alpha_out, int32_t* best, void* loss, void* gram,
+                            int32_t* status, void* ws, size_t ws_bytes, void* stream) {
+  if (!X || !Y || !X->base || !Y->base || !alphas || !coef || !intercept || !alpha_out || !best || !status || !ws)
+    return fail(MVB_E_ARG, "dense_ridge_batched: bad argument");
+  if (dtype != MVB_F32) return fail(MVB_E_UNSUPPORTED, "dense_ridge_batched: float32 only (float64 problems take mvb_ridge_solve per problem)");
+  if (!dense_batched_ok(batch, n_samples, n_cols, n_targets, n_alphas) || batch > 65535)
+    return fail(MVB_E_UNSUPPORTED, "dense_ridge_batched: needs 1 <= n_cols <= %d, n_samples > n_cols + 1, batch <= 65535 (got n = %d, p = %d, batch = %d)",
+                mvb::db::MAX_COLS, n_samples, n_cols, batch);
+  return dense_ridge_batched_impl(X, Y, sample_idx, n_samples, n_cols, n_targets, batch, (const float*)alphas, n_alphas, fit_intercept,
+                                  alpha_per_target, (float*)coef, (float*)intercept, (float*)alpha_out, best, (float*)loss, (float*)gram,
+                                  status, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int mvb_dense_predict_batched(const mvb_strided* X, int n_samples, int n_cols, int batch, const void* coef, const void* intercept,
+                              int n_targets, int dtype, void* yhat, int64_t out_sample_stride, int64_t out_target_stride,
+                              int64_t out_batch_stride, void* stream) {
+  if (!X || !X->base || !coef || !yhat || n_samples < 1 || n_cols < 1 || batch < 1 || n_targets < 1)
+    return fail(MVB_E_ARG, "dense_predict_batched: bad argument");
+  if (dtype != MVB_F32) return fail(MVB_E_UNSUPPORTED, "dense_predict_batched: float32 only");
+  cudaStream_t st = (cudaStream_t)stream;
+  const mvb::db::View xv{(const float*)X->base, X->sample_stride, X->col_stride, X->batch_stride};
+  if (cdiv(n_samples, 4) > 65535 || cdiv(n_targets, 4) > 65535) return fail(MVB_E_UNSUPPORTED, "dense_predict_batched: too many samples / targets");
+  mvb::db::predict_kernel<<<dim3(cdiv(batch, 32), cdiv(n_samples, 4), cdiv(n_targets, 4)), dim3(32, 4), 0, st>>>(
+      xv, n_samples, n_cols, batch, (const float*)coef, (const float*)intercept, n_targets, (float*)yhat, out_sample_stride,
+      out_target_stride, out_batch_stride);
+  MVB_LAUNCHED();
+  return MVB_OK;
 }
 
 int mvb_rank(const void* x, int64_t R, int64_t K, int dtype, void* out, void* stream) {

@@ -61,8 +61,10 @@ struct TcGemmParams {
   // ---- output options ----
   int c_block_cols;                   // > 0: C is stored in column blocks, [N / c_block_cols][M][c_block_cols]
   int64_t c_block_stride;             //      elements between consecutive column blocks (>= M * c_block_cols)
-  float* rowsq;                       // optional [TC_ROWSQ_PARTS][batch][M]: += sum over this thread's columns of C[m][n]^2
-                                      // (one output tile wide only: N <= BN; split-K not allowed)
+  float* rowsq;                       // optional [N tiles][TC_ROWSQ_PARTS][batch][M]: += sum over this thread's columns of C[m][n]^2
+                                      // (split-K not allowed); C may be nullptr when only the row squares are wanted
+  int b_tri_period;                   // > 0: B is a stack of lower-triangular blocks (B[n][k] = 0 for k > n mod period*BN), `period`
+                                      //      N tiles each: tile t contracts only k < ((t mod period) + 1) * BN  (batch kernel only)
   // ---- pre-split B operand (256-wide tiles only, batch == 1) ----
   const uint8_t* b_planes;            // optional: B already split into TF32 hi / lo planes, one shared-memory image per
   int b_planes_nkb;                   //   (256-row tile, 32-k stage), [n_tile][b_planes_nkb][2 * plane bytes] (tc_presplit_launch);
@@ -326,9 +328,9 @@ __device__ __forceinline__ void store_tile(const TcGemmParams& p, const float (&
 #pragma unroll
       for (int j = 0; j < NACC; ++j)
         if (n0 + col_half * NACC + j < p.N) sq += acc[j] * acc[j];
-      p.rowsq[((int64_t)col_half * p.batch + batch_id) * p.M + gm] += sq;
+      p.rowsq[(((int64_t)(n0 / BN) * TC_ROWSQ_PARTS + col_half) * p.batch + batch_id) * p.M + gm] += sq;
     }
-    if (gm < p.M) {
+    if (gm < p.M && p.C != nullptr) {
 #pragma unroll
       for (int cc = 0; cc < NACC / 32; ++cc) {
         const int c0 = col_half * NACC + cc * 32;
@@ -414,7 +416,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
   const uint32_t tmem_base = *tmem_slot;
 
   // K range of this split
-  const int nkb_total = (p.K + BK - 1) / BK;
+  const int k_eff = p.b_tri_period > 0 ? min(p.K, (((n0 / BN) % p.b_tri_period) + 1) * BN) : p.K;
+  const int nkb_total = (k_eff + BK - 1) / BK;
   const int kb_per = (nkb_total + splits - 1) / splits;
   const int kb_begin = split_id * kb_per;
   const int kb_end = min(nkb_total, kb_begin + kb_per);

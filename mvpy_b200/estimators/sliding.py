@@ -12,7 +12,7 @@ import numpy as np
 import sklearn.base
 import torch
 
-from .. import _graphs, metrics
+from .. import _batched, _graphs, metrics
 
 
 class _Sliding_torch(sklearn.base.BaseEstimator):
@@ -26,6 +26,7 @@ class _Sliding_torch(sklearn.base.BaseEstimator):
         self.verbose = verbose
         self.top = top
         self.estimators_ = None
+        self._stacked = None
 
     # -- helpers --------------------------------------------------------------------------------
     def _moved(self, X: torch.Tensor, y: Optional[torch.Tensor]):
@@ -52,8 +53,15 @@ class _Sliding_torch(sklearn.base.BaseEstimator):
             proto = _Sliding_torch(estimator=self.estimator, dims=eff[1:], n_jobs=None, top=False) if len(self.dims) > 1 \
                 else self.estimator.clone()
             pairs = self._pairs(Xm, ym)
-            # many small identical fits: captured once as a CUDA graph and replayed per slice on concurrent streams
-            fitted = _graphs.fit_slices(proto, Xm, ym, pairs) if (len(self.dims) == 1 and not args) else None
+            # many small identical fits: one batched call for the whole stack (mvb_dense_ridge_batched); shapes it does not
+            # take are captured once as a CUDA graph and replayed per slice on concurrent streams
+            fitted, self._stacked = None, None
+            if len(self.dims) == 1 and not args:
+                got = _batched.fit_slices(proto, Xm, ym, pairs)
+                if got is not None:
+                    fitted, self._stacked = got
+                else:
+                    fitted = _graphs.fit_slices(proto, Xm, ym, pairs)
             self.estimators_ = fitted if fitted is not None else [proto.clone().fit(Xm[..., i], ym[..., j], *args) for i, j in pairs]
         else:
             self.estimators_ = []
@@ -66,6 +74,10 @@ class _Sliding_torch(sklearn.base.BaseEstimator):
             raise ValueError('Estimators not fitted yet.')
         if isinstance(self.estimator, sklearn.base.BaseEstimator):
             Xm = torch.moveaxis(X, self.dims[0], -1)
+            if method == 'predict' and not args and len(self.dims) == 1:
+                yh = _batched.predict_slices(self.estimators_, Xm, getattr(self, '_stacked', None))     # (N, F, slices) in one launch
+                if yh is not None:
+                    return torch.movedim(yh, -1, self.dims[0])
             return torch.stack([getattr(self.estimators_[i], method)(Xm[..., i], *args) for i in range(Xm.shape[-1])], self.dims[0])
         Xm, ym, eff = self._moved(X, y)
         fn = getattr(_Sliding_torch(estimator=self.estimator, dims=eff[1:], n_jobs=None, top=False), method) if len(self.dims) > 1 \

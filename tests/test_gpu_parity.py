@@ -626,6 +626,7 @@ def test_sliding_graph_executor_matches_eager(shape, monkeypatch):
     X = torch.randn(n, p, t, generator=g).cuda()
     y = (torch.einsum('npt,pf->nft', X.cpu(), torch.randn(p, f, generator=g) * 0.1) + torch.randn(n, f, t, generator=g)).cuda()
     al = torch.logspace(-3, 3, 9)
+    monkeypatch.setenv('MVB_SLIDING_BATCHED', '0')           # the batched executor would take these shapes first
     for make in (lambda: mv.estimators.RidgeDecoder(alphas=al), lambda: mv.estimators.RidgeCV(alphas=al, alpha_per_target=False)):
         monkeypatch.setenv('MVB_SLIDING_GRAPHS', '0')
         eager = mv.estimators.Sliding(make(), dims=-1).fit(X, y)
@@ -646,6 +647,103 @@ def test_sliding_graph_executor_matches_eager(shape, monkeypatch):
         np.testing.assert_allclose(again.collect('coef_').cpu().numpy(), eager.collect('coef_').cpu().numpy(), rtol=2e-3, atol=2e-5)
         assert torch.equal(again.collect('alpha_'), eager.collect('alpha_'))
     _graphs.clear_cache()
+
+
+@pytest.mark.parametrize('shape', [(200, 40, 3, 24), (700, 306, 2, 16), (420, 320, 1, 5), (90, 7, 5, 40)])
+def test_dense_ridge_batched_matches_general_route_and_oracle(shape, monkeypatch):
+    """mvb_dense_ridge_batched (one call for all slices of a Sliding fit; replaces the loop sliding.py:575-622 around
+    ridgecv.py:96-303) against (a) the per-slice general route of this library and (b) the fp64 oracle: chosen alphas
+    exact, LOO losses 2e-5 relative (1e-4 when n < 2p), coefficients 1e-4 relative to the largest coefficient, patterns, intercepts and
+    predictions accordingly; per-target and shared alphas, with and without intercept, host inputs, broadcast targets."""
+    from mvpy_b200 import _batched, _lib
+    mv, orc = _mv(), _orc()
+    n, p, f, t = shape
+    g = torch.Generator().manual_seed(100 + p)
+    X = torch.randn(n, p, t, generator=g)
+    y = torch.einsum('npt,pf->nft', X, torch.randn(p, f, generator=g) * 0.1) + torch.randn(n, f, t, generator=g)
+    X = X + 3.0 * torch.randn(1, p, 1, generator=g)              # non-zero column means: the route centres before multiplying
+    al = torch.logspace(-3, 4, 8)
+    ltol = 2e-5 if n >= 2 * p else 1e-4          # n close to p: 1 - leverage is small and fp32 noise in it is amplified
+    calls = {'n': 0}
+    real = _lib.dense_ridge_batched
+
+    def counting(*a, **k):
+        calls['n'] += 1
+        return real(*a, **k)
+    monkeypatch.setattr(_lib, 'dense_ridge_batched', counting)
+    makes = [lambda: mv.estimators.RidgeDecoder(alphas=al),
+             lambda: mv.estimators.RidgeCV(alphas=al, alpha_per_target=False),
+             lambda: mv.estimators.RidgeCV(alphas=al, fit_intercept=False, alpha_per_target=True)]
+    for mi, make in enumerate(makes):
+        monkeypatch.setenv('MVB_SLIDING_BATCHED', '0')
+        monkeypatch.setenv('MVB_SLIDING_GRAPHS', '0')
+        eager = mv.estimators.Sliding(make(), dims=-1).fit(X.cuda(), y.cuda())
+        monkeypatch.setenv('MVB_SLIDING_BATCHED', '1')
+        calls['n'] = 0
+        n0 = _lib.launch_count()
+        batched = mv.estimators.Sliding(make(), dims=-1).fit(X.cuda(), y.cuda())
+        assert calls['n'] == 1 and _lib.launch_count() - n0 < 40                  # the whole stack in one call, < 40 launches
+        assert torch.equal(batched.collect('alpha_'), eager.collect('alpha_')), mi
+        ce, cb = eager.collect('coef_').cpu().numpy(), batched.collect('coef_').cpu().numpy()
+        assert ce.shape == cb.shape == (t, f, p)
+        np.testing.assert_allclose(cb, ce, rtol=0, atol=2e-4 * np.abs(ce).max(), err_msg=f'coef {mi}')     # two fp32 routes: each within 1e-4 of fp64
+        if mi != 2:
+            np.testing.assert_allclose(batched.collect('intercept_').cpu().numpy(), eager.collect('intercept_').cpu().numpy(), rtol=0,
+                                       atol=2e-4 * max(1.0, float(np.abs(eager.collect('intercept_').cpu().numpy()).max())))
+        else:
+            assert batched.estimators_[0].intercept_ == 0.0
+        if mi == 0:
+            pe, pb = eager.collect('pattern_').cpu().numpy(), batched.collect('pattern_').cpu().numpy()
+            np.testing.assert_allclose(pb, pe, rtol=0, atol=2e-4 * np.abs(pe).max(), err_msg='pattern')
+        inner = (lambda e: e.estimator) if mi == 0 else (lambda e: e)
+        le = torch.stack([inner(e).loss_ for e in eager.estimators_]).cpu().numpy()
+        lb = torch.stack([inner(e).loss_ for e in batched.estimators_]).cpu().numpy()
+        np.testing.assert_allclose(lb, le, rtol=2 * ltol, atol=0, err_msg=f'loss {mi}')
+        yh_e, yh_b = eager.predict(X.cuda()), batched.predict(X.cuda())
+        assert yh_b.shape == yh_e.shape == (n, f, t)
+        np.testing.assert_allclose(yh_b.cpu().numpy(), yh_e.cpu().numpy(), rtol=0, atol=2e-4 * float(yh_e.abs().max()))
+        # fp64 oracle on three slices
+        for b in (0, t // 2, t - 1):
+            ref = orc.ridge_loo_fit(X[..., b].double(), y[..., b].double(), al.double(), fit_intercept=(mi != 2), alpha_per_target=(mi != 1))
+            assert torch.equal(inner(batched.estimators_[b]).alpha_.cpu().double().reshape(-1), ref['alpha'].reshape(-1)), (mi, b)
+            np.testing.assert_allclose(inner(batched.estimators_[b]).coef_.cpu().numpy(), ref['coef'].numpy(), rtol=0,
+                                       atol=1e-4 * float(ref['coef'].abs().max()))
+            np.testing.assert_allclose(inner(batched.estimators_[b]).loss_.cpu().numpy(), ref['losses'].numpy(), rtol=ltol)
+    # host tensors in -> host tensors out; a singleton target slice is broadcast over the X slices (sliding.py:606-611)
+    host = mv.estimators.Sliding(mv.estimators.RidgeDecoder(alphas=al), dims=-1).fit(X, y[..., :1])
+    assert host.estimators_[0].coef_.device.type == 'cpu' and host.collect('coef_').shape == (t, f, p)
+    one = mv.estimators.RidgeDecoder(alphas=al).fit(X[..., t - 1].cuda(), y[..., 0].cuda())
+    np.testing.assert_allclose(host.estimators_[t - 1].coef_.numpy(), one.coef_.cpu().numpy(), rtol=0, atol=1e-4 * float(one.coef_.abs().max()))
+    assert host.predict(X).device.type == 'cpu'
+
+
+def test_dense_ridge_batched_hands_rank_deficient_slices_to_the_general_route(monkeypatch):
+    """A slice whose Gram + alpha I is numerically singular at the small alphas (two identical channels) is flagged by the
+    batched factorisation (status != 0) and refitted on the guarded route; the other slices are untouched."""
+    from mvpy_b200 import _lib
+    mv = _mv()
+    g = torch.Generator().manual_seed(9)
+    n, p, f, t = 300, 24, 2, 6
+    X = torch.randn(n, p, t, generator=g)
+    y = torch.einsum('npt,pf->nft', X, torch.randn(p, f, generator=g) * 0.2) + torch.randn(n, f, t, generator=g)
+    X[:, 5, 2] = X[:, 4, 2]                                       # slice 2: duplicated channel
+    al = torch.logspace(-7, 3, 6)
+    res = _lib.dense_ridge_batched(X.cuda(), y.cuda(), None, al.cuda(), True, True)
+    assert res['status'].cpu().tolist() == [0, 0, 1, 0, 0, 0]
+    monkeypatch.setenv('MVB_SLIDING_GRAPHS', '0')
+    batched = mv.estimators.Sliding(mv.estimators.RidgeDecoder(alphas=al), dims=-1).fit(X.cuda(), y.cuda())
+    monkeypatch.setenv('MVB_SLIDING_BATCHED', '0')
+    eager = mv.estimators.Sliding(mv.estimators.RidgeDecoder(alphas=al), dims=-1).fit(X.cuda(), y.cuda())
+    assert torch.equal(batched.collect('alpha_'), eager.collect('alpha_'))
+    np.testing.assert_array_equal(batched.estimators_[2].coef_.cpu().numpy(), eager.estimators_[2].coef_.cpu().numpy())   # same route
+    np.testing.assert_allclose(batched.collect('coef_').cpu().numpy(), eager.collect('coef_').cpu().numpy(), rtol=0, atol=2e-4)
+    np.testing.assert_allclose(batched.predict(X.cuda()).cpu().numpy(), eager.predict(X.cuda()).cpu().numpy(), rtol=0, atol=1e-4)
+    # training subsets through sample_idx (what a driver passes instead of X[train])
+    idx = torch.arange(0, n, 2)
+    sub = _lib.dense_ridge_batched(X.cuda(), y.cuda(), idx.cuda(), al.cuda(), True, True)
+    ref = _lib.dense_ridge_batched(X[idx].cuda(), y[idx].cuda(), None, al.cuda(), True, True)
+    for k in ('coef', 'intercept', 'alpha', 'loss'):
+        assert torch.equal(sub[k], ref[k]), k
 
 
 def test_classification_metrics_golden(golden):
