@@ -256,7 +256,7 @@ def main():
     ap.add_argument('--check-sharded', action='store_true', help='also compute the unsharded hierarchical scores on rank 0 and compare')
     ap.add_argument('--reference-budget', type=float, default=240.0, help='seconds of reference samples (--impl reference)')
     ap.add_argument('--no-reference-cuda', action='store_true', help='--impl reference: skip the device=cuda incumbent')
-    ap.add_argument('--fold-streams', type=int, default=None, help='stream lanes for independent folds (default: MVB_FOLD_STREAMS or 2)')
+    ap.add_argument('--fold-streams', type=int, default=None, help='stream lanes for independent folds (default: MVB_FOLD_STREAMS or 3)')
     ap.add_argument('--profile-steps', type=int, default=1, help='serial steps timed per kernel class for the roofline (after the timed region)')
     args = ap.parse_args()
 

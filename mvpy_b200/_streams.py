@@ -35,7 +35,7 @@ def set_fold_streams(n: Optional[int]) -> None:
 def n_fold_streams() -> int:
     if _n_override is not None:
         return _n_override
-    return max(1, int(os.environ.get('MVB_FOLD_STREAMS', '2')))
+    return max(1, int(os.environ.get('MVB_FOLD_STREAMS', '3')))
 
 
 def _device_lanes(device: torch.device, n: int) -> List['torch.cuda.Stream']:
