@@ -153,7 +153,7 @@ __device__ __forceinline__ void diag_inverse(const float* __restrict__ Lp, int J
 
 __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __restrict__ G, int p, int Pp, const float* __restrict__ alphas,
                                                                 int A, float pivot_tol, float* __restrict__ Li, int tri_rows,
-                                                                int* __restrict__ status) {
+                                                                int* __restrict__ status, long long* __restrict__ phase_clk = nullptr) {
   extern __shared__ __align__(16) float sm[];
   float* Lp = sm;
   float* panel = sm + ((tri(Pp) + 3) & ~3);
@@ -166,6 +166,12 @@ __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __
   const float* Gb = G + (int64_t)b * Pp * Pp;
   if (tid == 0) { s_dmax = 0u; s_bad = 0; }
   __syncthreads();
+  // developer timing (tools/chol_inv_phases.py): cycles of block 0 per phase, [0] load [1] diag factor [2] panel solve
+  // [3] trailing update [4] diag inverse [5] panel product [6] inverse update [7] store
+  long long t_last = phase_clk ? clock64() : 0;
+  auto tick = [&](int ph) {
+    if (phase_clk && prob == 0 && tid == 0) { const long long t = clock64(); phase_clk[ph] += t - t_last; t_last = t; }
+  };
   float dmax = 0.f;
   for (int e = tid; e < Pp * Pp; e += CI_THREADS) {
     const int i = e / Pp, j = e - i * Pp;
@@ -180,6 +186,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __
   if (lane == 0 && dmax > 0.f) atomicMax(&s_dmax, __float_as_uint(dmax));
   __syncthreads();
   const float floor_ = fmaxf(__uint_as_float(s_dmax) * pivot_tol, 1e-30f);
+  tick(0);
 
   // ---- blocked right-looking Cholesky ----
   for (int kb = 0; kb < Pp; kb += NB) {
@@ -203,6 +210,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __
       if (bad && lane == 0) s_bad = 1;
     }
     __syncthreads();
+    tick(1);
     for (int i = kb + NB + tid; i < Pp; i += CI_THREADS) {      // (b) rows below: L[i, panel] = A[i, panel] L_kk^-T
       float* row = Lp + tri(i) + kb;
       float x[NB];
@@ -218,6 +226,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __
       for (int c = 0; c < NB; ++c) row[c] = x[c];
     }
     __syncthreads();
+    tick(2);
     {                                                          // (c) trailing update in 4 x 4 tiles of the lower triangle
       const int base = kb + NB, nt = (Pp - base) / 4, ntiles = tri(nt);
       for (int e = tid; e < ntiles; e += CI_THREADS) {
@@ -253,12 +262,14 @@ __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __
       }
     }
     __syncthreads();
+    tick(3);
   }
 
   // ---- in-place inverse of the triangular factor, block columns from the right ----
   for (int J = Pp - NB; J >= 0; J -= NB) {
     if (warp == 0) diag_inverse(Lp, J, Dinv, lane);
     __syncthreads();
+    tick(4);
     for (int i = J + NB + tid; i < Pp; i += CI_THREADS) {       // panel[i] = L[i, J..J+16) Dinv
       const float* row = Lp + tri(i) + J;
       float l[NB];
@@ -278,6 +289,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __
       if (c <= r) Lp[tri(J + r) + J + c] = Dinv[r * (NB + 1) + c];
     }
     __syncthreads();
+    tick(5);
     {                                                            // Inv[R, J] = -Inv[R, R] panel[R]   (R = rows below the block)
       const int base = J + NB, nrt = (Pp - base) / 4, ntiles = nrt * 4;
       for (int e = tid; e < ntiles; e += CI_THREADS) {
@@ -318,6 +330,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __
       }
     }
     __syncthreads();
+    tick(6);
   }
 
   float* out = Li + (int64_t)prob * tri_rows * Pp;
@@ -325,6 +338,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __
     const int i = e / Pp, j = e - i * Pp;
     out[e] = (i < Pp && j <= i) ? Lp[tri(i) + j] : 0.f;
   }
+  tick(7);
   if (tid == 0 && s_bad) atomicOr(&status[b], 1);
 }
 

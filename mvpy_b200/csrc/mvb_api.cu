@@ -1278,6 +1278,19 @@ int mvb_trf_predict(const mvb_design* d, const void* coef, const void* intercept
 
 int mvb_dense_ridge_batched_max_cols(void) { return mvb::db::MAX_COLS; }
 
+// developer entry (not in include/mvb.h; tools/chol_inv_phases.py): the factorisation kernel alone with per-phase cycle counters
+int mvb_dev_chol_inv(const float* G, int p, int batch, const float* alphas, int n_alphas, float* Li, int* status, long long* phase_clk,
+                     void* stream) {
+  namespace db = mvb::db;
+  const int Pp = (p + db::NB - 1) / db::NB * db::NB, tri_rows = (Pp + db::TRI_TILE - 1) / db::TRI_TILE * db::TRI_TILE;
+  if (p < 1 || p > db::MAX_COLS) return fail(MVB_E_ARG, "dev_chol_inv: p");
+  MVB_CUDA(cudaFuncSetAttribute(db::chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)db::chol_inv_smem(db::MAX_COLS)));
+  db::chol_inv_kernel<<<batch * n_alphas, db::CI_THREADS, db::chol_inv_smem(Pp), (cudaStream_t)stream>>>(G, p, Pp, alphas, n_alphas, 1e-4f, Li, tri_rows,
+                                                                                                     status, phase_clk);
+  MVB_LAUNCHED();
+  return MVB_OK;
+}
+
 size_t mvb_dense_ridge_batched_workspace_bytes(int batch, int n_samples, int n_cols, int n_targets, int n_alphas) {
   if (!dense_batched_ok(batch, n_samples, n_cols, n_targets, n_alphas) || batch > 65535) return 0;
   Arena ar(nullptr, 0);
