@@ -130,25 +130,92 @@ __global__ void xty_kernel(const float* __restrict__ Xc, const float* __restrict
 
 // One CTA per (slice b, alpha a): M = G_b + alpha I (padding rows: identity) -> L (Cholesky) -> L^-1, written as a full
 // [tri_rows][Pp] block (zeros above the diagonal and in the rows beyond Pp) for the leverage product.
-// Shared memory: packed lower triangle (row i at tri(i)), one [Pp][16] panel, one 16 x 17 diagonal-block inverse.
+// Shared memory: the packed lower triangle (row i at tri(i)) + a [16][Pp] k-major copy of the current panel + the 16 x 17
+// inverse of the current diagonal block.  What the phases cost was measured with the counters below (tools/chol_inv_phases.py);
+// the layout choices follow from it:
+//   * 16 x 16 diagonal blocks are factored / inverted in the registers of one warp (lane = row, values exchanged by shuffles):
+//     the same steps on shared memory were 27 % of the kernel;
+//   * the trailing update reads the panel from the k-major copy -- for one k the 8 rows of a tile are two 16-byte loads and the
+//     lanes of a warp (consecutive column pairs of one row group) read consecutive 8-byte words, no bank conflicts -- instead
+//     of from the packed rows, whose start offsets tri(i) scatter the lanes over the banks (3-way conflicts, 26 %);
+//   * the inverse's block-column update splits every tile's k range over 4 adjacent lanes (all 512 threads busy instead of
+//     m <= 304 with trip counts up to m).
 inline size_t chol_inv_smem(int Pp) { return ((size_t)((tri(Pp) + 3) & ~3) + (size_t)Pp * NB + NB * (NB + 1)) * 4; }
 
-__device__ __forceinline__ void diag_inverse(const float* __restrict__ Lp, int J, float* __restrict__ Dinv, int lane) {
-  // inverse of the lower-triangular 16 x 16 diagonal block at J: lane c < 16 solves column c by forward substitution
-  if (lane < NB) {
-    const int c = lane;
-    float x[NB];
+// lane r (mod 16) loads row r of the 16 x 16 lower-triangular diagonal block at J into registers
+__device__ __forceinline__ void diag_load(const float* __restrict__ Lp, int J, int r, float (&row)[NB]) {
 #pragma unroll
-    for (int i = 0; i < NB; ++i) {
-      float v = (i == c) ? 1.f : 0.f;
+  for (int c = 0; c < NB; ++c) row[c] = (c <= r) ? Lp[tri(J + r) + J + c] : 0.f;
+}
+
+// in-register Cholesky of the diagonal block: on exit lane r holds row r of L.  Returns true when a pivot of a real
+// (non-padding) row was not above floor_.
+__device__ __forceinline__ bool diag_factor(float (&row)[NB], int r, int n_real, float floor_) {
+  bool bad = false;
 #pragma unroll
-      for (int k = 0; k < NB; ++k)
-        if (k < i && k >= c) v -= Lp[tri(J + i) + J + k] * x[k];
-      x[i] = (i < c) ? 0.f : v / Lp[tri(J + i) + J + i];
+  for (int k = 0; k < NB; ++k) {
+    float piv = __shfl_sync(0xffffffffu, row[k], k);
+    if (k < n_real && !(piv > floor_)) { bad = true; piv = floor_; }      // (padding rows are an identity block: pivot 1)
+    // 1 / sqrt(piv) from the special-function unit + one Newton step (full fp32 accuracy): the precise sqrtf and division
+    // are ~80 dependent instructions per column on the one warp that works here
+    float is = rsqrtf(piv);
+    is = is * (1.5f - 0.5f * piv * is * is);
+    if (r == k) row[k] = piv * is;
+    else if (r > k) row[k] = row[k] * is;
+    const float lrk = row[k];
+#pragma unroll
+    for (int c = k + 1; c < NB; ++c) {
+      const float lck = __shfl_sync(0xffffffffu, row[k], c);              // L[c][k], scaled just above by lane c
+      if (r >= c) row[c] -= lrk * lck;
     }
+  }
+  return bad;
+}
+
+// inverse of the lower-triangular block held row-wise in registers: lane c (mod 16) solves column c by forward substitution
+// (L[i][k] comes from lane i by shuffle) and writes it to Dinv[i][c]
+__device__ __forceinline__ void diag_invert(const float (&row)[NB], int lane, float* __restrict__ Dinv) {
+  const int c = lane & (NB - 1);
+  float x[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    float v = (i == c) ? 1.f : 0.f;
+#pragma unroll
+    for (int k = 0; k < NB; ++k)
+      if (k < i) {
+        const float lik = __shfl_sync(0xffffffffu, row[k], i);
+        if (k >= c) v -= lik * x[k];
+      }
+    const float lii = __shfl_sync(0xffffffffu, row[i], i);
+    x[i] = (i < c) ? 0.f : v * __frcp_rn(lii);
+  }
+  if (lane < NB) {
 #pragma unroll
     for (int i = 0; i < NB; ++i) Dinv[i * (NB + 1) + c] = x[i];
   }
+}
+
+// The two warp-level steps as separate (not inlined) functions: inlined into the 128-register kernel the compiler kept the
+// 16-value row in local memory (304 LDL / STL, 12 000 cycles per block instead of ~1 500; cuobjdump -sass).
+__device__ __noinline__ bool diag_block_factor(float* __restrict__ Lp, int kb, int n_real, float floor_, float* __restrict__ rdiag, int lane) {
+  const int r = lane & (NB - 1);
+  float row[NB];
+  diag_load(Lp, kb, r, row);
+  const bool bad = diag_factor(row, r, n_real, floor_);
+  if (lane < NB) {
+#pragma unroll
+    for (int c = 0; c < NB; ++c)
+      if (c <= r) Lp[tri(kb + r) + kb + c] = row[c];
+#pragma unroll
+    for (int c = 0; c < NB; ++c)
+      if (c == r) rdiag[c] = __frcp_rn(row[c]);               // reciprocal diagonal for the panel solve
+  }
+  return bad;
+}
+__device__ __noinline__ void diag_block_invert(const float* __restrict__ Lp, int J, float* __restrict__ Dinv, int lane) {
+  float row[NB];
+  diag_load(Lp, J, lane & (NB - 1), row);
+  diag_invert(row, lane, Dinv);
 }
 
 __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __restrict__ G, int p, int Pp, const float* __restrict__ alphas,
@@ -156,8 +223,8 @@ __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __
                                                                 int* __restrict__ status, long long* __restrict__ phase_clk = nullptr) {
   extern __shared__ __align__(16) float sm[];
   float* Lp = sm;
-  float* panel = sm + ((tri(Pp) + 3) & ~3);
-  float* Dinv = panel + Pp * NB;
+  float* panelT = sm + ((tri(Pp) + 3) & ~3);       // [16][Pp]: panelT[k * Pp + i] = panel entry (row base + i, column k)
+  float* Dinv = panelT + Pp * NB;
   __shared__ unsigned int s_dmax;
   __shared__ int s_bad;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -173,10 +240,9 @@ __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __
     if (phase_clk && prob == 0 && tid == 0) { const long long t = clock64(); phase_clk[ph] += t - t_last; t_last = t; }
   };
   float dmax = 0.f;
-  for (int e = tid; e < Pp * Pp; e += CI_THREADS) {
-    const int i = e / Pp, j = e - i * Pp;
-    if (j <= i) {
-      float v = (i < p) ? Gb[e] : 0.f;
+  for (int i = warp; i < Pp; i += CI_THREADS / 32) {          // one warp per row of the lower triangle
+    for (int j = lane; j <= i; j += 32) {
+      float v = (i < p) ? Gb[(int64_t)i * Pp + j] : 0.f;
       if (i == j) { v = (i < p) ? v + alpha : 1.f; if (i < p) dmax = fmaxf(dmax, v); }
       Lp[tri(i) + j] = v;
     }
@@ -190,28 +256,14 @@ __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __
 
   // ---- blocked right-looking Cholesky ----
   for (int kb = 0; kb < Pp; kb += NB) {
-    if (warp == 0) {                               // (a) the 16 x 16 diagonal block: lane r owns row kb + r
-      const int r = lane;
-      bool bad = false;
-      for (int k = 0; k < NB; ++k) {
-        float piv = Lp[tri(kb + k) + kb + k];
-        if (kb + k < p && !(piv > floor_)) { bad = true; piv = floor_; }      // (padding rows are an identity block: pivot 1)
-        const float d = sqrtf(piv);
-        __syncwarp();
-        if (r == k) Lp[tri(kb + k) + kb + k] = d;
-        if (r > k && r < NB) Lp[tri(kb + r) + kb + k] /= d;
-        __syncwarp();
-        if (r > k && r < NB) {
-          const float lrk = Lp[tri(kb + r) + kb + k];
-          for (int c = k + 1; c <= r; ++c) Lp[tri(kb + r) + kb + c] -= lrk * Lp[tri(kb + c) + kb + k];
-        }
-        __syncwarp();
-      }
+    if (warp == 0) {                               // (a) the 16 x 16 diagonal block, in registers
+      const bool bad = diag_block_factor(Lp, kb, p - kb, floor_, Dinv, lane);
       if (bad && lane == 0) s_bad = 1;
     }
     __syncthreads();
     tick(1);
-    for (int i = kb + NB + tid; i < Pp; i += CI_THREADS) {      // (b) rows below: L[i, panel] = A[i, panel] L_kk^-T
+    const int base = kb + NB, m = Pp - base;
+    for (int i = base + tid; i < Pp; i += CI_THREADS) {         // (b) rows below: L[i, panel] = A[i, panel] L_kk^-T
       float* row = Lp + tri(i) + kb;
       float x[NB];
 #pragma unroll
@@ -220,45 +272,39 @@ __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __
 #pragma unroll
         for (int k = 0; k < NB; ++k)
           if (k < c) v -= x[k] * Lp[tri(kb + c) + kb + k];
-        x[c] = v / Lp[tri(kb + c) + kb + c];
+        x[c] = v * Dinv[c];
       }
 #pragma unroll
-      for (int c = 0; c < NB; ++c) row[c] = x[c];
+      for (int c = 0; c < NB; ++c) { row[c] = x[c]; panelT[c * Pp + (i - base)] = x[c]; }
     }
     __syncthreads();
     tick(2);
-    {                                                          // (c) trailing update in 4 x 4 tiles of the lower triangle
-      const int base = kb + NB, nt = (Pp - base) / 4, ntiles = tri(nt);
+    {                                                          // (c) trailing update, 8 x 2 register tiles of the lower triangle
+      const int nrg = m / 8, ntiles = 2 * nrg * (nrg + 1);     // row group ti (8 rows) has 4 (ti + 1) column pairs
       for (int e = tid; e < ntiles; e += CI_THREADS) {
-        int ti = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
-        while (tri(ti + 1) <= e) ++ti;
-        while (tri(ti) > e) --ti;
-        const int tj = e - tri(ti);
-        const int i0 = base + 4 * ti, j0 = base + 4 * tj;
-        float acc[4][4];
+        int ti = (int)((sqrtf(2.f * (float)e + 1.f) - 1.f) * 0.5f);
+        while (2 * (ti + 1) * (ti + 2) <= e) ++ti;
+        while (2 * ti * (ti + 1) > e) --ti;
+        const int tj = e - 2 * ti * (ti + 1);
+        const int i0 = 8 * ti, j0 = 2 * tj;                    // relative to base
+        float acc[8][2];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-        const float* ra[4];
-        const float* rb[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) { ra[r] = Lp + tri(i0 + r) + kb; rb[r] = Lp + tri(j0 + r) + kb; }
+        for (int r = 0; r < 8; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
 #pragma unroll
         for (int k = 0; k < NB; ++k) {
-          float av[4], bv[4];
+          const float4 a0 = *reinterpret_cast<const float4*>(panelT + k * Pp + i0);
+          const float4 a1 = *reinterpret_cast<const float4*>(panelT + k * Pp + i0 + 4);
+          const float2 bv = *reinterpret_cast<const float2*>(panelT + k * Pp + j0);
+          const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-          for (int r = 0; r < 4; ++r) { av[r] = ra[r][k]; bv[r] = rb[r][k]; }
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c] += av[r] * bv[c];
+          for (int r = 0; r < 8; ++r) { acc[r][0] += av[r] * bv.x; acc[r][1] += av[r] * bv.y; }
         }
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (j0 + c <= i0 + r) Lp[tri(i0 + r) + j0 + c] -= acc[r][c];
+        for (int r = 0; r < 8; ++r) {
+          float* dst = Lp + tri(base + i0 + r) + base + j0;
+          if (j0 <= i0 + r) dst[0] -= acc[r][0];
+          if (j0 + 1 <= i0 + r) dst[1] -= acc[r][1];
+        }
       }
     }
     __syncthreads();
@@ -267,10 +313,12 @@ __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __
 
   // ---- in-place inverse of the triangular factor, block columns from the right ----
   for (int J = Pp - NB; J >= 0; J -= NB) {
-    if (warp == 0) diag_inverse(Lp, J, Dinv, lane);
+    if (warp == 0) diag_block_invert(Lp, J, Dinv, lane);
     __syncthreads();
     tick(4);
-    for (int i = J + NB + tid; i < Pp; i += CI_THREADS) {       // panel[i] = L[i, J..J+16) Dinv
+    const int base = J + NB, m = Pp - base;
+    float* panel = panelT;                                       // here row-major [m][16]: panel[(i - base) * 16 + c]
+    for (int i = base + tid; i < Pp; i += CI_THREADS) {          // panel[i] = L[i, J..J+16) Dinv
       const float* row = Lp + tri(i) + J;
       float l[NB];
 #pragma unroll
@@ -281,7 +329,7 @@ __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __
 #pragma unroll
         for (int k = 0; k < NB; ++k)
           if (k >= c) v += l[k] * Dinv[k * (NB + 1) + c];
-        panel[i * NB + c] = v;
+        panel[(i - base) * NB + c] = v;
       }
     }
     if (tid < NB * NB) {                                         // the diagonal block itself
@@ -291,42 +339,55 @@ __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __
     __syncthreads();
     tick(5);
     {                                                            // Inv[R, J] = -Inv[R, R] panel[R]   (R = rows below the block)
-      const int base = J + NB, nrt = (Pp - base) / 4, ntiles = nrt * 4;
-      for (int e = tid; e < ntiles; e += CI_THREADS) {
-        // long rows first: tile e -> row group from the bottom, so that the threads of a warp have similar trip counts
-        const int ti = nrt - 1 - e / 4, c0 = (e & 3) * 4;
-        const int i0 = base + 4 * ti;
+      // tile = 4 rows x 4 of the 16 columns; its k range is split over 4 adjacent lanes (k = q mod 4) and summed by shuffles
+      const int nrt = m / 4, total = nrt * 4 * 4;
+      for (int wb = 0; wb < total; wb += CI_THREADS) {
+        const int w = wb + tid;
+        const bool valid = w < total;
+        const int t = valid ? (w >> 2) : 0, q = w & 3;
+        const int ti = nrt - 1 - (t >> 2), c0 = (t & 3) * 4;     // long rows first
+        const int i0 = 4 * ti;                                   // relative to base
         float acc[4][4];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
           for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-        const float* ra[4];
+        if (valid) {
+          const float* ra[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) ra[r] = Lp + tri(i0 + r);
-        for (int k = base; k < i0; ++k) {                        // full part: k below the tile's first row
-          const float4 t = *reinterpret_cast<const float4*>(panel + k * NB + c0);
+          for (int r = 0; r < 4; ++r) ra[r] = Lp + tri(base + i0 + r) + base;
+          for (int k = q; k < i0; k += 4) {                      // full part: k below the tile's first row
+            const float4 tv = *reinterpret_cast<const float4*>(panel + k * NB + c0);
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const float av = ra[r][k];
-            acc[r][0] += av * t.x; acc[r][1] += av * t.y; acc[r][2] += av * t.z; acc[r][3] += av * t.w;
-          }
-        }
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {                         // triangular corner
-          const int k = i0 + kk;
-          const float4 t = *reinterpret_cast<const float4*>(panel + k * NB + c0);
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-            if (kk <= r) {
+            for (int r = 0; r < 4; ++r) {
               const float av = ra[r][k];
-              acc[r][0] += av * t.x; acc[r][1] += av * t.y; acc[r][2] += av * t.z; acc[r][3] += av * t.w;
+              acc[r][0] += av * tv.x; acc[r][1] += av * tv.y; acc[r][2] += av * tv.z; acc[r][3] += av * tv.w;
             }
+          }
+          {                                                      // triangular corner: lane q takes k = i0 + q
+            const int k = i0 + q;
+            const float4 tv = *reinterpret_cast<const float4*>(panel + k * NB + c0);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              if (q <= r) {
+                const float av = ra[r][k];
+                acc[r][0] += av * tv.x; acc[r][1] += av * tv.y; acc[r][2] += av * tv.z; acc[r][3] += av * tv.w;
+              }
+          }
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) Lp[tri(i0 + r) + J + c0 + c] = -acc[r][c];
+          for (int c = 0; c < 4; ++c) {
+            acc[r][c] += __shfl_xor_sync(0xffffffffu, acc[r][c], 1);
+            acc[r][c] += __shfl_xor_sync(0xffffffffu, acc[r][c], 2);
+          }
+        if (valid) {                                             // lane q writes row q of the tile
+          float* dst = Lp + tri(base + i0 + q) + J + c0;
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            if (r == q) { dst[0] = -acc[r][0]; dst[1] = -acc[r][1]; dst[2] = -acc[r][2]; dst[3] = -acc[r][3]; }
+        }
       }
     }
     __syncthreads();

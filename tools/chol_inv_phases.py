@@ -18,7 +18,7 @@ G = torch.bmm(X.transpose(1, 2), X).contiguous()
 al = torch.logspace(-5, 5, A).cuda()
 Li = torch.empty(B * A, tri_rows, Pp, device='cuda')
 status = torch.zeros(B, dtype=torch.int32, device='cuda')
-clk = torch.zeros(8, dtype=torch.int64, device='cuda')
+clk = torch.zeros(12, dtype=torch.int64, device='cuda')
 st = torch.cuda.current_stream().cuda_stream
 for it in range(3):
     clk.zero_()
@@ -28,7 +28,7 @@ for it in range(3):
     e1.record(); torch.cuda.synchronize()
     assert rc == 0, lib.mvb_last_error()
     print(f'chol_inv {B * A} problems p={p}: {e0.elapsed_time(e1):.2f} ms')
-names = ['load', 'diag factor', 'panel solve', 'trailing update', 'diag inverse', 'panel product', 'inverse update', 'store']
+names = ['load', 'diag factor (rest: sync)', 'panel solve', 'trailing update', 'diag inverse', 'panel product', 'inverse update', 'store', '  diag: load', '  diag: factor', '  diag: write-back', '-']
 c = clk.cpu().tolist()
 for nm, v in zip(names, c):
     print(f'  {nm:16s} {v:9d} cycles  {100.0 * v / max(1, sum(c)):5.1f} %')
