@@ -548,7 +548,7 @@ def main():
         roof = dict(bound='tensor', kernel='tg::toeplitz_gram_kernel + tc::tc_gemm_ta_kernel + tc::tc_gemm_kernel + sc::sweep_chain_tmem_kernel '
                                            '(all contraction launches of the step)', achieved=achieved,
                     peak=peak_eff, unit='TFLOP/s', frac=achieved / peak_eff, traffic=None, launches=tot_n, ms_total=tot_ms,
-                    share_of_step=tot_ms / (ms if lanes == 1 else prof_ms), peak_source=peak_src,
+                    share_of_step=tot_ms / (ms if lanes == 1 else prof_ms), profile_steps=prof_steps, peak_source=peak_src,
                     measured_in=('the timed region' if lanes == 1 else
                                  f'{prof_steps} step(s) with the folds serialised on one stream ({prof_ms / prof_steps:.1f} ms/step), run right after the '
                                  f'timed region; in the timed region folds overlap on {lanes} stream lanes'),

@@ -27,14 +27,26 @@ from .kfold import KFold
 
 def _move_tensors(obj: Any, device: torch.device, _seen=None) -> Any:
     """Return ``obj`` with every tensor reachable from it (estimator attributes, pipeline steps, lists,
-    dicts, metric metadata) moved to ``device``; estimators are updated in place."""
+    dicts, metric metadata) moved to ``device``; estimators are updated in place.  Views of one base tensor (the per-slice
+    attributes of a batched ``Sliding`` fit are rows of a few stacked arrays) move with ONE copy of the base and stay views."""
     if _seen is None:
-        _seen = set()
+        _seen = {'ids': set(), 'bases': {}}
     if isinstance(obj, torch.Tensor):
-        return obj.to(device)
-    if obj is None or isinstance(obj, (int, float, str, bool)) or id(obj) in _seen:
+        base = obj._base
+        if base is None or obj.device == device or obj.requires_grad or base.numel() * base.element_size() > (256 << 20):
+            return obj.to(device)
+        key = (id(base), base.data_ptr())
+        moved = _seen['bases'].get(key)
+        if moved is None:
+            moved = base.to(device)
+            _seen['bases'][key] = moved
+            _seen.setdefault('keep', []).append(base)           # keeps id(base) unique while the cache lives
+        if moved.stride() != base.stride():
+            return obj.to(device)
+        return moved.as_strided(obj.size(), obj.stride(), obj.storage_offset() - base.storage_offset() + moved.storage_offset())
+    if obj is None or isinstance(obj, (int, float, str, bool)) or id(obj) in _seen['ids']:
         return obj
-    _seen.add(id(obj))
+    _seen['ids'].add(id(obj))
     if isinstance(obj, list):
         for i, o in enumerate(obj):
             obj[i] = _move_tensors(o, device, _seen)
@@ -156,7 +168,11 @@ class Validator(sklearn.base.BaseEstimator):
 
         def one(k: int):
             train, test = folds[k]
-            return fit_model_(self.model, train.to(Xd.device), test.to(Xd.device), Xd, y=yd, metric=self.metric, train_key=keys.get(k))
+            r = fit_model_(self.model, train.to(Xd.device), test.to(Xd.device), Xd, y=yd, metric=self.metric, train_key=keys.get(k))
+            # host inputs: the fitted model goes back to the input's device here, i.e. on this fold's lane, so that its
+            # device-to-host copies overlap the other folds' kernels
+            r['model'], r['metric'] = _move_tensors(r['model'], out_dev), _move_tensors(r['metric'], out_dev)
+            return r
         with _dist.sharded_region():           # process-wide depth counter: held by this thread while the lanes work
             # large fits leave SMs idle inside their launch chains: folds go to a few stream lanes (fold k always on lane k mod n)
             if Xd.is_cuda and _lanes_ok(self.model):
@@ -172,8 +188,8 @@ class Validator(sklearn.base.BaseEstimator):
                 self.metric_.append(None)
                 continue
             local_scores[k] = r['score_']
-            self.model_.append(_move_tensors(r['model'], out_dev))
-            self.metric_.append(_move_tensors(r['metric'], out_dev))
+            self.model_.append(r['model'])
+            self.metric_.append(r['metric'])
         if self._multi():
             self.score_ = {}
             for m in self.metric:

@@ -1022,14 +1022,13 @@ int dense_ridge_batched_impl(const mvb_strided* X, const mvb_strided* Y, const i
   db::chol_inv_kernel<<<B * A, db::CI_THREADS, db::chol_inv_smem(Pp), st>>>(w.G, p, Pp, alphas, A, 1e-4f, w.Li, w.tri_rows, status);
   MVB_LAUNCHED();
   // 4. leverages: row squares of Xc_b [L_a^-1]^T for the stack of all alphas (nothing but the squares is stored)
-  MVB_CUDA(cudaMemsetAsync(w.rowsq, 0, (size_t)A * w.tiles_per_alpha * mvb::TC_ROWSQ_PARTS * B * n * sizeof(float), st));
   {
     mvb::TcGemmParams g = mvb::tc_gemm_defaults();
     g.A = {w.Xc, w.roffX, w.iota, n, 2};
     g.B = {w.Li, w.roffLi, w.iota, A * w.tri_rows, 2};
     g.M = n; g.N = A * w.tri_rows; g.K = Pp; g.C = nullptr; g.ldc = 0; g.batch = B;
     g.a_roff_batch = n; g.b_roff_batch = (int64_t)A * w.tri_rows;
-    g.rowsq = w.rowsq; g.b_tri_period = w.tiles_per_alpha;
+    g.rowsq = w.rowsq; g.rowsq_assign = 1; g.b_tri_period = w.tiles_per_alpha;      // every (tile, part, slice, row) entry is written once
     // flops counted for the triangular half actually contracted
     double kk = 0;
     for (int t = 0; t < w.tiles_per_alpha; ++t) kk += std::min(Pp, (t + 1) * db::TRI_TILE);

@@ -63,6 +63,7 @@ struct TcGemmParams {
   int64_t c_block_stride;             //      elements between consecutive column blocks (>= M * c_block_cols)
   float* rowsq;                       // optional [N tiles][TC_ROWSQ_PARTS][batch][M]: += sum over this thread's columns of C[m][n]^2
                                       // (split-K not allowed); C may be nullptr when only the row squares are wanted
+  int rowsq_assign;                   // 1: rowsq entries are written (=) instead of accumulated (+=): every entry is produced once
   int b_tri_period;                   // > 0: B is a stack of lower-triangular blocks (B[n][k] = 0 for k > n mod period*BN), `period`
                                       //      N tiles each: tile t contracts only k < ((t mod period) + 1) * BN  (batch kernel only)
   // ---- pre-split B operand (256-wide tiles only, batch == 1) ----
@@ -328,7 +329,8 @@ __device__ __forceinline__ void store_tile(const TcGemmParams& p, const float (&
 #pragma unroll
       for (int j = 0; j < NACC; ++j)
         if (n0 + col_half * NACC + j < p.N) sq += acc[j] * acc[j];
-      p.rowsq[(((int64_t)(n0 / BN) * TC_ROWSQ_PARTS + col_half) * p.batch + batch_id) * p.M + gm] += sq;
+      float* dst = p.rowsq + (((int64_t)(n0 / BN) * TC_ROWSQ_PARTS + col_half) * p.batch + batch_id) * p.M + gm;
+      if (p.rowsq_assign) *dst = sq; else *dst += sq;
     }
     if (gm < p.M && p.C != nullptr) {
 #pragma unroll
