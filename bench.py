@@ -552,6 +552,14 @@ def main():
                     measured_in=('the timed region' if lanes == 1 else
                                  f'{prof_steps} step(s) with the folds serialised on one stream ({prof_ms / prof_steps:.1f} ms/step), run right after the '
                                  f'timed region; in the timed region folds overlap on {lanes} stream lanes'),
+                    survey_nominal=(None if args.workload not in ('cfg1', 'cfg2') else (lambda n_, p_, F_, nte_: dict(
+                        flops_per_fold=n_ * p_ * (p_ + 1) + 2 * n_ * p_ * F_ + 2 * n_ * p_ * p_ + 2 * n_ * p_ * F_ * N_ALPHAS + 9 * p_ ** 3 + 2 * nte_ * p_ * F_,
+                        achieved=(n_ * p_ * (p_ + 1) + 2 * n_ * p_ * F_ + 2 * n_ * p_ * p_ + 2 * n_ * p_ * F_ * N_ALPHAS + 9 * p_ ** 3 + 2 * nte_ * p_ * F_)
+                        * N_FOLDS / (ms_per_step * 1e-3) * 1e-12,
+                        note='SURVEY 8(d) nominal work of the reference formulation per fold (Gram + X^T y + leverages + residuals + 9 p^3 '
+                             'eigensolve + predict) x folds / step time of the timed region: what the step delivers in units of the '
+                             'formulation it replaces (the displacement-structure Gram and the band reduction do less arithmetic than that)'))(
+                        (X.shape[0] - X.shape[0] // N_FOLDS) * X.shape[2], X.shape[1] * 201, y.shape[1], (X.shape[0] // N_FOLDS) * X.shape[2])),
                     whole_step=dict(achieved=tot_fl / prof_steps / (ms_per_step * 1e-3) * 1e-12,
                                     frac=tot_fl / prof_steps / (ms_per_step * 1e-3) * 1e-12 / peak_eff,
                                     note='algorithmic flops of all contraction launches of one step / the step time of the timed region '
