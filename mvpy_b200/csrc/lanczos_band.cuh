@@ -40,6 +40,7 @@ struct Plan {
   // pre-split TF32 planes (tc_gemm.cuh, TcGemmParams::b_planes) of the three dense B operands of the big products:
   // Gp (filled once), Qt and Q^T (extended by one block per step); 0 bytes for small problems
   size_t off_plG, off_plQt, off_plQc, planes_bytes;
+  bool planes_raw;         // planes hold the raw fp32 values (4 B per entry; TcGemmParams::b_planes_raw) instead of hi / lo pairs
 };
 
 inline Plan make_plan(int p) {
@@ -68,7 +69,11 @@ inline Plan make_plan(int p) {
   pl.off_part = take(pl.part_elems * 4);
   pl.off_ctl = take(sizeof(bj::Ctl));
   static const bool planes_on = [] { const char* e = getenv("MVB_LB_PLANES"); return !e || atoi(e) != 0; }();
-  pl.planes_bytes = (planes_on && pl.P >= 2048) ? tc_planes_bytes(pl.P, pl.P) : 0;
+  // the big products of a step stream their B operand from HBM once against a single 128-row tile, i.e. they are bound by the
+  // plane bytes: single raw planes halve them (MVB_LB_RAW_PLANES=0: hi / lo pairs as in r01)
+  static const bool raw_on = [] { const char* e = getenv("MVB_LB_RAW_PLANES"); return e && atoi(e) != 0; }();
+  pl.planes_raw = raw_on;
+  pl.planes_bytes = (planes_on && pl.P >= 2048) ? tc_planes_bytes(pl.P, pl.P, raw_on) : 0;
   pl.off_plG = take(pl.planes_bytes);
   pl.off_plQt = take(pl.planes_bytes);
   pl.off_plQc = take(pl.planes_bytes);
@@ -395,7 +400,11 @@ inline bool gemm(Ctx& cx, const GatherOperand& A, const GatherOperand& B, int M,
   const int splits = tc_choose_splits(tiles, (K + tc::BK - 1) / tc::BK, max_splits, (int64_t)M * N);
   TcGemmParams g = tc_gemm_defaults();
   g.A = A; g.B = B; g.M = M; g.N = N; g.K = K; g.skip_flag = skip;
-  if (b_planes && bn == 256) { g.b_planes = b_planes; g.b_planes_nkb = (cx.pl.P + tc::BK - 1) / tc::BK; }
+  if (b_planes && bn == 256) {
+    g.b_planes = b_planes; g.b_planes_nkb = (cx.pl.P + tc::BK - 1) / tc::BK; g.b_planes_raw = cx.pl.planes_raw ? 1 : 0;
+    static const bool hint_on = [] { const char* e = getenv("MVB_LB_STREAM_HINTS"); return !e || atoi(e) != 0; }();
+    g.b_stream_once = (hint_on && M <= 128) ? 1 : 0;      // one M tile: B streams once, the 128-row A block is what every CTA re-reads
+  }
   const bool via_parts = splits > 1 || subtract;      // C -= A B^T always goes through the partial-sum buffer
   if (via_parts) { g.C = cx.f(cx.pl.off_part); g.ldc = N; g.c_split_stride = (int64_t)M * N; }
   else { g.C = C; g.ldc = ldc; }
@@ -501,7 +510,7 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
   if (pl.planes_bytes) {
     plG = (uint8_t*)(cx.base + pl.off_plG); plQt = (uint8_t*)(cx.base + pl.off_plQt); plQc = (uint8_t*)(cx.base + pl.off_plQc);
     GatherOperand g_all{Gp, rowP, iota, P, 2};
-    LB_CK(tc_presplit_launch(g_all, P, plG, st)); ++cx.launches;
+    LB_CK(tc_presplit_launch(g_all, P, plG, st, 0, -1, 0, -1, pl.planes_raw)); ++cx.launches;
     LB_CK(cudaMemsetAsync(plQt, 0, pl.planes_bytes, st));       // blocks arrive one per step; rows / stages not yet there read as zero
     LB_CK(cudaMemsetAsync(plQc, 0, pl.planes_bytes, st));
   }
@@ -515,8 +524,8 @@ inline int reduce(const float* G, int p, float* Qt, float* Tdiag, float* Tsub, v
     transpose_block_kernel<<<dim3(P / 32, NB / 32), dim3(32, 8), 0, st>>>(Qj, P, j * NB, cx.f(pl.off_Qc)); ++cx.launches;   // block j is final
     if (pl.planes_bytes) {        // ... and joins the pre-split copies of Qt (128 new rows) and Q^T (128 new contraction columns)
       GatherOperand qt_all{Qt, rowP, iota, P, 2}, qc_all{cx.f(pl.off_Qc), rowP, iota, P, 2};
-      LB_CK(tc_presplit_launch(qt_all, P, plQt, st, j * NB, (j + 1) * NB, 0, -1)); ++cx.launches;
-      LB_CK(tc_presplit_launch(qc_all, P, plQc, st, 0, P, j * (NB / tc::BK), (j + 1) * (NB / tc::BK))); ++cx.launches;
+      LB_CK(tc_presplit_launch(qt_all, P, plQt, st, j * NB, (j + 1) * NB, 0, -1, pl.planes_raw)); ++cx.launches;
+      LB_CK(tc_presplit_launch(qc_all, P, plQc, st, 0, P, j * (NB / tc::BK), (j + 1) * (NB / tc::BK), pl.planes_raw)); ++cx.launches;
     }
     // W = Q_j Gp ;  H = W Q_{0..j}^T  -> T_jj, T_{j,j-1}
     GatherOperand qj{Qj, rowP, iota, NB, 2}, g{Gp, rowP, iota, P, 2};

@@ -1277,6 +1277,23 @@ int mvb_trf_predict(const mvb_design* d, const void* coef, const void* intercept
 
 int mvb_dense_ridge_batched_max_cols(void) { return mvb::db::MAX_COLS; }
 
+// developer entry (not in include/mvb.h; tools/skinny_time.py): one skinny Lanczos-shaped product C (128 x N) = A (128 x K) B (N x K)^T on the
+// TMEM-A kernel with B as pre-split planes.  planes must hold tc_planes_bytes(N, K, raw); part: [splits][128][N] floats; tables: rowK[max(N,128)]
+// = i * K, iota[K].  mode bit 0: raw single planes, bit 1: stream-once cache hints.
+int mvb_dev_skinny(const float* A, const float* B, int N, int K, int splits, int mode, void* planes, float* part, const int64_t* rowK,
+                   const int64_t* iota, int presplit, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  mvb::GatherOperand a{A, rowK, iota, 128, 2}, b{B, rowK, iota, N, 2};
+  const bool raw = mode & 1;
+  if (presplit) { MVB_CUDA(mvb::tc_presplit_launch(b, K, (uint8_t*)planes, st, 0, -1, 0, -1, raw)); return MVB_OK; }
+  mvb::TcGemmParams g = mvb::tc_gemm_defaults();
+  g.A = a; g.B = b; g.M = 128; g.N = N; g.K = K; g.C = part; g.ldc = N; g.c_split_stride = (int64_t)128 * N;
+  g.b_planes = (const uint8_t*)planes; g.b_planes_nkb = (K + mvb::tc::BK - 1) / mvb::tc::BK; g.b_planes_raw = raw ? 1 : 0;
+  g.b_stream_once = (mode & 2) ? 1 : 0;
+  MVB_CUDA(mvb::tc_gemm_launch(g, splits, 256, st));
+  return MVB_OK;
+}
+
 // developer entry (not in include/mvb.h; tools/chol_inv_phases.py): the factorisation kernel alone with per-phase cycle counters
 int mvb_dev_chol_inv(const float* G, int p, int batch, const float* alphas, int n_alphas, float* Li, int* status, long long* phase_clk,
                      void* stream) {

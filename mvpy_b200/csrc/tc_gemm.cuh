@@ -70,11 +70,20 @@ struct TcGemmParams {
   const uint8_t* b_planes;            // optional: B already split into TF32 hi / lo planes, one shared-memory image per
   int b_planes_nkb;                   //   (256-row tile, 32-k stage), [n_tile][b_planes_nkb][2 * plane bytes] (tc_presplit_launch);
                                       //   the stage's B half is then one TMA bulk copy instead of LDG -> split -> STS by the threads
+  int b_stream_once;                  // 1 (TMEM-A kernel): every B tile is read once by one CTA (single M tile) while the small A operand is
+                                      //    re-read by every CTA: B's bulk copies carry an L2 evict-first policy and A's loads evict-last, so
+                                      //    that the B stream does not push A out of L2
+  int b_planes_raw;                   // 1: b_planes holds ONE plane per (tile, stage) -- the raw fp32 values in the same layout (4 B per
+                                      //    entry instead of 8): the tensor core reads their top 19 bits as the hi part, the lo plane is
+                                      //    produced in shared memory by the CTA's threads.  For products that stream B once from HBM
+                                      //    (the skinny block-Lanczos products), which are bound by the plane bytes.
 };
 
 inline TcGemmParams tc_gemm_defaults() {
   TcGemmParams p{};
   p.batch = 1;
+  static const int dbg = [] { const char* e = getenv("MVB_TC_DBG"); return e ? atoi(e) : 0; }();    // developer timing experiments only
+  p.dbg = dbg;
   return p;
 }
 
@@ -547,10 +556,42 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
                : "memory");
 }
 
-template <int A_MODE>
+__device__ __forceinline__ uint64_t l2_policy(bool evict_first) {
+  uint64_t pol;
+  if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_load_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ float4 ldg_hint(const float4* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+
+// exact remainder of x after truncation to TF32 (what the tensor core sees of a raw fp32 operand), itself rounded to TF32
+__device__ __forceinline__ float lo_after_trunc(float x) {
+  return rn_tf32(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
+}
+
+template <int A_MODE, bool RAW_B = false>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_ta_kernel(const TcGemmParams p) {
   using C_ = CfgTA;
   static_assert(A_MODE == 0 || A_MODE == 2, "A gather modes 0 and 2 only");
+  constexpr uint32_t SRC_BYTES = RAW_B ? (uint32_t)C_::B_PLANE : C_::B_BYTES;      // bytes of one (tile, stage) in b_planes
+  // B ring: three hi / lo pairs (copy issued two stages ahead), or -- raw planes -- FIVE single planes (copy issued four stages
+  // ahead) plus two lo planes produced in place.  A bulk copy that comes from HBM takes ~7 000 cycles to land whatever its size
+  // (measured: a stage of the skinny Lanczos products takes 3 500 cycles with 64 KB pairs and with 32 KB raw planes alike when two
+  // copies are in flight), so what shortens those products is more copies in flight per SM, which the halved stage makes room for.
+  constexpr int NSB = RAW_B ? 5 : C_::NS;
+  constexpr int AHEAD = NSB - 1;
+  constexpr uint32_t SLOT_BYTES = RAW_B ? (uint32_t)C_::B_PLANE : C_::B_BYTES;
+  constexpr int BAR_OFF = RAW_B ? 7 * C_::B_PLANE : C_::BAR_OFF;        // bars [0..2] stage's MMAs done; [3] chunk done; [4..] landed
   extern __shared__ __align__(1024) uint8_t smem[];
   const int m0 = (p.raster_m_fast ? blockIdx.x : blockIdx.y) * BM;
   const int n0 = (p.raster_m_fast ? blockIdx.y : blockIdx.x) * C_::BN;
@@ -559,10 +600,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_ta_kernel(const TcGemmPar
   const int splits = gridDim.z, split_id = blockIdx.z;
   const GatherOperand opA = p.A;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::BAR_OFF);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C_::BAR_OFF + 64);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 96);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 7; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    for (int i = 0; i < 4 + NSB; ++i) mbar_init(smem_u32(&bars[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -582,20 +623,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_ta_kernel(const TcGemmPar
   const int kb_end = min(nkb_total, kb_begin + kb_per);
   const int nkb = max(0, kb_end - kb_begin);
 
-  const uint8_t* b_tiles = p.b_planes + ((int64_t)(n0 / C_::BN) * p.b_planes_nkb + kb_begin) * (int64_t)C_::B_BYTES;
+  const uint8_t* b_tiles = p.b_planes + ((int64_t)(n0 / C_::BN) * p.b_planes_nkb + kb_begin) * (int64_t)SRC_BYTES;
   const int q = warp & 3, part = warp >> 2;   // TMEM lane quarter; k columns part * 8 .. + 8 of a stage, accumulator columns part * 64 ..
   const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
   const bool rok = m0 + q * 32 + lane < opA.rows;
   const float* arow = opA.base + (rok ? opA.roff[m0 + q * 32 + lane] : 0);
   float av[8];
+  const uint64_t pol_a = l2_policy(false), pol_b = l2_policy(true);
   auto fetch = [&](int it) {      // this thread's 8 values of stage it: row q * 32 + lane, k = (kb_begin + it) * BK + part * 8 ..
-    const int k0 = (kb_begin + it) * BK + part * 8;
+    // dbg 3 (timing experiment, results invalid): every stage re-reads stage 0's A values (L1 hits): what the loop costs without A latency
+    // dbg 4: B copies of every stage come from the first stage's planes (L2 hits): what it costs without the HBM stream
+    const int k0 = (kb_begin + (p.dbg == 3 ? 0 : it)) * BK + part * 8;
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       const int kg = k0 + g * 4;
       if (A_MODE == 2) {          // 4-aligned k groups are contiguous and 16-byte aligned; K % 4 == 0
         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rok && kg < p.K) t = __ldg(reinterpret_cast<const float4*>(arow + opA.koff[kg]));
+        if (rok && kg < p.K) t = p.b_stream_once ? ldg_hint(reinterpret_cast<const float4*>(arow + opA.koff[kg]), pol_a)
+                                                 : __ldg(reinterpret_cast<const float4*>(arow + opA.koff[kg]));
         av[g * 4 + 0] = t.x; av[g * 4 + 1] = t.y; av[g * 4 + 2] = t.z; av[g * 4 + 3] = t.w;
       } else {                    // lanes sit on consecutive rows (contiguous in memory): coalesced scalar loads
         int64_t ko[4];
@@ -618,11 +663,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_ta_kernel(const TcGemmPar
     }
   };
   auto load_b = [&](int it) {     // thread 0 only
-    const int sb = it % C_::NS;
-    bulk_load(smem_u32(smem + sb * C_::B_BYTES), b_tiles + (int64_t)it * C_::B_BYTES, C_::B_BYTES, smem_u32(&bars[4 + sb]));
+    const int sb = it % NSB;
+    const int64_t src_it = p.dbg == 4 ? 0 : it;
+    if (p.b_stream_once) bulk_load_hint(smem_u32(smem + sb * SLOT_BYTES), b_tiles + src_it * SRC_BYTES, SRC_BYTES, smem_u32(&bars[4 + sb]), pol_b);
+    else bulk_load(smem_u32(smem + sb * SLOT_BYTES), b_tiles + src_it * SRC_BYTES, SRC_BYTES, smem_u32(&bars[4 + sb]));
   };
   if (nkb > 0) {
-    if (threadIdx.x == 0) { load_b(0); if (nkb > 1) load_b(1); }
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int d = 0; d < AHEAD; ++d)
+        if (nkb > d) load_b(d);
+    }
     fetch(0);
   }
   constexpr int NACC = C_::BN / NPART;
@@ -633,7 +684,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_ta_kernel(const TcGemmPar
 
   for (int it = 0; it < nkb; ++it) {
     const int s = it % C_::NS;
-    if (it >= C_::NS) mbar_wait(smem_u32(&bars[s]), (uint32_t)(((it / C_::NS) - 1) & 1));   // stage s (A in TMEM, B in smem) is free
+    if (!RAW_B) {
+      if (it >= C_::NS) mbar_wait(smem_u32(&bars[s]), (uint32_t)(((it / C_::NS) - 1) & 1));   // stage s (A in TMEM, B in smem) is free
+    } else if (it >= 2) {
+      // the lo plane of this stage goes where stage it - 2's was: its MMAs must be done (which implies stage it - 3's, i.e. the
+      // A stage in TMEM is free as well)
+      mbar_wait(smem_u32(&bars[(it - 2) % C_::NS]), (uint32_t)(((it - 2) / C_::NS) & 1));
+    }
     {
       float hi[8], lo[8];
 #pragma unroll
@@ -642,14 +699,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_ta_kernel(const TcGemmPar
       tmem_st8(lane_addr + C_::COL_A + s * 64 + 32 + part * 8, lo);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
+    if (RAW_B) {
+      // the stage's raw plane has landed (requested four stages ago): every thread turns 4 of its 2048 16-byte groups into the lo
+      // plane next to it.  The raw plane itself is the hi operand -- kind::tf32 ignores the low 13 mantissa bits.
+      mbar_wait(smem_u32(&bars[4 + it % NSB]), (uint32_t)((it / NSB) & 1));
+      const float4* raw = reinterpret_cast<const float4*>(smem + (it % NSB) * C_::B_PLANE);
+      float4* lop = reinterpret_cast<float4*>(smem + (NSB + (it & 1)) * C_::B_PLANE);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = threadIdx.x + NTHREADS * i;                   // (k-chunk, row) of the 8 x 256 groups
+        const int off = (e >> 8) * (C_::B_LBO / 16) + (e & 255);
+        const float4 v = raw[off];
+        lop[off] = make_float4(lo_after_trunc(v.x), lo_after_trunc(v.y), lo_after_trunc(v.z), lo_after_trunc(v.w));
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     const bool chunk_first = (it % DRAIN) == 0;
     const bool chunk_last = ((it + 1) % DRAIN) == 0 || it == nkb - 1;
     if (threadIdx.x == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      mbar_wait(smem_u32(&bars[4 + s]), (uint32_t)((it / C_::NS) & 1));                     // this stage's B planes have landed
-      const uint32_t b_hi = smem_u32(smem + s * C_::B_BYTES), b_lo = b_hi + C_::B_PLANE;
+      mbar_wait(smem_u32(&bars[4 + it % NSB]), (uint32_t)((it / NSB) & 1));                  // this stage's B planes have landed
+      const uint32_t b_hi = smem_u32(smem + (it % NSB) * SLOT_BYTES);
+      const uint32_t b_lo = RAW_B ? smem_u32(smem + (NSB + (it & 1)) * C_::B_PLANE) : b_hi + C_::B_PLANE;
       const uint32_t a_hi = tmem_base + C_::COL_A + s * 64, a_lo = a_hi + 32;
 #pragma unroll
       for (int j = 0; j < BK / 8; ++j) {
@@ -661,10 +734,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_ta_kernel(const TcGemmPar
       }
       mma_commit(smem_u32(&bars[s]));
       if (chunk_last) mma_commit(smem_u32(&bars[3]));
-      if (it + 2 < nkb) {       // buffer (it + 2) % NS was last read by stage it - 1
-        const int s2 = (it + 2) % C_::NS;
-        if (it >= 1) mbar_wait(smem_u32(&bars[s2]), (uint32_t)(((it - 1) / C_::NS) & 1));
-        load_b(it + 2);
+      if (it + AHEAD < nkb) {   // ring slot (it + AHEAD) % NSB = (it - 1) % NSB was last read by stage it - 1
+        if (it >= 1) mbar_wait(smem_u32(&bars[(it - 1) % C_::NS]), (uint32_t)(((it - 1) / C_::NS) & 1));
+        load_b(it + AHEAD);
       }
     }
     if (it + 1 < nkb) fetch(it + 1);   // next stage's global loads fly while this stage's MMAs run
@@ -695,6 +767,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_ta_kernel(const TcGemmPar
 // planes[(tile * nkb_total + kb) * 2 * PLANE + plane * PLANE + kc * LBO + r * 16 + (k % 4) * 4], zero-filled outside
 // the operand.  One thread per (tile row, 16-byte chunk); rows [row_begin, row_end) and stages [kb_begin, kb_end) only,
 // so a growing operand (a Lanczos basis) is extended in place.
+template <bool RAW>
 __global__ void presplit_kernel(const GatherOperand op, int K, int nkb_total, int row_begin, int row_end, int kb_begin,
                                 int kb_end, uint8_t* __restrict__ planes) {
   constexpr int BN = 256, LBO = BN * 16 + 16, PLANE = KC * LBO;
@@ -717,6 +790,12 @@ __global__ void presplit_kernel(const GatherOperand op, int K, int nkb_total, in
         if (k + 2 < K) v.z = __ldg(src + op.koff[k + 2]);
         if (k + 3 < K) v.w = __ldg(src + op.koff[k + 3]);
       }
+    }
+    if (RAW) {                                    // one plane: the values themselves (TcGemmParams::b_planes_raw)
+      uint8_t* dst = planes + ((int64_t)tile * nkb_total + kb) * PLANE + kc * LBO + r * 16;
+      *reinterpret_cast<float4*>(dst) = v;
+      if (r == 0) *reinterpret_cast<float4*>(dst + BN * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
     }
     float4 h, l;
     split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
@@ -749,10 +828,17 @@ inline bool ta_enabled() {
 
 template <int AM>
 inline cudaError_t launch_ta(const TcGemmParams& p, int k_splits, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(tc_gemm_ta_kernel<AM>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgTA::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
   const unsigned nt = (p.N + CfgTA::BN - 1) / CfgTA::BN, mt = (p.M + BM - 1) / BM;
   dim3 grid(p.raster_m_fast ? mt : nt, p.raster_m_fast ? nt : mt, k_splits);
+  if (p.b_planes_raw) {
+    constexpr int SMEM_RAW = 7 * CfgTA::B_PLANE + 128;      // five raw planes + two lo planes + barriers
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_ta_kernel<AM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_RAW);
+    if (e != cudaSuccess) return e;
+    tc_gemm_ta_kernel<AM, true><<<grid, NTHREADS, SMEM_RAW, st>>>(p);
+    return cudaGetLastError();
+  }
+  cudaError_t e = cudaFuncSetAttribute(tc_gemm_ta_kernel<AM>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgTA::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   tc_gemm_ta_kernel<AM><<<grid, NTHREADS, CfgTA::SMEM_BYTES, st>>>(p);
   return cudaGetLastError();
 }
@@ -761,7 +847,8 @@ template <int BN, int AM>
 inline cudaError_t launch_b(const TcGemmParams& p, int k_splits, cudaStream_t st) {
   if (p.b_planes) {
     if (BN != 256 || p.batch > 1) return cudaErrorInvalidValue;
-    if (AM != 1 && ta_enabled()) return launch_ta<AM == 1 ? 0 : AM>(p, k_splits, st);
+    if (AM != 1 && (ta_enabled() || p.b_planes_raw)) return launch_ta<AM == 1 ? 0 : AM>(p, k_splits, st);
+    if (p.b_planes_raw) return cudaErrorInvalidValue;  // single raw planes exist for the TMEM-A kernel only
     if (p.symmetric) return cudaErrorInvalidValue;      // symmetric products with pre-split planes: TMEM-A kernel only
     return launch_variant<256, AM, 3>(p, k_splits, st);
   }
@@ -801,18 +888,19 @@ inline int tc_choose_splits(int64_t tiles, int nkb, int max_splits, int64_t out_
 }
 
 // Pre-split planes of a B operand (see TcGemmParams::b_planes): bytes needed, and the (partial) fill.
-inline size_t tc_planes_bytes(int rows, int K) {
-  return (size_t)((rows + 255) / 256) * ((K + tc::BK - 1) / tc::BK) * 2 * tc::Cfg<256>::B_PLANE;
+inline size_t tc_planes_bytes(int rows, int K, bool raw = false) {
+  return (size_t)((rows + 255) / 256) * ((K + tc::BK - 1) / tc::BK) * (raw ? 1 : 2) * tc::Cfg<256>::B_PLANE;
 }
 inline cudaError_t tc_presplit_launch(const GatherOperand& op, int K, uint8_t* planes, cudaStream_t st, int row_begin = 0,
-                                      int row_end = -1, int kb_begin = 0, int kb_end = -1) {
+                                      int row_end = -1, int kb_begin = 0, int kb_end = -1, bool raw = false) {
   const int nkb = (K + tc::BK - 1) / tc::BK;
   if (row_end < 0) row_end = ((op.rows + 255) / 256) * 256;      // whole tiles: rows past the operand are zero-filled
   if (kb_end < 0) kb_end = nkb;
   const int64_t total = (int64_t)(row_end - row_begin) * (kb_end - kb_begin) * tc::KC;
   if (total <= 0) return cudaSuccess;
   const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
-  tc::presplit_kernel<<<grid, 256, 0, st>>>(op, K, nkb, row_begin, row_end, kb_begin, kb_end, planes);
+  if (raw) tc::presplit_kernel<true><<<grid, 256, 0, st>>>(op, K, nkb, row_begin, row_end, kb_begin, kb_end, planes);
+  else tc::presplit_kernel<false><<<grid, 256, 0, st>>>(op, K, nkb, row_begin, row_end, kb_begin, kb_end, planes);
   return cudaGetLastError();
 }
 
