@@ -212,10 +212,31 @@ __device__ __noinline__ bool diag_block_factor(float* __restrict__ Lp, int kb, i
   }
   return bad;
 }
-__device__ __noinline__ void diag_block_invert(const float* __restrict__ Lp, int J, float* __restrict__ Dinv, int lane) {
+// in place: the lower-triangular diagonal block at J is replaced by its inverse (lane c solves column c from the rows held in
+// the warp's registers, so every load precedes every store)
+__device__ __noinline__ void diag_block_invert_inplace(float* __restrict__ Lp, int J, int lane) {
   float row[NB];
   diag_load(Lp, J, lane & (NB - 1), row);
-  diag_invert(row, lane, Dinv);
+  const int c = lane & (NB - 1);
+  float x[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    float v = (i == c) ? 1.f : 0.f;
+#pragma unroll
+    for (int k = 0; k < NB; ++k)
+      if (k < i) {
+        const float lik = __shfl_sync(0xffffffffu, row[k], i);
+        if (k >= c) v -= lik * x[k];
+      }
+    const float lii = __shfl_sync(0xffffffffu, row[i], i);
+    x[i] = (i < c) ? 0.f : v * __frcp_rn(lii);
+  }
+  __syncwarp();
+  if (lane < NB) {
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+      if (i >= c) Lp[tri(J + i) + J + c] = x[i];
+  }
 }
 
 __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __restrict__ G, int p, int Pp, const float* __restrict__ alphas,
@@ -311,11 +332,13 @@ __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __
     tick(3);
   }
 
-  // ---- in-place inverse of the triangular factor, block columns from the right ----
+  // ---- in-place inverse of the triangular factor ----
+  // all diagonal blocks first (independent of each other once the factor is complete: 16 warps, one block each, instead of one
+  // serial one-warp phase per block column), then the block columns from the right
+  for (int blk = warp; blk < Pp / NB; blk += CI_THREADS / 32) diag_block_invert_inplace(Lp, blk * NB, lane);
+  __syncthreads();
+  tick(4);
   for (int J = Pp - NB; J >= 0; J -= NB) {
-    if (warp == 0) diag_block_invert(Lp, J, Dinv, lane);
-    __syncthreads();
-    tick(4);
     const int base = J + NB, m = Pp - base;
     float* panel = panelT;                                       // here row-major [m][16]: panel[(i - base) * 16 + c]
     for (int i = base + tid; i < Pp; i += CI_THREADS) {          // panel[i] = L[i, J..J+16) Dinv
@@ -328,13 +351,9 @@ __global__ void __launch_bounds__(CI_THREADS, 1) chol_inv_kernel(const float* __
         float v = 0.f;
 #pragma unroll
         for (int k = 0; k < NB; ++k)
-          if (k >= c) v += l[k] * Dinv[k * (NB + 1) + c];
+          if (k >= c) v += l[k] * Lp[tri(J + k) + J + c];        // the block's inverse, already in place (same address for all threads)
         panel[(i - base) * NB + c] = v;
       }
-    }
-    if (tid < NB * NB) {                                         // the diagonal block itself
-      const int r = tid / NB, c = tid % NB;
-      if (c <= r) Lp[tri(J + r) + J + c] = Dinv[r * (NB + 1) + c];
     }
     __syncthreads();
     tick(5);
