@@ -184,6 +184,8 @@ int run_contract(const mvb_operand& A, const mvb_operand& B, int M, int N, int K
       g_launches.fetch_add(1, std::memory_order_relaxed);
       p.b_planes = (const uint8_t*)planes;
       p.b_planes_nkb = (K + mvb::tc::BK - 1) / mvb::tc::BK;
+      static const bool reuse_hint = [] { const char* e = getenv("MVB_TC_REUSE_HINTS"); return !e || atoi(e) != 0; }();
+      if (reuse_hint && p.raster_m_fast) p.b_stream_once = 2;      // B tile re-read by every M tile of the wave: keep it in L2, let A stream
     }
     const int slot = prof_begin(2.0 * M * (double)N * K * (symmetric ? 0.5 : 1.0), st);
     MVB_CUDA(mvb::tc_gemm_launch(p, pl.splits, N > 128 ? 256 : 128, st));

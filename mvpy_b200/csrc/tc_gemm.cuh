@@ -73,6 +73,8 @@ struct TcGemmParams {
   int b_stream_once;                  // 1 (TMEM-A kernel): every B tile is read once by one CTA (single M tile) while the small A operand is
                                       //    re-read by every CTA: B's bulk copies carry an L2 evict-first policy and A's loads evict-last, so
                                       //    that the B stream does not push A out of L2
+                                      // 2: the other way round (raster_m_fast products: a B tile is re-read by all M tiles of a wave while the
+                                      //    dense A operand streams): B evict-last, A evict-first
   int b_planes_raw;                   // 1: b_planes holds ONE plane per (tile, stage) -- the raw fp32 values in the same layout (4 B per
                                       //    entry instead of 8): the tensor core reads their top 19 bits as the hi part, the lo plane is
                                       //    produced in shared memory by the CTA's threads.  For products that stream B once from HBM
@@ -629,7 +631,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_ta_kernel(const TcGemmPar
   const bool rok = m0 + q * 32 + lane < opA.rows;
   const float* arow = opA.base + (rok ? opA.roff[m0 + q * 32 + lane] : 0);
   float av[8];
-  const uint64_t pol_a = l2_policy(false), pol_b = l2_policy(true);
+  const uint64_t pol_a = l2_policy(p.b_stream_once == 2), pol_b = l2_policy(p.b_stream_once != 2);
   auto fetch = [&](int it) {      // this thread's 8 values of stage it: row q * 32 + lane, k = (kb_begin + it) * BK + part * 8 ..
     // dbg 3 (timing experiment, results invalid): every stage re-reads stage 0's A values (L1 hits): what the loop costs without A latency
     // dbg 4: B copies of every stage come from the first stage's planes (L2 hits): what it costs without the HBM stream
