@@ -10,13 +10,14 @@ Discipline that makes the caching allocator and cross-stream reads safe without 
   * every lane waits for the caller's stream before its first task, and the caller's stream waits for every lane after
     the last one, so nothing crosses between lanes and the caller inside a call;
   * tasks with the same ``lane_key`` always run on the same lane, in order (shared per-fold statistics stay on one stream).
-One host thread per lane, because the pending-launch queue of a stream is bounded: a single thread enqueueing a whole
-unit on lane 0 would block before it reaches lane 1.  ctypes calls and torch ops release the GIL.
+One host thread per lane (a small persistent pool), because the pending-launch queue of a stream is bounded: a single thread
+enqueueing a whole unit on lane 0 would block before it reaches lane 1.  ctypes calls and torch ops release the GIL.
 """
 from __future__ import annotations
 
 import os
 import threading
+from concurrent.futures import ThreadPoolExecutor
 from typing import Any, Callable, Dict, List, Optional, Sequence
 
 import torch
@@ -24,18 +25,29 @@ import torch
 _lanes: Dict[int, List['torch.cuda.Stream']] = {}
 _n_override: Optional[int] = None
 _lock = threading.Lock()
+MAX_LANES = 8
+_pool: Optional[ThreadPoolExecutor] = None      # persistent lane threads: the library keeps a few per-thread CUDA events, so threads are reused
+_in_lane = threading.local()
+
+
+def _lane_pool() -> ThreadPoolExecutor:
+    global _pool
+    with _lock:
+        if _pool is None:
+            _pool = ThreadPoolExecutor(max_workers=MAX_LANES, thread_name_prefix='mvb-lane')
+        return _pool
 
 
 def set_fold_streams(n: Optional[int]) -> None:
     """Number of lanes (1 = serial on the caller's stream); None restores the default / ``MVB_FOLD_STREAMS``."""
     global _n_override
-    _n_override = None if n is None else max(1, int(n))
+    _n_override = None if n is None else min(MAX_LANES, max(1, int(n)))
 
 
 def n_fold_streams() -> int:
     if _n_override is not None:
         return _n_override
-    return max(1, int(os.environ.get('MVB_FOLD_STREAMS', '3')))
+    return min(MAX_LANES, max(1, int(os.environ.get('MVB_FOLD_STREAMS', '3'))))
 
 
 def _device_lanes(device: torch.device, n: int) -> List['torch.cuda.Stream']:
@@ -64,8 +76,8 @@ def run_on_lanes(tasks: Sequence[Callable[[], Any]], device: torch.device, lane_
     order.  ``lane_keys[i]`` (default i) picks the lane: ``key % n_lanes``."""
     from . import _lib
     n = min(n_fold_streams(), len(tasks))
-    if n <= 1 or device.type != 'cuda' or torch.cuda.is_current_stream_capturing():
-        return [t() for t in tasks]
+    if n <= 1 or device.type != 'cuda' or getattr(_in_lane, 'active', False) or torch.cuda.is_current_stream_capturing():
+        return [t() for t in tasks]        # (a driver nested inside a lane task stays on that lane: the pool is not re-entered)
     keys = list(range(len(tasks))) if lane_keys is None else [int(k) for k in lane_keys]
     _warm(device)
     lanes = _device_lanes(device, n)
@@ -79,6 +91,7 @@ def run_on_lanes(tasks: Sequence[Callable[[], Any]], device: torch.device, lane_
 
     def work(lane: int) -> None:
         try:
+            _in_lane.active = True
             torch.cuda.set_device(device)
             _lib.fold_ctx.parent = parent
             with torch.cuda.stream(lanes[lane]):
@@ -88,14 +101,13 @@ def run_on_lanes(tasks: Sequence[Callable[[], Any]], device: torch.device, lane_
             errors[lane] = e
         finally:
             _lib.fold_ctx.parent = None
+            _in_lane.active = False
 
     for s in lanes:
         s.wait_stream(main)
-    threads = [threading.Thread(target=work, args=(lane,), name=f'mvb-lane-{lane}') for lane in range(n) if assigned[lane]]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
+    futures = [_lane_pool().submit(work, lane) for lane in range(n) if assigned[lane]]
+    for f in futures:
+        f.result()
     for s in lanes:
         main.wait_stream(s)
     for e in errors:

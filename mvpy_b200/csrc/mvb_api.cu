@@ -1,7 +1,9 @@
 // mvb_api.cu -- the C-ABI of libmvb.so (include/mvb.h): argument checking, workspace carving and
 // the kernel sequences of the ridge hot path.  No allocation, no synchronisation, no host fallback.
 #include <atomic>
+#include <map>
 #include <mutex>
+#include <utility>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -587,16 +589,26 @@ __global__ void intercept_kernel(const double* __restrict__ ybar, const double* 
 }
 
 // helper stream for work that is independent of the caller's stream for a while (forked / joined with events): one per
-// device, created on first use with that device current
-cudaStream_t side_stream() {
-  constexpr int kMaxDev = 64;
-  static cudaStream_t s[kMaxDev] = {};
+// (device, caller's stream), created on first use with that device current.  Per caller's stream, because independent fits are
+// enqueued on several stream lanes at once (mvpy_b200/_streams.py): on one shared helper stream the forked work of lane B would
+// queue behind lane A's and B's join would wait for both.
+cudaStream_t side_stream(cudaStream_t caller) {
+  static std::map<std::pair<int, cudaStream_t>, cudaStream_t> streams;
   static std::mutex mu;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
   std::lock_guard<std::mutex> lk(mu);
-  if (!s[dev] && cudaStreamCreateWithFlags(&s[dev], cudaStreamNonBlocking) != cudaSuccess) s[dev] = nullptr;
-  return s[dev];
+  const auto key = std::make_pair(dev, caller);
+  auto it = streams.find(key);
+  if (it != streams.end()) return it->second;
+  if (streams.size() >= 256) {                                   // callers that churn through streams: share the first helper of the device
+    for (auto& kv : streams)
+      if (kv.first.first == dev) return kv.second;
+  }
+  cudaStream_t s = nullptr;
+  if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  streams[key] = s;
+  return s;
 }
 // Joins forked side-stream work back into the caller's stream on every exit path (an error return between fork and join must
 // not leave the side stream writing into a workspace the caller is about to free, nor an open capture un-joined).
@@ -668,7 +680,7 @@ int ridge_solve_band(const mvb_design* d, const float* y, int F, float* G, const
   SideJoin side_join(st);
   {
     MVB_CUDA(cudaFuncSetAttribute(mvb::bl::block_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mvb::bl::CHOL_SMEM));
-    cudaStream_t side = side_stream();
+    cudaStream_t side = side_stream(st);
     if (!side) return fail(MVB_E_CUDA, "ridge_solve(band): no side stream for the current device");
     // one pair of events per host thread and device, reused: a wait binds to the record that precedes it in host order, so
     // reuse across calls and streams is safe, and nothing is created or destroyed while a caller is stream-capturing

@@ -287,3 +287,33 @@ def test_label_binariser_golden(golden):
         mv.estimators.Classifier(mv.estimators.RidgeClassifier, method='OvA')
     with pytest.raises(ValueError):
         c.predict(torch.zeros(2, 3))
+
+
+def test_fold_lanes_host_logic():
+    """mvpy_b200/_streams.py without a GPU: CPU tensors run the tasks in order on the caller's thread; lane count limits."""
+    import torch
+    from mvpy_b200 import _streams
+    order = []
+    out = _streams.run_on_lanes([(lambda i=i: (order.append(i), i * i)[1]) for i in range(5)], torch.device('cpu'), lane_keys=[0, 1, 0, 1, 2])
+    assert out == [0, 1, 4, 9, 16] and order == [0, 1, 2, 3, 4]
+    try:
+        _streams.set_fold_streams(100)
+        assert _streams.n_fold_streams() == _streams.MAX_LANES
+        _streams.set_fold_streams(0)
+        assert _streams.n_fold_streams() == 1
+    finally:
+        _streams.set_fold_streams(None)
+    assert _streams.n_fold_streams() >= 1
+
+
+def test_batched_executor_declines_without_a_gpu_or_for_other_estimators():
+    import torch
+    import mvpy_b200 as mv
+    from mvpy_b200 import _batched
+    X, y = torch.randn(50, 4, 6), torch.randn(50, 2, 6)
+    pairs = [(i, i) for i in range(6)]
+    if not torch.cuda.is_available():
+        assert _batched.fit_slices(mv.estimators.RidgeDecoder(alphas=torch.tensor([1.0])), X, y, pairs) is None
+    assert _batched.fit_slices(object(), X, y, pairs) is None
+    assert _batched.fit_slices(mv.estimators.RidgeDecoder(alphas=torch.tensor([1.0])), X.double(), y.double(), pairs) is None      # float64: general route
+    assert _batched.predict_slices([object()] * 6, X) is None
