@@ -514,7 +514,7 @@ def dense_ridge_batched_ok(n: int, p: int, F: int, A: int, dtype) -> bool:
     """Shapes the batched small-problem route takes (float32, p <= 320, more samples than columns)."""
     if dtype != torch.float32:
         return False
-    return p <= load().mvb_dense_ridge_batched_max_cols() and n > p + 1 and A * F <= 4096
+    return p <= load().mvb_dense_ridge_batched_max_cols() and p + 1 < n <= 65535 and A * F <= 4096
 
 
 def dense_ridge_batched(X3: torch.Tensor, Y3: torch.Tensor, sample_idx: Optional[torch.Tensor], alphas: torch.Tensor, fit_intercept: bool,

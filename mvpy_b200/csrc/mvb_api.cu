@@ -970,7 +970,7 @@ void carve_dense(Arena& ar, int B, int n, int p, int F, int A, DenseWs& w) {
 
 bool dense_batched_ok(int B, int n, int p, int F, int A) {
   return B >= 1 && p >= 1 && p <= mvb::db::MAX_COLS && F >= 1 && A >= 1 && n > p + 1 && (int64_t)A * F <= 4096 &&
-         (int64_t)A * ((p + 127) / 128) * 128 <= 65535 * 128LL && n <= 65535 * 4;
+         (int64_t)A * ((p + 127) / 128) * 128 <= 65535 * 128LL && n <= 65535;      // (n is a grid.z extent of the packing kernel)
 }
 
 int dense_batched_launch(mvb::TcGemmParams& g, int bn, int cls, double flops, cudaStream_t st) {

@@ -719,6 +719,31 @@ def test_dense_ridge_batched_matches_general_route_and_oracle(shape, monkeypatch
     assert host.predict(X).device.type == 'cpu'
 
 
+def test_sliding_batched_other_layouts(monkeypatch):
+    """The batched executor reads the user's array through its strides: a sliding dimension in the middle (dims=1, i.e. a
+    (trials, time, channels) array), a single target (the F = 1 pattern formula, ridgedecoder.py:283-285), non-contiguous inputs;
+    each against the per-slice loop."""
+    mv = _mv()
+    g = torch.Generator().manual_seed(21)
+    n, p, t = 150, 12, 9
+    X = torch.randn(n, t, p, generator=g).cuda()
+    y = (X @ (torch.randn(p, 1, generator=g).cuda() * 0.3) + torch.randn(n, t, 1, generator=g).cuda())
+    al = torch.logspace(-2, 3, 6)
+    Xbig = torch.randn(n, t, 2 * p, generator=g).cuda()
+    cases = [(X, y), (Xbig[:, :, ::2], y.expand(-1, -1, 1))]                      # the second X is a strided (non-contiguous) view
+    for Xc, yc in cases:
+        out = {}
+        for flag in ('0', '1'):
+            monkeypatch.setenv('MVB_SLIDING_BATCHED', flag)
+            monkeypatch.setenv('MVB_SLIDING_GRAPHS', '0')
+            sl = mv.estimators.Sliding(mv.estimators.RidgeDecoder(alphas=al), dims=1).fit(Xc, yc)
+            out[flag] = (sl.collect('coef_'), sl.collect('alpha_'), sl.collect('pattern_'), sl.collect('intercept_'), sl.predict(Xc))
+        assert out['1'][0].shape == (t, 1, p) and out['1'][4].shape == (n, t, 1)
+        assert torch.equal(out['0'][1], out['1'][1])
+        for a, b in zip(out['0'], out['1']):
+            np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=0, atol=2e-4 * float(a.abs().max()))
+
+
 def test_dense_ridge_batched_hands_rank_deficient_slices_to_the_general_route(monkeypatch):
     """A slice whose Gram + alpha I is numerically singular at the small alphas (two identical channels) is flagged by the
     batched factorisation (status != 0) and refitted on the guarded route; the other slices are untouched."""
