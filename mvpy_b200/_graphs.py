@@ -105,6 +105,9 @@ def fit_slices(proto, Xm: torch.Tensor, ym: torch.Tensor, pairs: Sequence[Tuple[
     global _broken
     if _broken or os.environ.get('MVB_SLIDING_GRAPHS', '1') == '0':
         return None
+    from . import _streams
+    if getattr(_streams._in_lane, 'active', False):          # stream capture next to other lanes' launches: keep the eager loop
+        return None
     if not (isinstance(Xm, torch.Tensor) and Xm.is_cuda and ym.is_cuda and Xm.ndim == 3 and ym.ndim in (2, 3)):
         return None
     if Xm.dtype not in (torch.float32, torch.float64) or ym.dtype != Xm.dtype:
