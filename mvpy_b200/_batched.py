@@ -89,19 +89,23 @@ def fit_slices(proto, Xm: torch.Tensor, ym: torch.Tensor, pairs: Sequence[Tuple[
     coef_o, icpt_o, alpha_o, loss_o = coef.to(out_dev), icpt.to(out_dev), alpha.to(out_dev), loss.to(out_dev)
     pattern_o = None if pattern is None else pattern.to(out_dev)
     al_o = al.to(out_dev)
+    # per-slice views of the stacked results, made by five unbind calls instead of thousands of Python-level indexing operations
+    coef_v, alpha_v, loss_v = coef_o.unbind(0), alpha_o.unbind(0), loss_o.unbind(0)
+    icpt_v = icpt_o[:, None, :].unbind(0) if fit_intercept else None
+    pattern_v = pattern_o.unbind(0) if pattern_o is not None else None
     fitted = []
     for b in range(B):
         est = proto.clone()
         inner = est.estimator if kind == 'decoder' else est
         inner.alphas = al_o                                      # ridgecv.py:125
-        inner.coef_ = coef_o[b]
-        inner.alpha_ = alpha_o[b] if per_target else alpha_o[b].reshape(())
-        inner.loss_ = loss_o[b]
-        inner.intercept_ = icpt_o[b][None, :] if fit_intercept else 0.0
+        inner.coef_ = coef_v[b]
+        inner.alpha_ = alpha_v[b]                                # (F,) per target, 0-d when shared
+        inner.loss_ = loss_v[b]
+        inner.intercept_ = icpt_v[b] if fit_intercept else 0.0
         inner._gram = None
         if kind == 'decoder':
             est.coef_, est.intercept_, est.alpha_ = inner.coef_, inner.intercept_, inner.alpha_
-            est.pattern_ = pattern_o[b]
+            est.pattern_ = pattern_v[b]
         fitted.append(est)
     for b in bad:                                                # rank-deficient / badly scaled slices: the guarded general route
         fitted[b] = proto.clone().fit(Xm[..., xi[b]], ym[..., yi[b]])

@@ -1043,6 +1043,9 @@ int dense_ridge_batched_impl(const mvb_strided* X, const mvb_strided* Y, const i
     g.M = n; g.N = A * w.tri_rows; g.K = Pp; g.C = nullptr; g.ldc = 0; g.batch = B;
     g.a_roff_batch = n; g.b_roff_batch = (int64_t)A * w.tri_rows;
     g.rowsq = w.rowsq; g.rowsq_assign = 1; g.b_tri_period = w.tiles_per_alpha;      // every (tile, part, slice, row) entry is written once
+    // a CTA walks the N tiles of `walk` alphas for its 128 rows (barriers / tensor memory set up once, the A rows stay in L1 / L2)
+    static const int walk = [] { const char* e = getenv("MVB_DENSE_WALK"); return e ? atoi(e) : 4; }();
+    g.n_tiles_per_cta = walk > 1 ? walk * w.tiles_per_alpha : 0;
     // flops counted for the triangular half actually contracted
     double kk = 0;
     for (int t = 0; t < w.tiles_per_alpha; ++t) kk += std::min(Pp, (t + 1) * db::TRI_TILE);

@@ -63,6 +63,7 @@ struct TcGemmParams {
   int64_t c_block_stride;             //      elements between consecutive column blocks (>= M * c_block_cols)
   float* rowsq;                       // optional [N tiles][TC_ROWSQ_PARTS][batch][M]: += sum over this thread's columns of C[m][n]^2
                                       // (split-K not allowed); C may be nullptr when only the row squares are wanted
+  int n_tiles_per_cta;                // > 1 (tc_gemm_kernel, k_splits == 1, not symmetric): a CTA walks this many consecutive N tiles
   int rowsq_assign;                   // 1: rowsq entries are written (=) instead of accumulated (+=): every entry is produced once
   int b_tri_period;                   // > 0: B is a stack of lower-triangular blocks (B[n][k] = 0 for k > n mod period*BN), `period`
                                       //      N tiles each: tile t contracts only k < ((t mod period) + 1) * BN  (batch kernel only)
@@ -385,7 +386,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
   using C_ = Cfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int m0 = (p.raster_m_fast ? blockIdx.x : blockIdx.y) * BM;
-  const int n0 = (p.raster_m_fast ? blockIdx.y : blockIdx.x) * BN;
+  // n_tiles_per_cta > 1: the CTA walks that many consecutive N tiles of its M tile with barriers / tensor memory set up once
+  // (short-K batched products, whose CTAs would otherwise be mostly prologue and epilogue); plain, non-symmetric launches only
+  const int tiles_per_cta = p.n_tiles_per_cta > 1 ? p.n_tiles_per_cta : 1;
+  const int nt0 = (p.raster_m_fast ? blockIdx.y : blockIdx.x) * tiles_per_cta;
+  int n0 = nt0 * BN;
   if (p.symmetric && n0 > m0 + BM - 1) return;  // strictly above the diagonal: mirrored by the lower tile
   if (p.skip_flag && *p.skip_flag) return;
   const int splits = gridDim.z / p.batch;
@@ -399,7 +404,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C_::BAR_OFF + 48);
   constexpr bool B_TMA = (B_MODE == 3);
   constexpr uint32_t B_BYTES = 2 * C_::B_PLANE;
-  const uint8_t* b_tiles = B_TMA ? p.b_planes + (int64_t)(n0 / BN) * p.b_planes_nkb * (int64_t)B_BYTES : nullptr;
   int64_t* sroffA = reinterpret_cast<int64_t*>(smem + C_::ROFF_OFF);
   int64_t* sroffB = sroffA + BM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -428,6 +432,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
+  constexpr int NACC = BN / NPART;             // columns per thread: warps 4i .. 4i+3 own column part i
+  const int q = warp & 3;                      // TMEM lane quarter this warp may access
+  const int col_half = warp >> 2;              // column part index, 0 .. NPART-1
+  uint32_t gs = 0;                             // stages issued so far by this CTA (buffer / barrier parity across tiles)
+  int n_drained = 0;
+  for (int tt = 0; tt < tiles_per_cta; ++tt) {
+  if (tt > 0) {
+    n0 = (nt0 + tt) * BN;
+    if (n0 >= p.N) break;
+    __syncthreads();                           // every thread is past its last read of the previous tile's row offsets
+    for (int r = threadIdx.x; r < BN; r += NTHREADS)
+      if (!B_TMA) sroffB[r] = (n0 + r < opB.rows) ? opB.roff[n0 + r] : 0;
+    __syncthreads();
+  }
+  const uint8_t* b_tiles = B_TMA ? p.b_planes + (int64_t)(n0 / BN) * p.b_planes_nkb * (int64_t)B_BYTES : nullptr;
   // K range of this split
   const int k_eff = p.b_tri_period > 0 ? min(p.K, (((n0 / BN) % p.b_tri_period) + 1) * BN) : p.K;
   const int nkb_total = (k_eff + BK - 1) / BK;
@@ -442,19 +461,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
     la.fetch(opA, sroffA, m0, kb_begin * BK, p.K);
     if (!B_TMA) lb.fetch(opB, sroffB, n0, kb_begin * BK, p.K);
     else if (threadIdx.x == 0)
-      bulk_load(smem_u32(stage_base[0] + 2 * C_::A_PLANE), b_tiles + (int64_t)kb_begin * B_BYTES, B_BYTES, smem_u32(&bars[3]));
+      bulk_load(smem_u32(stage_base[gs & 1u] + 2 * C_::A_PLANE), b_tiles + (int64_t)kb_begin * B_BYTES, B_BYTES, smem_u32(&bars[3 + (gs & 1u)]));
   }
-  constexpr int NACC = BN / NPART;             // columns per thread: warps 4i .. 4i+3 own column part i
-  const int q = warp & 3;                      // TMEM lane quarter this warp may access
-  const int col_half = warp >> 2;              // column part index, 0 .. NPART-1
   float acc[NACC];
 #pragma unroll
   for (int j = 0; j < NACC; ++j) acc[j] = 0.f;
-  int n_drained = 0;
 
   for (int it = 0; it < nkb; ++it) {
-    const int s = it & 1;
-    if (it >= 2) mbar_wait(smem_u32(&bars[s]), (uint32_t)(((it >> 1) - 1) & 1));
+    const uint32_t g = gs + (uint32_t)it;      // == it for a CTA that owns one tile
+    const int s = (int)(g & 1u);
+    if (g >= 2) mbar_wait(smem_u32(&bars[s]), (uint32_t)(((g >> 1) - 1) & 1u));
     uint8_t* sb = stage_base[s];
     if (p.dbg != 1) {
       la.store(sb, sb + C_::A_PLANE);
@@ -466,7 +482,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
     const bool chunk_last = ((it + 1) % DRAIN) == 0 || it == nkb - 1;
     if (threadIdx.x == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (B_TMA) mbar_wait(smem_u32(&bars[3 + s]), (uint32_t)((it >> 1) & 1));      // this stage's B planes have landed
+      if (B_TMA) mbar_wait(smem_u32(&bars[3 + s]), (uint32_t)((g >> 1) & 1u));      // this stage's B planes have landed
       if (p.dbg != 2) {
         const uint32_t a_hi = smem_u32(sb), a_lo = a_hi + C_::A_PLANE;
         const uint32_t b_hi = a_hi + 2 * C_::A_PLANE, b_lo = b_hi + C_::B_PLANE;
@@ -487,7 +503,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
         // the other buffer was last read by stage it - 1; once those MMAs are done the next stage's planes can land in it
         // while this stage's MMAs run
         const int s1 = s ^ 1;
-        if (it >= 1) mbar_wait(smem_u32(&bars[s1]), (uint32_t)(((it - 1) >> 1) & 1));
+        if (g >= 1) mbar_wait(smem_u32(&bars[s1]), (uint32_t)(((g - 1) >> 1) & 1u));
         bulk_load(smem_u32(stage_base[s1] + 2 * C_::A_PLANE), b_tiles + (int64_t)(kb_begin + it + 1) * B_BYTES, B_BYTES,
                   smem_u32(&bars[3 + s1]));
       }
@@ -513,8 +529,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const TcGemmParams
     }
   }
 
+  gs += (uint32_t)nkb;
   // ---- epilogue: register accumulators -> global ------------------------------------------------
   store_tile<NACC>(p, acc, m0, n0, BN, q, lane, col_half, batch_id, split_id);
+  }   // tiles of this CTA
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
@@ -816,7 +834,12 @@ inline cudaError_t launch_variant(const TcGemmParams& p, int k_splits, cudaStrea
   cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, AM, BMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg<BN>::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  const unsigned nt = (p.N + BN - 1) / BN, mt = (p.M + BM - 1) / BM;
+  unsigned nt = (p.N + BN - 1) / BN;
+  const unsigned mt = (p.M + BM - 1) / BM;
+  if (p.n_tiles_per_cta > 1) {
+    if (k_splits != 1 || p.symmetric) return cudaErrorInvalidValue;
+    nt = (nt + p.n_tiles_per_cta - 1) / p.n_tiles_per_cta;
+  }
   dim3 grid(p.raster_m_fast ? mt : nt, p.raster_m_fast ? nt : mt, k_splits * (p.batch > 0 ? p.batch : 1));
   tc_gemm_kernel<BN, AM, BMODE><<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, st>>>(p);
   return cudaGetLastError();
