@@ -401,7 +401,6 @@ def main():
     if args.fold_streams is not None:
         _streams.set_fold_streams(args.fold_streams)
     lanes = _streams.n_fold_streams()
-    config['fold_streams'] = lanes
     for _ in range(args.warmup):
         step_device()
     barrier()
@@ -657,7 +656,7 @@ def main():
         cb, _ = cpu_baseline(X, y, alphas, args.workload)
     line = dict(sharded_api=sharded, metric='TRF ridge fits/s (folds x alphas x sets)', value=value, unit='fits/s', n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype='f32', data='synthetic', config=config, clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roof,
+                dtype='f32', data='synthetic', config=config, fold_streams=lanes, clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roof,
                 roofline_score=score_roof, cpu_baseline=cb)
     line['sharded_api'] = line.pop('sharded_api')          # keep it at the end of the line
     print(json.dumps(line))
