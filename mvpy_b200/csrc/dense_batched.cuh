@@ -551,12 +551,342 @@ __global__ void select_kernel(const double* __restrict__ partial, int slabs, int
     for (int c = lane; c < p; c += 32) {
       const float v = src[c];
       coef[((int64_t)b * F + f) * p + c] = v;
-      m += (double)v * (double)mu[(int64_t)b * Pp + c];
+      if (mu) m += (double)v * (double)mu[(int64_t)b * Pp + c];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
-    if (lane == 0) intercept[(int64_t)b * F + f] = fit_intercept ? (float)((double)ybar[(int64_t)b * F + f] - m) : 0.f;
+    if (lane == 0 && mu) intercept[(int64_t)b * F + f] = fit_intercept ? (float)((double)ybar[(int64_t)b * F + f] - m) : 0.f;
   }
+}
+
+// =====================================================================================================================
+// Tridiagonal route (MVB_DENSE_ROUTE=tridiag, default for the shapes it takes): ONE orthogonal reduction per slice instead of one
+// Cholesky factor + inverse + leverage product per (slice, alpha).
+//
+//   G_b = Q T Q^T   (Householder, T tridiagonal; tridiag_kernel, one CTA per slice, packed lower triangle in shared memory)
+//   Z_b = Xc_b Q    (the p - 2 reflectors applied to 32-row tiles held in shared memory; rows_apply_leverage_kernel)
+//   h_i(alpha) = z_i^T (T + alpha I)^-1 z_i  from the L D L^T factors of the tridiagonal matrices (tri_ldl_solve_kernel):
+//                w_k = z_k - l_{k-1} w_{k-1},  h = sum_k w_k^2 / d_k       -- O(p) per (row, alpha), in the same kernel
+//   x_alpha = (T + alpha I)^-1 Q^T X^T y  (tridiagonal solves), fitted values Z x_alpha (batched tensor-core product, as before),
+//   coefficients of the chosen alphas back in the original basis: coef = Q x   (reflectors_small_kernel, reverse order)
+//
+// This is the eigen-route of SURVEY 8 a-note with "eigendecomposition" replaced by the tridiagonal form, which is what a
+// symmetric eigensolver computes first anyway and all that the alpha sweep needs: 2 p^3 / 3 + n p^2 fp32 FMAs per slice instead
+// of 20 x (2 p^3 / 3 + n p^2).
+// =====================================================================================================================
+constexpr int TD_THREADS = 1024;
+inline size_t tridiag_smem(int p) { return ((size_t)((tri(p) + 3) & ~3) + 3 * (size_t)((p + 3) & ~3) + 64) * 4; }
+
+__device__ __forceinline__ float block_sum_1024(float v, float* red) {      // all threads get the sum; two barriers
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < TD_THREADS / 32; ++w) s += red[w];
+  __syncthreads();
+  return s;
+}
+
+// dT [B][ldt], eT [B][ldt] (e[k] = T[k+1][k]), V [B][p][ldv] (row k = v_k: 0 up to k, 1 at k + 1, then the reflector), tau [B][ldt]
+__global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(const float* __restrict__ G, int p, int Pp, float* __restrict__ dT,
+                                                                float* __restrict__ eT, int ldt, float* __restrict__ V, int ldv,
+                                                                float* __restrict__ tau_out) {
+  extern __shared__ __align__(16) float sm[];
+  const int pa = (p + 3) & ~3;
+  float* Lp = sm;
+  float* sv = sm + ((tri(p) + 3) & ~3);
+  float* sw = sv + pa;
+  float* sp = sw + pa;
+  float* red = sp + pa;            // 32 + scalars
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, b = blockIdx.x;
+  const float* Gb = G + (int64_t)b * Pp * Pp;
+  float* Vb = V + (int64_t)b * p * ldv;
+  float gpart = 0.f;
+  for (int i = warp; i < p; i += TD_THREADS / 32)
+    for (int j = lane; j <= i; j += 32) {
+      const float v = Gb[(int64_t)i * Pp + j];
+      Lp[tri(i) + j] = v;
+      if (i == j) gpart = fmaxf(gpart, v);
+    }
+  for (int e = tid; e < p * ldv; e += TD_THREADS) Vb[e] = 0.f;
+  // largest diagonal entry of G: the scale of the pivot test in tri_ldl_solve_kernel (the same scale the Cholesky route uses), kept in the
+  // unused last slot of e
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gpart = fmaxf(gpart, __shfl_xor_sync(0xffffffffu, gpart, o));
+  if (lane == 0) red[warp] = gpart;
+  __syncthreads();
+  if (tid == 0) {
+    float gmax = 0.f;
+    for (int w = 0; w < TD_THREADS / 32; ++w) gmax = fmaxf(gmax, red[w]);
+    red[40] = gmax;
+  }
+  __syncthreads();
+  const float gmax_all = red[40];
+  const int quad = tid >> 2, q = tid & 3;
+  for (int k = 0; k + 2 < p; ++k) {
+    const int o = k + 1, m = p - o;
+    // column k below the diagonal
+    float part = 0.f;
+    for (int j = tid; j < m; j += TD_THREADS) {
+      const float x = Lp[tri(o + j) + k];
+      sv[j] = x;
+      if (j >= 1) part += x * x;
+    }
+    const float xnorm2 = block_sum_1024(part, red);          // (its barriers also publish sv)
+    const float alpha0 = sv[0];
+    float tau = 0.f, beta = alpha0, scale = 0.f;
+    if (xnorm2 > 0.f) {
+      beta = -copysignf(sqrtf(alpha0 * alpha0 + xnorm2), alpha0);
+      tau = (beta - alpha0) / beta;
+      scale = 1.f / (alpha0 - beta);
+    }
+    for (int j = tid; j < m; j += TD_THREADS) {
+      const float v = (j == 0) ? 1.f : sv[j] * scale;
+      sv[j] = v;
+      Vb[(int64_t)k * ldv + o + j] = v;
+    }
+    if (tid == 0) {
+      dT[(int64_t)b * ldt + k] = Lp[tri(k) + k];
+      eT[(int64_t)b * ldt + k] = beta;
+      tau_out[(int64_t)b * ldt + k] = tau;
+    }
+    __syncthreads();
+    if (tau != 0.f) {                                          // (uniform: every thread computed the same tau)
+      // p_vec = tau * A22 v, four lanes per row (j = q mod 4), rows in passes of 256
+      for (int i0 = 0; i0 < m; i0 += TD_THREADS / 4) {          // (uniform trip count: the shuffles need whole warps)
+        const int i = i0 + quad;
+        float acc = 0.f;
+        if (i < m) {
+          const float* row = Lp + tri(o + i) + o;
+          for (int j = q; j <= i; j += 4) acc += row[j] * sv[j];
+          for (int j = i + 1 + ((q - (i + 1)) & 3); j < m; j += 4) acc += Lp[tri(o + j) + o + i] * sv[j];
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (q == 0 && i < m) sp[i] = tau * acc;
+      }
+      __syncthreads();
+      float dpart = 0.f;
+      for (int j = tid; j < m; j += TD_THREADS) dpart += sp[j] * sv[j];
+      const float dot = block_sum_1024(dpart, red);
+      const float half = 0.5f * tau * dot;
+      for (int j = tid; j < m; j += TD_THREADS) sw[j] = sp[j] - half * sv[j];
+      __syncthreads();
+      for (int i = quad; i < m; i += TD_THREADS / 4) {         // A22 -= v w^T + w v^T (lower triangle)
+        float* row = Lp + tri(o + i) + o;
+        const float vi = sv[i], wi = sw[i];
+        for (int j = q; j <= i; j += 4) row[j] -= vi * sw[j] + wi * sv[j];
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) {
+    for (int k = (p >= 2 ? p - 2 : 0); k < p; ++k) {
+      dT[(int64_t)b * ldt + k] = Lp[tri(k) + k];
+      eT[(int64_t)b * ldt + k] = (k + 1 < p) ? Lp[tri(k + 1) + k] : gmax_all;
+      tau_out[(int64_t)b * ldt + k] = 0.f;
+    }
+  }
+}
+
+// Apply the reflectors of slice b to the columns of a small matrix held as M[i * s_i + f * s_f] (i < p rows, f < F columns), in place:
+// forward (reverse = 0): M <- H_{p-3} ... H_0 M = Q^T M;  reverse = 1: M <- H_0 ... H_{p-3} M = Q M.  One warp owns a column (the
+// steps of one column need no block barrier); grid (ceil(F / 8), B), block 256.
+__global__ void __launch_bounds__(256) reflectors_small_kernel(const float* __restrict__ V, int ldv, const float* __restrict__ tau, int ldt, int p,
+                                                               float* __restrict__ M, int64_t batch_stride, int64_t s_i, int64_t s_f, int F,
+                                                               int reverse) {
+  __shared__ float col[8][MAX_COLS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y, f = blockIdx.x * 8 + warp;
+  if (f >= F) return;
+  float* Mb = M + (int64_t)b * batch_stride + (int64_t)f * s_f;
+  float* c = col[warp];
+  for (int i = lane; i < p; i += 32) c[i] = Mb[(int64_t)i * s_i];
+  __syncwarp();
+  const float* Vb = V + (int64_t)b * p * ldv;
+  for (int kk = 0; kk + 2 < p; ++kk) {
+    const int k = reverse ? (p - 3 - kk) : kk;
+    const float t = tau[(int64_t)b * ldt + k];
+    if (t == 0.f) continue;
+    const float* v = Vb + (int64_t)k * ldv;
+    float s = 0.f;
+    for (int i = k + 1 + lane; i < p; i += 32) s += v[i] * c[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    s *= t;
+    for (int i = k + 1 + lane; i < p; i += 32) c[i] -= s * v[i];
+    __syncwarp();
+  }
+  for (int i = lane; i < p; i += 32) Mb[(int64_t)i * s_i] = c[i];
+}
+
+// L D L^T of T_b + alpha I for every (slice, alpha) and the reduced-basis solutions x = (T + alpha I)^-1 bt for the F columns of
+// bt = Q^T X^T y ([B][Pp][F]).  One thread per (slice, alpha): the recurrences are sequential in k and tiny.
+// lfac / dinv: [B][A][ldt];  xout: [B][A][F][Pp] (zero beyond p).  A pivot <= pivot_tol * (largest diagonal entry of G + alpha I) flags the slice.
+__global__ void tri_ldl_solve_kernel(const float* __restrict__ dT, const float* __restrict__ eT, int ldt, int p, int Pp, const float* __restrict__ alphas,
+                                     int A, int B, const float* __restrict__ bt, int F, float pivot_tol, float* __restrict__ lfac,
+                                     float* __restrict__ dinv, float* __restrict__ xout, int* __restrict__ status) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * A) return;
+  const int b = e / A, a = e - b * A;
+  const float alpha = alphas[a];
+  const float* d = dT + (int64_t)b * ldt;
+  const float* ev = eT + (int64_t)b * ldt;
+  float* l = lfac + (int64_t)e * ldt;
+  float* di = dinv + (int64_t)e * ldt;
+  const float floor_ = fmaxf((ev[p - 1] + alpha) * pivot_tol, 1e-30f);      // ev[p - 1] = largest diagonal entry of G_b (tridiag_kernel)
+  bool bad = false;
+  float dk = d[0] + alpha;
+  for (int k = 0; k < p; ++k) {
+    if (!(dk > floor_)) { bad = true; dk = floor_; }
+    const float inv = 1.f / dk;
+    di[k] = inv;
+    if (k + 1 < p) {
+      const float lk = ev[k] * inv;
+      l[k] = lk;
+      dk = d[k + 1] + alpha - lk * ev[k];
+    } else {
+      l[k] = 0.f;
+    }
+  }
+  if (bad) atomicOr(&status[b], 1);
+  for (int f = 0; f < F; ++f) {
+    float* x = xout + ((int64_t)e * F + f) * Pp;
+    const float* rhs = bt + (int64_t)b * Pp * F + f;
+    float u = 0.f;
+    for (int k = 0; k < p; ++k) {                 // forward: u_k = b_k - l_{k-1} u_{k-1};  y_k = u_k / d_k
+      u = rhs[(int64_t)k * F] - (k > 0 ? l[k - 1] * u : 0.f);
+      x[k] = u * di[k];
+    }
+    for (int k = p - 2; k >= 0; --k) x[k] -= l[k] * x[k + 1];      // backward
+    for (int k = p; k < Pp; ++k) x[k] = 0.f;
+  }
+}
+
+// grid (ceil(n / 32), B), block 256: a 32-row tile of Xc_b goes to shared memory, all reflectors are applied (Z = Xc Q, written back in
+// place), and the leverages of the tile's rows for every alpha follow from the tridiagonal factors:  d_out[(b A + a) n + i] = 1 - h - c0.
+// The reflector rows arrive through an 8-deep cp.async ring (first version: one global load per step = one L2 round trip per
+// reflector, 71 ms per fold; the step itself is ~80 FMAs per thread).
+constexpr int RA_ROWS = 32;
+constexpr int RA_RING = 8;
+inline size_t rows_apply_smem(int Pp, int p, int A) {
+  return ((size_t)RA_ROWS * (Pp + 1) + (size_t)RA_RING * Pp + (size_t)((p + 3) & ~3) + 2 * (size_t)A * p + 8) * 4;
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__global__ void __launch_bounds__(256) rows_apply_leverage_kernel(float* __restrict__ Xc, int n, int p, int Pp, const float* __restrict__ V, int ldv,
+                                                                  const float* __restrict__ tau, int ldt, const float* __restrict__ lfac,
+                                                                  const float* __restrict__ dinv, int A, float c0, float* __restrict__ d_out) {
+  extern __shared__ __align__(16) float sm[];
+  const int LDT = Pp + 1;
+  float* ring = sm;                                        // [RA_RING][Pp], 16-byte aligned rows (Pp % 16 == 0)
+  float* tile = ring + RA_RING * Pp;
+  float* stau = tile + RA_ROWS * LDT + ((4 - ((RA_ROWS * LDT) & 3)) & 3);
+  float* sl = stau + ((p + 3) & ~3);
+  float* sd = sl + A * p;
+  const int tid = threadIdx.x, b = blockIdx.y, row0 = blockIdx.x * RA_ROWS;
+  float* Xb = Xc + ((int64_t)b * n + row0) * Pp;
+  const int nrows = min(RA_ROWS, n - row0);
+  const float* Vb = V + (int64_t)b * p * ldv;
+  const int nref = p >= 3 ? p - 2 : 0;                     // reflectors 0 .. p - 3
+  const int chunks = Pp / 4;                               // 16-byte chunks of a reflector row (ldv == Pp)
+  auto issue = [&](int k) {                                // reflector k -> ring slot k % RA_RING (one commit group per reflector, possibly empty)
+    if (k < nref && tid < chunks) cp_async16(ring + (k % RA_RING) * Pp + tid * 4, Vb + (int64_t)k * ldv + tid * 4);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int k = 0; k < RA_RING - 1; ++k) issue(k);
+  for (int e = tid; e < RA_ROWS * Pp; e += 256) {
+    const int r = e / Pp, c = e - r * Pp;
+    tile[r * LDT + c] = (r < nrows) ? Xb[(int64_t)r * Pp + c] : 0.f;
+  }
+  for (int e = tid; e < A * p; e += 256) {
+    const int a = e / p, k = e - a * p;
+    sl[e] = lfac[((int64_t)b * A + a) * ldt + k];
+    sd[e] = dinv[((int64_t)b * A + a) * ldt + k];
+  }
+  for (int k = tid; k < p; k += 256) stau[k] = tau[(int64_t)b * ldt + k];
+  // eight lanes per row; lane q8 keeps the row's 16-byte chunks c = q8 (mod 8) in registers (Pp <= 320: at most 10 chunks), so a reflector
+  // costs one 16-byte shared-memory load per four FMAs and no stores (with the tile in shared memory: two loads + a store per FMA pair,
+  // measured 64 ms per fold)
+  const int r = tid >> 3, q8 = tid & 7;
+  constexpr int NCH = MAX_COLS / 32;                        // chunks per lane
+  float4 reg[NCH];
+  __syncthreads();                                          // the tile is complete
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c4 = 4 * (q8 + 8 * i);
+    reg[i] = (c4 < Pp) ? make_float4(tile[r * LDT + c4], tile[r * LDT + c4 + 1], tile[r * LDT + c4 + 2], tile[r * LDT + c4 + 3])
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int k = 0; k < nref; ++k) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(RA_RING - 2) : "memory");      // reflector k has landed (this thread's part)
+    __syncthreads();                                        // ... everybody's part; and step k - 1 is finished everywhere
+    issue(k + RA_RING - 1);                                 // into the slot step k - 1 just released
+    const float t = stau[k];
+    if (t != 0.f) {
+      const float4* sv4 = reinterpret_cast<const float4*>(ring + (k % RA_RING) * Pp);
+      float4 v[NCH];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = q8 + 8 * i;                           // chunk index; v_k is zero up to column k, chunks entirely below are skipped
+        if (4 * c + 3 > k && 4 * c < Pp) {
+          v[i] = sv4[c];
+          s += reg[i].x * v[i].x + reg[i].y * v[i].y + reg[i].z * v[i].z + reg[i].w * v[i].w;
+        }
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s *= t;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = q8 + 8 * i;
+        if (4 * c + 3 > k && 4 * c < Pp) {
+          reg[i].x -= s * v[i].x; reg[i].y -= s * v[i].y; reg[i].z -= s * v[i].z; reg[i].w -= s * v[i].w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {                           // rows back to the tile (leverage phase and write-back read it)
+    const int c4 = 4 * (q8 + 8 * i);
+    if (c4 < Pp) { tile[r * LDT + c4] = reg[i].x; tile[r * LDT + c4 + 1] = reg[i].y; tile[r * LDT + c4 + 2] = reg[i].z; tile[r * LDT + c4 + 3] = reg[i].w; }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  for (int e = tid; e < RA_ROWS * Pp; e += 256) {           // Z back in place
+    const int rr = e / Pp, c = e - rr * Pp;
+    if (rr < nrows) Xb[(int64_t)rr * Pp + c] = tile[rr * LDT + c];
+  }
+  for (int pr = tid; pr < RA_ROWS * A; pr += 256) {         // leverages: lanes = rows (conflict-free tile reads), alpha uniform per warp
+    const int rr = pr & (RA_ROWS - 1), a = pr / RA_ROWS;
+    if (rr >= nrows) continue;
+    const float* z = tile + rr * LDT;
+    const float* l = sl + a * p;
+    const float* di = sd + a * p;
+    float w = 0.f, h = 0.f;
+    for (int k = 0; k < p; ++k) {
+      w = z[k] - (k > 0 ? l[k - 1] * w : 0.f);
+      h += w * w * di[k];
+    }
+    d_out[((int64_t)b * A + a) * n + row0 + rr] = 1.f - h - c0;
+  }
+}
+
+// intercept[b][f] = ybar - <coef[b][f], mu[b]>  (after the coefficients are back in the original basis); one warp per (b, f)
+__global__ void intercept_batched_kernel(const float* __restrict__ coef, const float* __restrict__ mu, const float* __restrict__ ybar, int B, int F,
+                                         int p, int Pp, int fit_intercept, float* __restrict__ intercept) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= B * F) return;
+  const int b = w / F;
+  double m = 0;
+  for (int c = lane; c < p; c += 32) m += (double)coef[(int64_t)w * p + c] * (double)mu[(int64_t)b * Pp + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+  if (lane == 0) intercept[w] = fit_intercept ? (float)((double)ybar[w] - m) : 0.f;
 }
 
 // compact copy of the centred Grams: out[b][p][p] <- G[b][Pp][Pp]

@@ -937,10 +937,17 @@ int predict_impl(const mvb_design* d, const T* coef, const T* intercept, int F, 
 // ---- batched small dense LOO ridge (dense_batched.cuh) ------------------------------------------------------
 struct DenseWs {
   float *Xc, *Yc, *mu, *ybar, *G, *XtY, *Li, *rowsq, *beta, *R, *d;
+  float *dT, *eT, *tau, *V, *lfac, *dinv;          // tridiagonal route
   double* partial;
   int64_t *roffX, *roffXt, *koffN, *iota, *roffLi, *roffBeta;
   int Pp, tri_rows, tiles_per_alpha, slabs;
 };
+
+// 1: one Householder tridiagonalisation per slice (default); 0: one Cholesky factor + inverse + leverage product per (slice, alpha)
+bool dense_route_tridiag() {
+  static const bool on = [] { const char* e = getenv("MVB_DENSE_ROUTE"); return !e || strcmp(e, "chol") != 0; }();
+  return on;
+}
 
 void carve_dense(Arena& ar, int B, int n, int p, int F, int A, DenseWs& w) {
   const int Pp = (p + mvb::db::NB - 1) / mvb::db::NB * mvb::db::NB;
@@ -954,8 +961,15 @@ void carve_dense(Arena& ar, int B, int n, int p, int F, int A, DenseWs& w) {
   w.ybar = ar.take<float>((int64_t)B * F);
   w.G = ar.take<float>((int64_t)B * Pp * Pp);
   w.XtY = ar.take<float>((int64_t)B * Pp * F);
-  w.Li = ar.take<float>((int64_t)B * A * tri_rows * Pp);
-  w.rowsq = ar.take<float>((int64_t)A * w.tiles_per_alpha * mvb::TC_ROWSQ_PARTS * B * n);
+  const bool tri_route = dense_route_tridiag();
+  w.Li = ar.take<float>(tri_route ? 0 : (int64_t)B * A * tri_rows * Pp);
+  w.rowsq = ar.take<float>(tri_route ? 0 : (int64_t)A * w.tiles_per_alpha * mvb::TC_ROWSQ_PARTS * B * n);
+  w.dT = ar.take<float>(tri_route ? (int64_t)B * Pp : 0);
+  w.eT = ar.take<float>(tri_route ? (int64_t)B * Pp : 0);
+  w.tau = ar.take<float>(tri_route ? (int64_t)B * Pp : 0);
+  w.V = ar.take<float>(tri_route ? (int64_t)B * p * Pp : 0);
+  w.lfac = ar.take<float>(tri_route ? (int64_t)B * A * Pp : 0);
+  w.dinv = ar.take<float>(tri_route ? (int64_t)B * A * Pp : 0);
   w.beta = ar.take<float>((int64_t)B * AF * Pp);
   w.R = ar.take<float>((int64_t)B * n * AF);
   w.d = ar.take<float>((int64_t)B * A * n);
@@ -1031,6 +1045,48 @@ int dense_ridge_batched_impl(const mvb_strided* X, const mvb_strided* Y, const i
   if (gram) {
     db::copy_gram_kernel<<<grid_for((int64_t)B * p * p), 256, 0, st>>>(w.G, B, p, Pp, gram);
     MVB_LAUNCHED();
+  }
+  if (dense_route_tridiag()) {
+    // 3'. one orthogonal reduction per slice: G = Q T Q^T;  Q^T X^T y;  L D L^T of T + alpha I and the reduced-basis solutions;
+    //     Z = Xc Q in place with the leverages of every alpha from the tridiagonal factors
+    static std::once_flag tri_once;
+    static cudaError_t tri_err = cudaSuccess;
+    std::call_once(tri_once, [] {
+      tri_err = cudaFuncSetAttribute(db::tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)db::tridiag_smem(db::MAX_COLS));
+      if (tri_err == cudaSuccess)
+        tri_err = cudaFuncSetAttribute(db::rows_apply_leverage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    });
+    MVB_CUDA(tri_err);
+    const size_t ra_smem = db::rows_apply_smem(Pp, p, A);
+    if (ra_smem > 160 * 1024) return fail(MVB_E_UNSUPPORTED, "dense_ridge_batched: %d alphas x %d columns exceed the tridiagonal route's shared memory", A, p);
+    db::tridiag_kernel<<<B, db::TD_THREADS, db::tridiag_smem(p), st>>>(w.G, p, Pp, w.dT, w.eT, Pp, w.V, Pp, w.tau);
+    MVB_LAUNCHED();
+    db::reflectors_small_kernel<<<dim3(cdiv(F, 8), B), 256, 0, st>>>(w.V, Pp, w.tau, Pp, p, w.XtY, (int64_t)Pp * F, F, 1, F, 0);
+    MVB_LAUNCHED();
+    db::tri_ldl_solve_kernel<<<cdiv((int64_t)B * A, 128), 128, 0, st>>>(w.dT, w.eT, Pp, p, Pp, alphas, A, B, w.XtY, F, 1e-4f, w.lfac, w.dinv, w.beta, status);
+    MVB_LAUNCHED();
+    db::rows_apply_leverage_kernel<<<dim3(cdiv(n, db::RA_ROWS), B), 256, ra_smem, st>>>(w.Xc, n, p, Pp, w.V, Pp, w.tau, Pp, w.lfac, w.dinv, A,
+                                                                                         fit_intercept ? 1.f / (float)n : 0.f, w.d);
+    MVB_LAUNCHED();
+    {
+      mvb::TcGemmParams g = mvb::tc_gemm_defaults();
+      g.A = {w.Xc, w.roffX, w.iota, n, 2};                 // Z, in place of Xc
+      g.B = {w.beta, w.roffBeta, w.iota, AF, 2};
+      g.M = n; g.N = AF; g.K = Pp; g.C = w.R; g.ldc = AF; g.batch = B;
+      g.a_roff_batch = n; g.b_roff_batch = AF; g.c_batch_stride = (int64_t)n * AF;
+      int rc = dense_batched_launch(g, AF > 128 ? 256 : 128, PC_RESIDUAL, 2.0 * n * (double)AF * Pp * B, st);
+      if (rc) return rc;
+    }
+    db::loss_kernel<<<dim3(B, w.slabs), 128, 0, st>>>(w.R, w.Yc, w.d, n, A, F, w.slabs, w.partial);
+    MVB_LAUNCHED();
+    db::select_kernel<<<B, 256, (size_t)(AF + F) * 4, st>>>(w.partial, w.slabs, n, A, F, p, Pp, alphas, per_target, fit_intercept, w.beta, nullptr,
+                                                           w.ybar, loss, best, alpha_out, coef, intercept);
+    MVB_LAUNCHED();
+    db::reflectors_small_kernel<<<dim3(cdiv(F, 8), B), 256, 0, st>>>(w.V, Pp, w.tau, Pp, p, coef, (int64_t)F * p, 1, p, F, 1);      // coef = Q x
+    MVB_LAUNCHED();
+    db::intercept_batched_kernel<<<cdiv((int64_t)B * F * 32, 256), 256, 0, st>>>(coef, w.mu, w.ybar, B, F, p, Pp, fit_intercept, intercept);
+    MVB_LAUNCHED();
+    return MVB_OK;
   }
   // 3. per (slice, alpha): Cholesky factor and its inverse
   db::chol_inv_kernel<<<B * A, db::CI_THREADS, db::chol_inv_smem(Pp), st>>>(w.G, p, Pp, alphas, A, 1e-4f, w.Li, w.tri_rows, status);
