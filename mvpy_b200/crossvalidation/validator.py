@@ -62,7 +62,11 @@ def _move_tensors(obj: Any, device: torch.device, _seen=None) -> Any:
             _move_tensors(step, device, _seen)
         return obj
     if isinstance(obj, (sklearn.base.BaseEstimator, Metric)):
+        stacked = getattr(obj, '_stacked', None)
         for k, v in list(vars(obj).items()):
+            if k == 'estimators_' and stacked is not None and isinstance(v, list) and v and stacked[0].device == device \
+                    and getattr(v[0], 'coef_', None) is not None and v[0].coef_.device == device:
+                continue        # a batched Sliding fit: hundreds of per-slice views of a few stacked arrays that already live on `device`
             if isinstance(v, torch.Tensor) and k.startswith('_'):
                 setattr(obj, k, None)              # private device scratch (cached Gram) is dropped
             elif isinstance(v, (torch.Tensor, list, tuple, dict, sklearn.base.BaseEstimator, Pipeline, Metric)):

@@ -1,4 +1,6 @@
 // dense_batched.cuh -- B independent dense leave-one-out ridge problems of one shape in a handful of launches.
+// Two routes behind mvb_dense_ridge_batched: the tridiagonal route (second half of this file, default) and the Cholesky route
+// described first (MVB_DENSE_ROUTE=chol).
 //
 // Replaces the per-slice estimator loop of _Sliding_torch.fit (mvpy/estimators/sliding.py:575-622) around
 // _RidgeCV_torch.fit (mvpy/estimators/ridgecv.py:96-303): per-timepoint decoding (BASELINE configs[4]: 500 slices of a
@@ -776,6 +778,7 @@ inline size_t rows_apply_smem(int Pp, int p, int A) {
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
+__device__ long long g_ra_clk[4];       // developer timing: cycles of block (0, 0) in load / reflectors / write-back / leverages (tools/tri_phases.py)
 __global__ void __launch_bounds__(256) rows_apply_leverage_kernel(float* __restrict__ Xc, int n, int p, int Pp, const float* __restrict__ V, int ldv,
                                                                   const float* __restrict__ tau, int ldt, const float* __restrict__ lfac,
                                                                   const float* __restrict__ dinv, int A, float c0, float* __restrict__ d_out) {
@@ -787,6 +790,9 @@ __global__ void __launch_bounds__(256) rows_apply_leverage_kernel(float* __restr
   float* sl = stau + ((p + 3) & ~3);
   float* sd = sl + A * p;
   const int tid = threadIdx.x, b = blockIdx.y, row0 = blockIdx.x * RA_ROWS;
+  const bool timed = blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+  long long t_last = timed ? clock64() : 0;
+  auto tick = [&](int ph) { if (timed) { const long long t = clock64(); g_ra_clk[ph] = t - t_last; t_last = t; } };
   float* Xb = Xc + ((int64_t)b * n + row0) * Pp;
   const int nrows = min(RA_ROWS, n - row0);
   const float* Vb = V + (int64_t)b * p * ldv;
@@ -814,6 +820,7 @@ __global__ void __launch_bounds__(256) rows_apply_leverage_kernel(float* __restr
   constexpr int NCH = MAX_COLS / 32;                        // chunks per lane
   float4 reg[NCH];
   __syncthreads();                                          // the tile is complete
+  tick(0);
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
     const int c4 = 4 * (q8 + 8 * i);
@@ -857,10 +864,12 @@ __global__ void __launch_bounds__(256) rows_apply_leverage_kernel(float* __restr
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  tick(1);
   for (int e = tid; e < RA_ROWS * Pp; e += 256) {           // Z back in place
     const int rr = e / Pp, c = e - rr * Pp;
     if (rr < nrows) Xb[(int64_t)rr * Pp + c] = tile[rr * LDT + c];
   }
+  tick(2);
   for (int pr = tid; pr < RA_ROWS * A; pr += 256) {         // leverages: lanes = rows (conflict-free tile reads), alpha uniform per warp
     const int rr = pr & (RA_ROWS - 1), a = pr / RA_ROWS;
     if (rr >= nrows) continue;
@@ -874,6 +883,7 @@ __global__ void __launch_bounds__(256) rows_apply_leverage_kernel(float* __restr
     }
     d_out[((int64_t)b * A + a) * n + row0 + rr] = 1.f - h - c0;
   }
+  tick(3);
 }
 
 // intercept[b][f] = ybar - <coef[b][f], mu[b]>  (after the coefficients are back in the original basis); one warp per (b, f)

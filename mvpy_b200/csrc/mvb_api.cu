@@ -1367,6 +1367,13 @@ int mvb_dev_skinny(const float* A, const float* B, int N, int K, int splits, int
   return MVB_OK;
 }
 
+// developer entry (not in include/mvb.h; tools/tri_phases.py): per-phase cycles of block (0, 0) of the last rows_apply_leverage_kernel launch
+int mvb_dev_rows_apply_phases(long long* host_out) {
+  MVB_CUDA(cudaDeviceSynchronize());
+  MVB_CUDA(cudaMemcpyFromSymbol(host_out, mvb::db::g_ra_clk, 4 * sizeof(long long)));
+  return MVB_OK;
+}
+
 // developer entry (not in include/mvb.h; tools/chol_inv_phases.py): the factorisation kernel alone with per-phase cycle counters
 int mvb_dev_chol_inv(const float* G, int p, int batch, const float* alphas, int n_alphas, float* Li, int* status, long long* phase_clk,
                      void* stream) {
