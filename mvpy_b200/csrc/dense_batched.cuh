@@ -781,7 +781,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ long long g_ra_clk[4];       // developer timing: cycles of block (0, 0) in load / reflectors / write-back / leverages (tools/tri_phases.py)
 __global__ void __launch_bounds__(256) rows_apply_leverage_kernel(float* __restrict__ Xc, int n, int p, int Pp, const float* __restrict__ V, int ldv,
                                                                   const float* __restrict__ tau, int ldt, const float* __restrict__ lfac,
-                                                                  const float* __restrict__ dinv, int A, float c0, float* __restrict__ d_out) {
+                                                                  const float* __restrict__ dinv, int A, float c0, float* __restrict__ d_out,
+                                                                  int apply) {
+  // apply = 1: reflectors + write-back (+ leverages when A > 0);  apply = 0: the rows already are in the reduced basis, leverages only
   extern __shared__ __align__(16) float sm[];
   const int LDT = Pp + 1;
   float* ring = sm;                                        // [RA_RING][Pp], 16-byte aligned rows (Pp % 16 == 0)
@@ -796,7 +798,7 @@ __global__ void __launch_bounds__(256) rows_apply_leverage_kernel(float* __restr
   float* Xb = Xc + ((int64_t)b * n + row0) * Pp;
   const int nrows = min(RA_ROWS, n - row0);
   const float* Vb = V + (int64_t)b * p * ldv;
-  const int nref = p >= 3 ? p - 2 : 0;                     // reflectors 0 .. p - 3
+  const int nref = (apply && p >= 3) ? p - 2 : 0;          // reflectors 0 .. p - 3
   const int chunks = Pp / 4;                               // 16-byte chunks of a reflector row (ldv == Pp)
   auto issue = [&](int k) {                                // reflector k -> ring slot k % RA_RING (one commit group per reflector, possibly empty)
     if (k < nref && tid < chunks) cp_async16(ring + (k % RA_RING) * Pp + tid * 4, Vb + (int64_t)k * ldv + tid * 4);
@@ -865,10 +867,11 @@ __global__ void __launch_bounds__(256) rows_apply_leverage_kernel(float* __restr
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   tick(1);
-  for (int e = tid; e < RA_ROWS * Pp; e += 256) {           // Z back in place
-    const int rr = e / Pp, c = e - rr * Pp;
-    if (rr < nrows) Xb[(int64_t)rr * Pp + c] = tile[rr * LDT + c];
-  }
+  if (apply)
+    for (int e = tid; e < RA_ROWS * Pp; e += 256) {         // Z back in place
+      const int rr = e / Pp, c = e - rr * Pp;
+      if (rr < nrows) Xb[(int64_t)rr * Pp + c] = tile[rr * LDT + c];
+    }
   tick(2);
   for (int pr = tid; pr < RA_ROWS * A; pr += 256) {         // leverages: lanes = rows (conflict-free tile reads), alpha uniform per warp
     const int rr = pr & (RA_ROWS - 1), a = pr / RA_ROWS;
@@ -884,6 +887,24 @@ __global__ void __launch_bounds__(256) rows_apply_leverage_kernel(float* __restr
     d_out[((int64_t)b * A + a) * n + row0 + rr] = 1.f - h - c0;
   }
   tick(3);
+}
+
+// gather tables of the basis-change product: roffQ[b][k] = b Pp^2 + k (row k' of the B operand = column k' of Q_b), koffQ[j] = j Pp
+__global__ void dense_q_tables_kernel(int B, int Pp, int64_t* __restrict__ roffQ, int64_t* __restrict__ koffQ) {
+  const int64_t total = (int64_t)B * Pp;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    roffQ[e] = (e / Pp) * (int64_t)Pp * Pp + (e % Pp);
+    if (e < Pp) koffQ[e] = e * (int64_t)Pp;
+  }
+}
+
+// Q workspace: B identity matrices [Pp][Pp] (rows >= p stay zero rows with a unit diagonal: they are never read as real columns)
+__global__ void identity_batched_kernel(float* __restrict__ Q, int B, int Pp) {
+  const int64_t total = (int64_t)B * Pp * Pp;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % Pp), r = (int)((e / Pp) % Pp);
+    Q[e] = (r == c) ? 1.f : 0.f;
+  }
 }
 
 // intercept[b][f] = ybar - <coef[b][f], mu[b]>  (after the coefficients are back in the original basis); one warp per (b, f)

@@ -937,7 +937,8 @@ int predict_impl(const mvb_design* d, const T* coef, const T* intercept, int F, 
 // ---- batched small dense LOO ridge (dense_batched.cuh) ------------------------------------------------------
 struct DenseWs {
   float *Xc, *Yc, *mu, *ybar, *G, *XtY, *Li, *rowsq, *beta, *R, *d;
-  float *dT, *eT, *tau, *V, *lfac, *dinv;          // tridiagonal route
+  float *dT, *eT, *tau, *V, *lfac, *dinv, *Q, *Z;  // tridiagonal route (Q, Z: explicit basis + tensor-core basis change)
+  int64_t *roffQ, *koffQ, *roffZ;
   double* partial;
   int64_t *roffX, *roffXt, *koffN, *iota, *roffLi, *roffBeta;
   int Pp, tri_rows, tiles_per_alpha, slabs;
@@ -946,6 +947,13 @@ struct DenseWs {
 // 1: one Householder tridiagonalisation per slice (default); 0: one Cholesky factor + inverse + leverage product per (slice, alpha)
 bool dense_route_tridiag() {
   static const bool on = [] { const char* e = getenv("MVB_DENSE_ROUTE"); return !e || strcmp(e, "chol") != 0; }();
+  return on;
+}
+
+// tridiagonal route: 1 (default) = the reflectors are applied to the identity (Pp rows per slice) and Z = Xc Q comes from the batched
+// tensor-core product; 0 = the reflectors are applied to every row tile of Xc (fp32 FMA work on n rows per slice)
+bool dense_explicit_q() {
+  static const bool on = [] { const char* e = getenv("MVB_DENSE_EXPLICIT_Q"); return !e || atoi(e) != 0; }();
   return on;
 }
 
@@ -970,6 +978,11 @@ void carve_dense(Arena& ar, int B, int n, int p, int F, int A, DenseWs& w) {
   w.V = ar.take<float>(tri_route ? (int64_t)B * p * Pp : 0);
   w.lfac = ar.take<float>(tri_route ? (int64_t)B * A * Pp : 0);
   w.dinv = ar.take<float>(tri_route ? (int64_t)B * A * Pp : 0);
+  const bool explicit_q = tri_route && dense_explicit_q();
+  w.Q = ar.take<float>(explicit_q ? (int64_t)B * Pp * Pp : 0);
+  w.Z = ar.take<float>(explicit_q ? (int64_t)B * n * Pp : 0);
+  w.roffQ = ar.take<int64_t>(explicit_q ? (int64_t)B * Pp : 0);
+  w.koffQ = ar.take<int64_t>(explicit_q ? Pp : 0);
   w.beta = ar.take<float>((int64_t)B * AF * Pp);
   w.R = ar.take<float>((int64_t)B * n * AF);
   w.d = ar.take<float>((int64_t)B * A * n);
@@ -1065,12 +1078,34 @@ int dense_ridge_batched_impl(const mvb_strided* X, const mvb_strided* Y, const i
     MVB_LAUNCHED();
     db::tri_ldl_solve_kernel<<<cdiv((int64_t)B * A, 128), 128, 0, st>>>(w.dT, w.eT, Pp, p, Pp, alphas, A, B, w.XtY, F, 1e-4f, w.lfac, w.dinv, w.beta, status);
     MVB_LAUNCHED();
-    db::rows_apply_leverage_kernel<<<dim3(cdiv(n, db::RA_ROWS), B), 256, ra_smem, st>>>(w.Xc, n, p, Pp, w.V, Pp, w.tau, Pp, w.lfac, w.dinv, A,
-                                                                                         fit_intercept ? 1.f / (float)n : 0.f, w.d);
-    MVB_LAUNCHED();
+    const float c0 = fit_intercept ? 1.f / (float)n : 0.f;
+    float* Zrows = w.Xc;
+    if (dense_explicit_q()) {
+      // Q = I H_0 H_1 ... (the reflectors applied to Pp identity rows per slice), then Z = Xc Q on the tensor cores, then the leverages
+      db::identity_batched_kernel<<<grid_for((int64_t)B * Pp * Pp), 256, 0, st>>>(w.Q, B, Pp);
+      MVB_LAUNCHED();
+      db::rows_apply_leverage_kernel<<<dim3(cdiv(Pp, db::RA_ROWS), B), 256, ra_smem, st>>>(w.Q, Pp, p, Pp, w.V, Pp, w.tau, Pp, w.lfac, w.dinv, 0, 0.f,
+                                                                                            nullptr, 1);
+      MVB_LAUNCHED();
+      db::dense_q_tables_kernel<<<grid_for((int64_t)B * Pp), 256, 0, st>>>(B, Pp, w.roffQ, w.koffQ);
+      MVB_LAUNCHED();
+      mvb::TcGemmParams g = mvb::tc_gemm_defaults();
+      g.A = {w.Xc, w.roffX, w.iota, n, 2};
+      g.B = {w.Q, w.roffQ, w.koffQ, Pp, 0};                // B(k', j) = Q[j][k']: rows k' contiguous, contraction j strides Pp
+      g.M = n; g.N = Pp; g.K = Pp; g.C = w.Z; g.ldc = Pp; g.batch = B;
+      g.a_roff_batch = n; g.b_roff_batch = Pp; g.c_batch_stride = (int64_t)n * Pp;
+      int rc = dense_batched_launch(g, Pp > 128 ? 256 : 128, PC_LEVERAGE_Z, 2.0 * n * (double)Pp * Pp * B, st);
+      if (rc) return rc;
+      Zrows = w.Z;
+      db::rows_apply_leverage_kernel<<<dim3(cdiv(n, db::RA_ROWS), B), 256, ra_smem, st>>>(w.Z, n, p, Pp, w.V, Pp, w.tau, Pp, w.lfac, w.dinv, A, c0, w.d, 0);
+      MVB_LAUNCHED();
+    } else {
+      db::rows_apply_leverage_kernel<<<dim3(cdiv(n, db::RA_ROWS), B), 256, ra_smem, st>>>(w.Xc, n, p, Pp, w.V, Pp, w.tau, Pp, w.lfac, w.dinv, A, c0, w.d, 1);
+      MVB_LAUNCHED();
+    }
     {
       mvb::TcGemmParams g = mvb::tc_gemm_defaults();
-      g.A = {w.Xc, w.roffX, w.iota, n, 2};                 // Z, in place of Xc
+      g.A = {Zrows, w.roffX, w.iota, n, 2};                // Z (in place of Xc, or the product's output: same row layout)
       g.B = {w.beta, w.roffBeta, w.iota, AF, 2};
       g.M = n; g.N = AF; g.K = Pp; g.C = w.R; g.ldc = AF; g.batch = B;
       g.a_roff_batch = n; g.b_roff_batch = AF; g.c_batch_stride = (int64_t)n * AF;
