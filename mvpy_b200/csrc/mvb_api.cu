@@ -945,9 +945,12 @@ struct DenseWs {
 };
 
 // 1: one Householder tridiagonalisation per slice (default); 0: one Cholesky factor + inverse + leverage product per (slice, alpha)
-bool dense_route_tridiag() {
+bool dense_route_tridiag(int p, int A) {
   static const bool on = [] { const char* e = getenv("MVB_DENSE_ROUTE"); return !e || strcmp(e, "chol") != 0; }();
-  return on;
+  // the leverage kernel keeps the L D L^T factors of all alphas of a slice in shared memory next to a row tile: very long alpha grids
+  // (2 A p floats beyond ~100 KB) take the Cholesky route, whose work is per alpha anyway
+  const int Pp = (p + mvb::db::NB - 1) / mvb::db::NB * mvb::db::NB;
+  return on && mvb::db::rows_apply_smem(Pp, p, A) <= (size_t)160 * 1024;
 }
 
 // tridiagonal route: 1 (default) = the reflectors are applied to the identity (Pp rows per slice) and Z = Xc Q comes from the batched
@@ -969,7 +972,7 @@ void carve_dense(Arena& ar, int B, int n, int p, int F, int A, DenseWs& w) {
   w.ybar = ar.take<float>((int64_t)B * F);
   w.G = ar.take<float>((int64_t)B * Pp * Pp);
   w.XtY = ar.take<float>((int64_t)B * Pp * F);
-  const bool tri_route = dense_route_tridiag();
+  const bool tri_route = dense_route_tridiag(p, A);
   w.Li = ar.take<float>(tri_route ? 0 : (int64_t)B * A * tri_rows * Pp);
   w.rowsq = ar.take<float>(tri_route ? 0 : (int64_t)A * w.tiles_per_alpha * mvb::TC_ROWSQ_PARTS * B * n);
   w.dT = ar.take<float>(tri_route ? (int64_t)B * Pp : 0);
@@ -1059,7 +1062,7 @@ int dense_ridge_batched_impl(const mvb_strided* X, const mvb_strided* Y, const i
     db::copy_gram_kernel<<<grid_for((int64_t)B * p * p), 256, 0, st>>>(w.G, B, p, Pp, gram);
     MVB_LAUNCHED();
   }
-  if (dense_route_tridiag()) {
+  if (dense_route_tridiag(p, A)) {
     // 3'. one orthogonal reduction per slice: G = Q T Q^T;  Q^T X^T y;  L D L^T of T + alpha I and the reduced-basis solutions;
     //     Z = Xc Q in place with the leverages of every alpha from the tridiagonal factors
     static std::once_flag tri_once;
@@ -1071,7 +1074,6 @@ int dense_ridge_batched_impl(const mvb_strided* X, const mvb_strided* Y, const i
     });
     MVB_CUDA(tri_err);
     const size_t ra_smem = db::rows_apply_smem(Pp, p, A);
-    if (ra_smem > 160 * 1024) return fail(MVB_E_UNSUPPORTED, "dense_ridge_batched: %d alphas x %d columns exceed the tridiagonal route's shared memory", A, p);
     db::tridiag_kernel<<<B, db::TD_THREADS, db::tridiag_smem(p), st>>>(w.G, p, Pp, w.dT, w.eT, Pp, w.V, Pp, w.tau);
     MVB_LAUNCHED();
     db::reflectors_small_kernel<<<dim3(cdiv(F, 8), B), 256, 0, st>>>(w.V, Pp, w.tau, Pp, p, w.XtY, (int64_t)Pp * F, F, 1, F, 0);

@@ -745,6 +745,27 @@ def test_sliding_batched_other_layouts(monkeypatch):
             np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=0, atol=2e-4 * float(a.abs().max()))
 
 
+def test_dense_ridge_batched_long_alpha_grid_takes_the_cholesky_route(monkeypatch):
+    """64 alphas x 306 columns: the tridiagonal route's per-slice factor table no longer fits next to a row tile, the call takes the
+    per-alpha Cholesky route (also reachable with MVB_DENSE_ROUTE=chol) -- same answers as the per-slice loop."""
+    from mvpy_b200 import _lib
+    mv = _mv()
+    g = torch.Generator().manual_seed(33)
+    n, p, f, t = 700, 306, 2, 4
+    X = torch.randn(n, p, t, generator=g).cuda()
+    y = (torch.einsum('npt,pf->nft', X.cpu(), torch.randn(p, f, generator=g) * 0.1) + torch.randn(n, f, t, generator=g)).cuda()
+    al = torch.logspace(-3, 4, 64)
+    monkeypatch.setenv('MVB_SLIDING_GRAPHS', '0')
+    n0 = _lib.launch_count()
+    batched = mv.estimators.Sliding(mv.estimators.RidgeCV(alphas=al, alpha_per_target=True), dims=-1).fit(X, y)
+    assert _lib.launch_count() - n0 < 40
+    monkeypatch.setenv('MVB_SLIDING_BATCHED', '0')
+    eager = mv.estimators.Sliding(mv.estimators.RidgeCV(alphas=al, alpha_per_target=True), dims=-1).fit(X, y)
+    assert torch.equal(batched.collect('alpha_'), eager.collect('alpha_'))
+    ce = eager.collect('coef_').cpu().numpy()
+    np.testing.assert_allclose(batched.collect('coef_').cpu().numpy(), ce, rtol=0, atol=2e-4 * np.abs(ce).max())
+
+
 def test_dense_ridge_batched_hands_rank_deficient_slices_to_the_general_route(monkeypatch):
     """A slice whose Gram + alpha I is numerically singular at the small alphas (two identical channels) is flagged by the
     batched factorisation (status != 0) and refitted on the guarded route; the other slices are untouched."""
