@@ -61,6 +61,23 @@ __global__ void means_kernel(View v, const int32_t* __restrict__ idx, int n, int
   }
 }
 
+// the same for few columns (the targets: 3 x 500 at configs[4]): one warp per (slice, column), lanes over the samples -- the
+// thread-per-column kernel above would walk 1600 samples with 1500 threads (0.58 ms of latency)
+__global__ void means_warp_kernel(View v, const int32_t* __restrict__ idx, int n, int ncol, int B, int centre, float* __restrict__ out, int ldo) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (int64_t)ncol * B) return;
+  const int b = (int)(w / ncol), c = (int)(w % ncol);
+  double s = 0;
+  if (centre) {
+    const float* src = v.base + (int64_t)b * v.s_batch + (int64_t)c * v.s_col;
+    for (int i = lane; i < n; i += 32) s += (double)__ldg(src + (int64_t)(idx ? idx[i] : i) * v.s_sample);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[(int64_t)b * ldo + c] = (float)(s / (double)n);
+}
+
 // out[(b * n + i) * ld + c] = X_b[idx[i], c] - mean[b * ldm + c]  (c < ncol), 0 for the padding columns.
 // grid (ceil(ld / 32), ceil(B / 32), n), block (32, 8): a 32 x 32 (column, slice) tile of one sample goes through shared
 // memory so that both the strided source (slices contiguous for a Sliding view) and the destination are read / written in rows.
@@ -606,6 +623,7 @@ __device__ __forceinline__ float block_sum_1024(float v, float* red) {
 // y_i += A_ij v_j (row sum, reduced by shuffles) and y_j += A_ij v_i (kept per lane in registers, the 32 warps' partial vectors are
 // combined through an 8-row buffer in four fixed rounds: deterministic).  First version (four lanes per row walking the row and
 // the column of the packed triangle): 16 000 cycles per step, 8.5 ms per fold.
+__device__ long long g_td_clk[8];       // developer timing: cycles of block 0 per phase, summed over the steps (tools/tri_phases.py)
 __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(const float* __restrict__ G, int p, int Pp, float* __restrict__ dT,
                                                                 float* __restrict__ eT, int ldt, float* __restrict__ V, int ldv,
                                                                 float* __restrict__ tau_out) {
@@ -641,6 +659,9 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(const float* __r
   }
   __syncthreads();
   const float gmax_all = red[40];
+  const bool timed = blockIdx.x == 0 && tid == 0;
+  long long t_last = timed ? clock64() : 0, acc_clk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto tick = [&](int ph) { if (timed) { const long long t = clock64(); acc_clk[ph] += t - t_last; t_last = t; } };
   for (int k = 0; k + 2 < p; ++k) {
     const int o = k + 1, m = p - o;
     // column k below the diagonal
@@ -651,6 +672,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(const float* __r
       if (j >= 1) ssq += x * x;
     }
     const float xnorm2 = block_sum_1024(ssq, red);           // (its barriers also publish sv)
+    tick(0);
     const float alpha0 = sv[0];
     float tau = 0.f, beta = alpha0, scale = 0.f;
     if (xnorm2 > 0.f) {
@@ -670,6 +692,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(const float* __r
       tau_out[(int64_t)b * ldt + k] = tau;
     }
     __syncthreads();
+    tick(1);
     if (tau != 0.f) {                                          // (uniform: every thread computed the same tau)
       float vr[TD_NC], yc[TD_NC];
 #pragma unroll
@@ -696,6 +719,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(const float* __r
       // the 32 warps' column parts, eight at a time into an 8-row buffer (fixed order)
       for (int round = 0; round < 4; ++round) {
         __syncthreads();
+        if (round == 0) tick(2);
         if ((warp >> 3) == round) {
           float* dst = part + (warp & 7) * pa;
 #pragma unroll
@@ -715,10 +739,12 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(const float* __r
         sp[j] = s2;
         dpart += s2 * sv[j];
       }
+      tick(3);
       const float dot = block_sum_1024(dpart, red);
       const float half = 0.5f * tau * dot;
       for (int j = tid; j < m; j += TD_THREADS) sw[j] = sp[j] - half * sv[j];
       __syncthreads();
+      tick(4);
       // ---- A22 -= v w^T + w v^T (lower triangle), same row / lane ownership ----
       float wr[TD_NC];
 #pragma unroll
@@ -734,8 +760,10 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(const float* __r
         }
       }
       __syncthreads();
+      tick(5);
     }
   }
+  if (timed) for (int i = 0; i < 8; ++i) g_td_clk[i] = acc_clk[i];
   if (tid == 0) {
     for (int k = (p >= 2 ? p - 2 : 0); k < p; ++k) {
       dT[(int64_t)b * ldt + k] = Lp[tri(k) + k];

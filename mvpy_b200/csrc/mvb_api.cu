@@ -1040,7 +1040,8 @@ int dense_ridge_batched_impl(const mvb_strided* X, const mvb_strided* Y, const i
   // 1. centring before multiplying (ridgecv.py:59-94) + slice-major packing
   db::means_kernel<<<grid_for((int64_t)p * B), 256, 0, st>>>(xv, sample_idx, n, p, B, fit_intercept, w.mu, Pp);
   MVB_LAUNCHED();
-  db::means_kernel<<<grid_for((int64_t)F * B), 256, 0, st>>>(yv, sample_idx, n, F, B, fit_intercept, w.ybar, F);
+  if ((int64_t)F * B < 65536) db::means_warp_kernel<<<cdiv((int64_t)F * B * 32, 256), 256, 0, st>>>(yv, sample_idx, n, F, B, fit_intercept, w.ybar, F);
+  else db::means_kernel<<<grid_for((int64_t)F * B), 256, 0, st>>>(yv, sample_idx, n, F, B, fit_intercept, w.ybar, F);
   MVB_LAUNCHED();
   db::pack_kernel<<<dim3(cdiv(Pp, 32), cdiv(B, 32), n), dim3(32, 8), 0, st>>>(xv, sample_idx, n, p, B, w.mu, Pp, w.Xc, Pp);
   MVB_LAUNCHED();
@@ -1408,6 +1409,7 @@ int mvb_dev_skinny(const float* A, const float* B, int N, int K, int splits, int
 int mvb_dev_rows_apply_phases(long long* host_out) {
   MVB_CUDA(cudaDeviceSynchronize());
   MVB_CUDA(cudaMemcpyFromSymbol(host_out, mvb::db::g_ra_clk, 4 * sizeof(long long)));
+  MVB_CUDA(cudaMemcpyFromSymbol(host_out + 4, mvb::db::g_td_clk, 8 * sizeof(long long)));      // + the tridiagonalisation's phases
   return MVB_OK;
 }
 
