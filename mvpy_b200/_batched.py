@@ -89,15 +89,28 @@ def fit_slices(proto, Xm: torch.Tensor, ym: torch.Tensor, pairs: Sequence[Tuple[
     coef_o, icpt_o, alpha_o, loss_o = coef.to(out_dev), icpt.to(out_dev), alpha.to(out_dev), loss.to(out_dev)
     pattern_o = None if pattern is None else pattern.to(out_dev)
     al_o = al.to(out_dev)
-    # per-slice views of the stacked results, made by five unbind calls instead of thousands of Python-level indexing operations
-    coef_v, alpha_v, loss_v = coef_o.unbind(0), alpha_o.unbind(0), loss_o.unbind(0)
-    icpt_v = icpt_o[:, None, :].unbind(0) if fit_intercept else None
-    pattern_v = pattern_o.unbind(0) if pattern_o is not None else None
-    fitted = []
-    for b in range(B):
-        est = proto.clone()
+    stack = dict(kind=kind, per_target=per_target, fit_intercept=fit_intercept, alphas=al_o, coef=coef_o, alpha=alpha_o, loss=loss_o,
+                 icpt=icpt_o, pattern=pattern_o)
+    fitted = [proto.clone() for _ in range(B)]
+    assign_views(fitted, stack)
+    for b in bad:                                                # rank-deficient / badly scaled slices: the guarded general route
+        fitted[b] = proto.clone().fit(Xm[..., xi[b]], ym[..., yi[b]])
+    # the stacked parameters stay with the caller so that predict needs no re-stacking (only when every slice came from here);
+    # `stack` (all per-slice attributes as stacked arrays) lets a driver move the whole list to another device with a few copies
+    stacked = None if bad else (coef, icpt if fit_intercept else None)
+    return fitted, stacked, (None if bad else stack)
+
+
+def assign_views(estimators: Sequence, stack: dict) -> None:
+    """Point the fitted attributes of the per-slice estimators at rows of the stacked arrays (a handful of unbind calls instead of
+    thousands of Python-level indexing operations)."""
+    kind, per_target, fit_intercept = stack['kind'], stack['per_target'], stack['fit_intercept']
+    coef_v, alpha_v, loss_v = stack['coef'].unbind(0), stack['alpha'].unbind(0), stack['loss'].unbind(0)
+    icpt_v = stack['icpt'][:, None, :].unbind(0) if fit_intercept else None
+    pattern_v = stack['pattern'].unbind(0) if stack['pattern'] is not None else None
+    for b, est in enumerate(estimators):
         inner = est.estimator if kind == 'decoder' else est
-        inner.alphas = al_o                                      # ridgecv.py:125
+        inner.alphas = stack['alphas']                           # ridgecv.py:125
         inner.coef_ = coef_v[b]
         inner.alpha_ = alpha_v[b]                                # (F,) per target, 0-d when shared
         inner.loss_ = loss_v[b]
@@ -106,12 +119,13 @@ def fit_slices(proto, Xm: torch.Tensor, ym: torch.Tensor, pairs: Sequence[Tuple[
         if kind == 'decoder':
             est.coef_, est.intercept_, est.alpha_ = inner.coef_, inner.intercept_, inner.alpha_
             est.pattern_ = pattern_v[b]
-        fitted.append(est)
-    for b in bad:                                                # rank-deficient / badly scaled slices: the guarded general route
-        fitted[b] = proto.clone().fit(Xm[..., xi[b]], ym[..., yi[b]])
-    # the stacked parameters stay with the caller so that predict needs no re-stacking (only when every slice came from here)
-    stacked = None if bad else (coef, icpt if fit_intercept else None)
-    return fitted, stacked
+
+
+def move_stack(estimators: Sequence, stack: dict, device: torch.device) -> dict:
+    """The per-slice estimators of a batched fit on another device: the stacked arrays move (one copy each), the views follow."""
+    new = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in stack.items()}
+    assign_views(estimators, new)
+    return new
 
 
 def stacked_parameters(estimators: Sequence) -> Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]]:

@@ -63,7 +63,18 @@ def _move_tensors(obj: Any, device: torch.device, _seen=None) -> Any:
         return obj
     if isinstance(obj, (sklearn.base.BaseEstimator, Metric)):
         stacked = getattr(obj, '_stacked', None)
+        stack_all = getattr(obj, '_stack_all', None)
+        if stack_all is not None and isinstance(getattr(obj, 'estimators_', None), list) and stack_all['coef'].device != device:
+            # a batched Sliding fit going to another device (host inputs): the stacked arrays move, one copy each, and the
+            # per-slice estimators are re-pointed at the moved rows -- instead of ~4 000 per-attribute moves per fold
+            from .. import _batched
+            obj._stack_all = _batched.move_stack(obj.estimators_, stack_all, device)
+            obj._stacked = None                                  # (the compute-device copy for predict is dropped with the move)
+            _seen['ids'].add(id(obj.estimators_))
+            stacked = None
         for k, v in list(vars(obj).items()):
+            if k == '_stack_all':
+                continue
             if k == 'estimators_' and stacked is not None and isinstance(v, list) and v and stacked[0].device == device \
                     and getattr(v[0], 'coef_', None) is not None and v[0].coef_.device == device:
                 continue        # a batched Sliding fit: hundreds of per-slice views of a few stacked arrays that already live on `device`

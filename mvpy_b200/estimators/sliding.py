@@ -28,6 +28,7 @@ class _Sliding_torch(sklearn.base.BaseEstimator):
         self.top = top
         self.estimators_ = None
         self._stacked = None
+        self._stack_all = None
 
     # (Folds of a batched Sliding fit do NOT take the Validator's stream lanes: measured at configs[4], 3 lanes 96 k fits/s against
     # 118 k serial -- the per-fold host work is Python under the GIL and the batched kernels already fill the GPU.)
@@ -59,11 +60,11 @@ class _Sliding_torch(sklearn.base.BaseEstimator):
             pairs = self._pairs(Xm, ym)
             # many small identical fits: one batched call for the whole stack (mvb_dense_ridge_batched); shapes it does not
             # take are captured once as a CUDA graph and replayed per slice on concurrent streams
-            fitted, self._stacked = None, None
+            fitted, self._stacked, self._stack_all = None, None, None
             if len(self.dims) == 1 and not args:
                 got = _batched.fit_slices(proto, Xm, ym, pairs)
                 if got is not None:
-                    fitted, self._stacked = got
+                    fitted, self._stacked, self._stack_all = got
                 else:
                     fitted = _graphs.fit_slices(proto, Xm, ym, pairs)
             self.estimators_ = fitted if fitted is not None else [proto.clone().fit(Xm[..., i], ym[..., j], *args) for i, j in pairs]
